@@ -1,0 +1,127 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY (see oracle/sw_oracle.c header).
+
+ctypes front-ends for
+  * liboracle.so          the C restatement of the reference's GPU extension path, and
+  * _ref/libgasal_ref*.so the reference's own kernel headers compiled for the host
+                          (oracle/ref_shim.cpp; built in the dev container from /root/reference).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+package.  The product package `rabbitsalign_b200` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@dataclass
+class PairResult:
+    """Mirror of `struct gasal_tmp_res` (reference src/gasal2_ssw.h:31-38)."""
+
+    score: int
+    query_start: int
+    query_end: int
+    ref_start: int
+    ref_end: int
+    cigar_str: str
+
+    def astuple(self):
+        return (self.score, self.query_start, self.query_end, self.ref_start, self.ref_end, self.cigar_str)
+
+
+def build(force: bool = False) -> None:
+    """Compile the checkers (oracle/Makefile).  _ref/ targets are only (re)built when
+    /root/reference is present; on the GPU box the prebuilt files that travelled are used."""
+    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def pack_strings(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenate byte strings -> (uint8 buffer, int64 offsets[n+1])."""
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    buf = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    if buf.size == 0:
+        buf = np.zeros(1, np.uint8)
+    return buf, off
+
+
+_BATCH_ARGS = [
+    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+    C.c_void_p,
+]
+
+
+class _BatchLib:
+    def __init__(self, path: str, symbol: str):
+        self.path = path
+        self.lib = C.CDLL(path)
+        self.fn = getattr(self.lib, symbol)
+        self.fn.argtypes = _BATCH_ARGS
+        self.fn.restype = C.c_int
+
+    def align_packed(self, qbuf, qoff, tbuf, toff, match=2, mismatch=8, gap_open=12, gap_extend=1):
+        """Same scoring convention as solve_ssw_on_gpu (gasal2_ssw.cpp:52-56): gap_open is the
+        strobealign value; GASAL gets gap_open-1."""
+        n = len(qoff) - 1
+        score = np.zeros(n, np.int32); qs = np.zeros(n, np.int32); qe = np.zeros(n, np.int32)
+        rs = np.zeros(n, np.int32); re = np.zeros(n, np.int32); nops = np.zeros(n, np.int32)
+        cap = int(4 * (qoff[-1] + toff[-1]) + 64 * n + 64)
+        pool = np.zeros(cap, np.uint8)
+        coff = np.zeros(n + 1, np.int64)
+        rc = self.fn(n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data, toff.ctypes.data,
+                     match, mismatch, gap_open - 1, gap_extend, score.ctypes.data, qs.ctypes.data,
+                     qe.ctypes.data, rs.ctypes.data, re.ctypes.data, nops.ctypes.data,
+                     pool.ctypes.data, cap, coff.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"{self.path}: batch call failed rc={rc}")
+        return score, qs, qe, rs, re, nops, pool, coff
+
+    def align(self, queries: Sequence[bytes], targets: Sequence[bytes], **kw) -> List[PairResult]:
+        qbuf, qoff = pack_strings(queries)
+        tbuf, toff = pack_strings(targets)
+        score, qs, qe, rs, re, nops, pool, coff = self.align_packed(qbuf, qoff, tbuf, toff, **kw)
+        raw = pool.tobytes()
+        return [PairResult(int(score[i]), int(qs[i]), int(qe[i]), int(rs[i]), int(re[i]),
+                           raw[coff[i]:coff[i + 1]].decode()) for i in range(len(queries))]
+
+
+_cache = {}
+
+
+def restatement() -> _BatchLib:
+    """The C restatement (sw_oracle.c)."""
+    if "o" not in _cache:
+        p = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(p):
+            build()
+        _cache["o"] = _BatchLib(p, "rsa_oracle_batch")
+    return _cache["o"]
+
+
+def reference(max_query_len: int = 500) -> Optional[_BatchLib]:
+    """The reference's own kernels compiled for the host, or None when _ref/ was not built."""
+    name = "libgasal_ref.so" if max_query_len == 500 else "libgasal_ref512.so"
+    if name not in _cache:
+        p = os.path.join(_HERE, "_ref", name)
+        _cache[name] = _BatchLib(p, "gasal_ref_batch") if os.path.exists(p) else None
+    return _cache[name]
+
+
+def gasal_fail(query: bytes, target: bytes, r: PairResult) -> bool:
+    """reference src/pc.cpp:466-478."""
+    lib = restatement().lib
+    lib.rsa_oracle_gasal_fail.argtypes = [C.c_int] * 7 + [C.c_char_p]
+    lib.rsa_oracle_gasal_fail.restype = C.c_int
+    return bool(lib.rsa_oracle_gasal_fail(len(query), len(target), r.score, r.query_start, r.query_end,
+                                          r.ref_start, r.ref_end, r.cigar_str.encode()))

@@ -1,0 +1,176 @@
+"""Synthetic (query, reference-window) pair workloads shaped like the ones the reference's pipeline
+hands to `solve_ssw_on_gpu` (reference src/pc.cpp:214-242 builds the extension windows:
+read + |ref_span - query_span| + up to 50 bases of flank on each side; src/pc.cpp:333-368 builds the
+mate-rescue windows).  Pure numpy; used by tests and bench.py.  SURVEY.md section 8(d) lists the shapes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_CODE = np.zeros(256, np.int64)
+_CODE[_ACGT] = np.arange(4)
+
+
+@dataclass
+class PairBatch:
+    """n pairs as concatenated ASCII plus int64 offsets (offsets[i]..offsets[i+1])."""
+
+    qbuf: np.ndarray
+    qoff: np.ndarray
+    tbuf: np.ndarray
+    toff: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return len(self.qoff) - 1
+
+    @property
+    def cells(self) -> int:
+        ql = np.diff(self.qoff)
+        tl = np.diff(self.toff)
+        return int(np.sum(ql * tl))
+
+    def queries(self) -> List[bytes]:
+        b = self.qbuf.tobytes()
+        return [b[self.qoff[i]:self.qoff[i + 1]] for i in range(self.n)]
+
+    def targets(self) -> List[bytes]:
+        b = self.tbuf.tobytes()
+        return [b[self.toff[i]:self.toff[i + 1]] for i in range(self.n)]
+
+    def slice(self, lo: int, hi: int) -> "PairBatch":
+        qo = self.qoff[lo:hi + 1]
+        to = self.toff[lo:hi + 1]
+        return PairBatch(self.qbuf[qo[0]:qo[-1]].copy(), (qo - qo[0]).copy(),
+                         self.tbuf[to[0]:to[-1]].copy(), (to - to[0]).copy())
+
+
+def from_lists(queries: List[bytes], targets: List[bytes]) -> PairBatch:
+    def pack(seqs):
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        if seqs:
+            off[1:] = np.cumsum([len(s) for s in seqs])
+        buf = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy()
+        return buf, off
+    qb, qo = pack(queries)
+    tb, to = pack(targets)
+    return PairBatch(qb, qo, tb, to)
+
+
+def _mutate(rng: np.random.Generator, seq: np.ndarray, sub_rate: float, indel_rate: float,
+            max_indel: int) -> np.ndarray:
+    """Apply substitutions and indel events to one read (small python loop over events only)."""
+    s = seq.copy()
+    if sub_rate > 0:
+        m = rng.random(len(s)) < sub_rate
+        k = int(m.sum())
+        if k:
+            # substitute with a different base
+            shift = rng.integers(1, 4, size=k)
+            s[m] = _ACGT[(_CODE[s[m]] + shift) % 4]
+    if indel_rate > 0:
+        n_ev = rng.binomial(len(s), indel_rate)
+        if n_ev:
+            pos = np.sort(rng.integers(1, max(2, len(s) - 1), size=n_ev))[::-1]
+            out = s.tolist()
+            for p in pos:
+                ln = int(rng.integers(1, max_indel + 1))
+                if rng.random() < 0.5:
+                    del out[p:p + ln]
+                else:
+                    out[p:p] = _ACGT[rng.integers(0, 4, size=ln)].tolist()
+            s = np.array(out, dtype=np.uint8)
+    return s
+
+
+def extension_pairs(n: int, read_len: int = 150, sub_rate: float = 0.01, indel_rate: float = 0.002,
+                    max_indel: int = 3, rescue_frac: float = 0.05, n_rate: float = 0.0,
+                    seed: int = 43, fixed_query_len: bool = True) -> PairBatch:
+    """Pairs distributed like the reference's todo lists (SURVEY.md 8a workload facts):
+    windows = read_len + diff + ext_left + ext_right with ext in [0, 50] (mostly 50), and a
+    `rescue_frac` share of mate-rescue windows (read_len + ~200..250)."""
+    rng = np.random.default_rng(seed)
+    qs: List[np.ndarray] = []
+    ts: List[np.ndarray] = []
+    for _ in range(n):
+        rescue = rng.random() < rescue_frac
+        if rescue:
+            left = int(rng.integers(0, 150))
+            right = int(rng.integers(50, 100))
+        else:
+            left = 50 if rng.random() < 0.9 else int(rng.integers(0, 50))
+            right = 50 if rng.random() < 0.9 else int(rng.integers(0, 50))
+        core = _ACGT[rng.integers(0, 4, size=read_len)]
+        read = _mutate(rng, core, sub_rate, indel_rate, max_indel)
+        if fixed_query_len:
+            # sequencers emit fixed-length reads: trim/extend to read_len
+            if len(read) >= read_len:
+                read = read[:read_len]
+            else:
+                read = np.concatenate([read, _ACGT[rng.integers(0, 4, size=read_len - len(read))]])
+        win = np.concatenate([_ACGT[rng.integers(0, 4, size=left)], core,
+                              _ACGT[rng.integers(0, 4, size=right)]])
+        if n_rate > 0:
+            m = rng.random(len(read)) < n_rate
+            read = read.copy()
+            read[m] = ord("N")
+        qs.append(read)
+        ts.append(win)
+    qoff = np.zeros(n + 1, np.int64); qoff[1:] = np.cumsum([len(x) for x in qs])
+    toff = np.zeros(n + 1, np.int64); toff[1:] = np.cumsum([len(x) for x in ts])
+    return PairBatch(np.concatenate(qs), qoff, np.concatenate(ts), toff)
+
+
+def fixed_pairs_fast(n: int, qlen: int = 150, tlen: int = 250, sub_rate: float = 0.01,
+                     seed: int = 43) -> PairBatch:
+    """Vectorised generator for the microbenchmark shape: fixed |q| x |t|,
+    substitutions only, read placed at a random offset of the window.  Scales to millions of pairs."""
+    rng = np.random.default_rng(seed)
+    t = _ACGT[rng.integers(0, 4, size=(n, tlen), dtype=np.uint8)]
+    start = rng.integers(0, tlen - qlen + 1, size=n)
+    idx = start[:, None] + np.arange(qlen)[None, :]
+    q = np.take_along_axis(t, idx, axis=1)
+    if sub_rate > 0:
+        m = rng.random((n, qlen)) < sub_rate
+        shift = rng.integers(1, 4, size=(n, qlen), dtype=np.uint8)
+        code = np.zeros(256, np.uint8)
+        code[_ACGT] = np.arange(4, dtype=np.uint8)
+        q = np.where(m, _ACGT[(code[q] + shift) % 4], q)
+    qoff = np.arange(n + 1, dtype=np.int64) * qlen
+    toff = np.arange(n + 1, dtype=np.int64) * tlen
+    return PairBatch(np.ascontiguousarray(q).reshape(-1), qoff, np.ascontiguousarray(t).reshape(-1), toff)
+
+
+def adversarial_pairs(n: int, seed: int = 7, max_q: int = 60, max_t: int = 90,
+                      alphabet: bytes = b"ACGTN") -> PairBatch:
+    """Short random pairs over small alphabets: dense in ties, zero scores, N cells and walks that
+    leave the matrix (SURVEY.md 8a rules 3-9)."""
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(alphabet, dtype=np.uint8)
+    qs, ts = [], []
+    for _ in range(n):
+        ql = int(rng.integers(1, max_q + 1))
+        tl = int(rng.integers(1, max_t + 1))
+        if rng.random() < 0.5 and tl >= 4:
+            t = alpha[rng.integers(0, len(alpha), size=tl)]
+            a = int(rng.integers(0, tl))
+            q = t[a:a + ql].copy()
+            if len(q) == 0:
+                q = alpha[rng.integers(0, len(alpha), size=1)]
+            m = rng.random(len(q)) < 0.15
+            q[m] = alpha[rng.integers(0, len(alpha), size=int(m.sum()))]
+            if rng.random() < 0.5 and len(q) > 4:
+                p = int(rng.integers(1, len(q) - 1))
+                q = np.delete(q, slice(p, p + int(rng.integers(1, 4))))
+        else:
+            q = alpha[rng.integers(0, len(alpha), size=ql)]
+            t = alpha[rng.integers(0, len(alpha), size=tl)]
+        qs.append(q.astype(np.uint8))
+        ts.append(t.astype(np.uint8))
+    qoff = np.zeros(n + 1, np.int64); qoff[1:] = np.cumsum([len(x) for x in qs])
+    toff = np.zeros(n + 1, np.int64); toff[1:] = np.cumsum([len(x) for x in ts])
+    return PairBatch(np.concatenate(qs), qoff, np.concatenate(ts), toff)
