@@ -1,0 +1,22 @@
+# Builds the product library (CUDA, sm_100a) and the checkers.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall
+CSRC := rabbitsalign_b200/csrc
+LIB  := rabbitsalign_b200/librsa_ext.so
+
+all: $(LIB) oracle
+
+$(LIB): $(CSRC)/engine.cu $(wildcard $(CSRC)/*.cuh) include/rsa_ext.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/engine.cu
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/engine.cu
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -f $(LIB)
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean ptxas-info

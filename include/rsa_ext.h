@@ -1,0 +1,138 @@
+/*
+ * rsa_ext.h -- C ABI of the B200-native extension engine (librsa_ext.so).
+ *
+ * Drop-in boundary for the one GPU hot path of RabbitSAlign: the batched affine-gap local
+ * Smith-Waterman + traceback + CIGAR step behind
+ *
+ *     void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res>&, std::vector<std::string>&,
+ *                           std::vector<std::string>&, int match, int mismatch, int gap_open,
+ *                           int gap_extend);                       (reference src/gasal2_ssw.h:46-47)
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference).
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return RSA_EXT_OK (0) or a
+ * negative status; rsa_ext_last_error() gives the text.  A handle is owned by one host thread at a
+ * time (the reference keeps one GASAL stream + storage per worker `thread_id`,
+ * src/gasal2_ssw.cpp:29,92-102); different handles are independent and may live on different GPUs.
+ *
+ * There is NO CPU fallback inside this library: without a usable CUDA device rsa_ext_create fails.
+ */
+#ifndef RSA_EXT_H
+#define RSA_EXT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSA_EXT_OK 0
+#define RSA_EXT_ERR_ARG -1      /* bad argument (NULL, n <= 0, offsets not monotone, ...) */
+#define RSA_EXT_ERR_CUDA -2     /* a CUDA call failed; the reference exit()s here (GASAL2/src/gasal.h:15-22) */
+#define RSA_EXT_ERR_QUERY_LEN -3 /* a query is longer than max_query_len; the reference prints and exit(0)s
+                                    (src/gasal2_ssw.cpp:84-87) */
+#define RSA_EXT_ERR_STATE -4    /* wait without submit, submit while a batch is pending, ... */
+
+#define RSA_EXT_RLE_INLINE 40   /* RLE bytes carried inside each result record */
+
+typedef struct rsa_ext rsa_ext_t;
+
+/* Replaces the compile-time knobs of src/gasal2_ssw.h:15-25 (MAX_QUERY_LEN 500, MAX_TARGET_LEN 2000,
+ * STREAM_BATCH_SIZE 512 -- batches here may have any n >= 1) and the `Parameters` fake argv of
+ * src/gasal2_ssw.cpp:37-44 plus gasal_copy_subst_scores (GASAL2/src/gasal_align.cu:329-339).
+ * Scores are the strobealign values (src/cmdline.hpp:46-50: A=2 B=8 O=12 E=1); like
+ * src/gasal2_ssw.cpp:52-56 the engine opens a gap with gap_open-1+gap_extend and extends with
+ * gap_extend.  Scores are per handle, not global __constant__ state. */
+typedef struct {
+    int32_t device;         /* CUDA ordinal; the reference never calls cudaSetDevice (gasal2_ssw.cpp:34) */
+    int32_t max_query_len;  /* 0 -> 500 */
+    int32_t max_target_len; /* 0 -> 2000; longer windows get a failed record (score 0, n_ops 0), the
+                               caller never consumes those (src/aligner.cpp:18-24) */
+    int32_t match, mismatch, gap_open, gap_extend; /* all 0 -> 2, 8, 12, 1 */
+    int32_t flags;          /* RSA_EXT_FLAG_* */
+    int64_t scratch_bytes;  /* direction-bit scratch per handle; 0 -> default */
+} rsa_ext_config_t;
+
+#define RSA_EXT_FLAG_EXACT_ONLY 1 /* route every pair through the exact int32 kernel (testing) */
+
+/* One result per pair: the integer fields of `struct gasal_tmp_res` (src/gasal2_ssw.h:31-38; starts and
+ * ends 0-based inclusive, starts may be -1) plus the traceback's run-length bytes exactly as
+ * GASAL2/src/kernels/get_tb.h:87-117 emits them: (count<<2)|op, count <= 63, op 0=M 1=X 2=D 3=I, in
+ * END-TO-START order.  n_ops > RSA_EXT_RLE_INLINE: the full byte string is fetched with
+ * rsa_ext_rle_overflow().  status: 0 ok, 1 window longer than max_target_len (not aligned). */
+typedef struct {
+    int32_t score;
+    int32_t query_start;
+    int32_t query_end;
+    int32_t ref_start;
+    int32_t ref_end;
+    int16_t n_ops;
+    int16_t status;
+    uint8_t rle[RSA_EXT_RLE_INLINE];
+} rsa_ext_result_t; /* 64 bytes */
+
+/* gasal_init_gpu_storage_v + gasal_init_streams (GASAL2/src/ctors.cpp:26-128; call site
+ * src/gasal2_ssw.cpp:92-102).  Storage grows on demand and is freed by rsa_ext_destroy (the reference
+ * never frees: gasal2_ssw.cpp:252-255). */
+int rsa_ext_create(const rsa_ext_config_t *cfg, rsa_ext_t **out);
+void rsa_ext_destroy(rsa_ext_t *h);
+const char *rsa_ext_last_error(const rsa_ext_t *h); /* h may be NULL: error of the last failed create */
+
+/* gasal_host_batch_fill x 2n + gasal_op_fill + gasal_aln_async (src/gasal2_ssw.cpp:114-153,
+ * GASAL2/src/host_batch.cpp:79-153, GASAL2/src/gasal_align.cu:29-307).  Asynchronous: returns once the
+ * copies and kernels are enqueued.  Pair i is qbuf[qoff[i] .. qoff[i+1]) against tbuf[toff[i] ..
+ * toff[i+1]) (raw ASCII, any case; bases are compared on `byte & 0xF` with 0xE as the zero-scoring
+ * wildcard, GASAL2/src/kernels/pack_rc_seqs.h:13-53, gasal_kernels.h:48-51).  Buffers must stay valid
+ * until rsa_ext_wait returns; pinned buffers are copied without staging. */
+int rsa_ext_submit(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff, const char *tbuf,
+                   const int64_t *toff, rsa_ext_result_t *results);
+
+/* Same, from n separate strings (the shape of std::vector<std::string>). */
+int rsa_ext_submit_ptrs(rsa_ext_t *h, int64_t n, const char *const *q, const int32_t *qlen,
+                        const char *const *t, const int32_t *tlen, rsa_ext_result_t *results);
+
+/* gasal_is_aln_async_done (GASAL2/src/gasal_align.cu:310-326): 0 = finished, 1 = still running. */
+int rsa_ext_poll(rsa_ext_t *h);
+
+/* The poll/usleep loop and result unpacking of src/gasal2_ssw.cpp:179-249: blocks until `results`
+ * (given to submit) is filled. */
+int rsa_ext_wait(rsa_ext_t *h);
+
+/* Full RLE byte string of pair i of the last waited batch when n_ops > RSA_EXT_RLE_INLINE.
+ * Returns the number of bytes written (<= cap) or a negative status. */
+int rsa_ext_rle_overflow(rsa_ext_t *h, int64_t i, uint8_t *out, int32_t cap);
+
+/* Host CIGAR text of src/gasal2_ssw.cpp:184-243 from RLE bytes: read last-to-first, merge equal
+ * neighbours, "<count><M|X|D|I>".  Returns text length (no NUL counted) or -1 if cap is too small. */
+int rsa_ext_rle_to_text(const uint8_t *rle, int32_t n_ops, char *out, int32_t cap);
+
+/* ---- device-resident legs (bench.py `value`, roofline): inputs already in HBM ---------------- */
+
+/* Upload + plan a batch once; afterwards rsa_ext_run_resident() re-runs only the GPU kernels on the
+ * handle's stream (no host<->device traffic) and rsa_ext_fetch_resident() copies the records out. */
+int rsa_ext_stage_resident(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff,
+                           const char *tbuf, const int64_t *toff);
+int rsa_ext_run_resident(rsa_ext_t *h);
+int rsa_ext_fetch_resident(rsa_ext_t *h, rsa_ext_result_t *results);
+
+/* The handle's CUDA stream (cudaStream_t as void*) so callers can bracket launches with events. */
+void *rsa_ext_stream(rsa_ext_t *h);
+
+/* Counters of the last submit/run: kernels launched, pairs taken by each kernel family, DP cells. */
+typedef struct {
+    int64_t kernel_launches;
+    int64_t pairs_fast;   /* packed s16x2 DPX kernel */
+    int64_t pairs_exact;  /* int32 exact kernel (odd nibbles, ties, tiny/huge shapes) */
+    int64_t pairs_failed; /* status != 0 */
+    int64_t cells;        /* sum |q|*|t| */
+    int64_t h2d_bytes, d2h_bytes;
+    double dp_ms;         /* device time of the DP kernels of the last run_resident (CUDA events) */
+    double tb_ms;         /* device time of the traceback kernels */
+} rsa_ext_stats_t;
+int rsa_ext_get_stats(const rsa_ext_t *h, rsa_ext_stats_t *out);
+
+int rsa_ext_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSA_EXT_H */

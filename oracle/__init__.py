@@ -125,3 +125,74 @@ def gasal_fail(query: bytes, target: bytes, r: PairResult) -> bool:
     lib.rsa_oracle_gasal_fail.restype = C.c_int
     return bool(lib.rsa_oracle_gasal_fail(len(query), len(target), r.score, r.query_start, r.query_end,
                                           r.ref_start, r.ref_end, r.cigar_str.encode()))
+
+
+class SswReference:
+    """The reference's CPU extension path (Aligner::align, reference src/aligner.cpp:114-210) compiled from
+    /root/reference into oracle/_ref/libssw_ref_*.so.  Timing baseline for bench.py; None if not built."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.lib = C.CDLL(path)
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+        self.lib.ssw_ref_align_batch.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                                 vp, vp, vp, vp, vp, vp, vp, i32]
+        self.lib.ssw_ref_align_batch.restype = i32
+        self.lib.ssw_ref_align_gpu_batch.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                                     vp, vp, vp, vp, vp, vp, vp,
+                                                     vp, vp, vp, vp, vp, vp, vp, i32]
+        self.lib.ssw_ref_align_gpu_batch.restype = i32
+
+    def align_packed(self, qbuf, qoff, tbuf, toff, threads=1, match=2, mismatch=8, gap_open=12, gap_extend=1,
+                     end_bonus=10, want_cigar=False):
+        n = len(qoff) - 1
+        out = {k: np.zeros(n, np.int32) for k in ("score", "qs", "qe", "rs", "re", "ed")}
+        slot = 1024 if want_cigar else 0
+        pool = np.zeros(n * slot, np.uint8) if want_cigar else None
+        rc = self.lib.ssw_ref_align_batch(n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data, toff.ctypes.data,
+                                          match, mismatch, gap_open, gap_extend, end_bonus, threads,
+                                          out["score"].ctypes.data, out["qs"].ctypes.data, out["qe"].ctypes.data,
+                                          out["rs"].ctypes.data, out["re"].ctypes.data, out["ed"].ctypes.data,
+                                          pool.ctypes.data if want_cigar else None, slot)
+        if rc != 0:
+            raise RuntimeError("ssw_ref_align_batch failed")
+        if want_cigar:
+            raw = pool.tobytes()
+            out["cigar"] = [raw[i * slot:(i + 1) * slot].split(b"\0", 1)[0].decode() for i in range(n)]
+        return out
+
+    def align_gpu_packed(self, qbuf, qoff, tbuf, toff, g, match=2, mismatch=8, gap_open=12, gap_extend=1,
+                         end_bonus=10):
+        """Aligner::align_gpu (reference src/aligner.cpp:13-112) on GPU-path records `g` (dict with int32
+        arrays score/qs/qe/rs/re and a list of CIGAR strings)."""
+        n = len(qoff) - 1
+        gp, go = pack_strings([c.encode() for c in g["cigar"]])
+        out = {k: np.zeros(n, np.int32) for k in ("score", "qs", "qe", "rs", "re", "ed")}
+        slot = 1024
+        pool = np.zeros(n * slot, np.uint8)
+        a = {k: np.ascontiguousarray(g[k], dtype=np.int32) for k in ("score", "qs", "qe", "rs", "re")}
+        rc = self.lib.ssw_ref_align_gpu_batch(n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data,
+                                              toff.ctypes.data, match, mismatch, gap_open, gap_extend, end_bonus,
+                                              a["score"].ctypes.data, a["qs"].ctypes.data, a["qe"].ctypes.data,
+                                              a["rs"].ctypes.data, a["re"].ctypes.data, gp.ctypes.data, go.ctypes.data,
+                                              out["score"].ctypes.data, out["qs"].ctypes.data, out["qe"].ctypes.data,
+                                              out["rs"].ctypes.data, out["re"].ctypes.data, out["ed"].ctypes.data,
+                                              pool.ctypes.data, slot)
+        if rc != 0:
+            raise RuntimeError("ssw_ref_align_gpu_batch failed")
+        raw = pool.tobytes()
+        out["cigar"] = [raw[i * slot:(i + 1) * slot].split(b"\0", 1)[0].decode() for i in range(n)]
+        return out
+
+
+def ssw_reference() -> Optional[SswReference]:
+    if "ssw" not in _cache:
+        flags = ""
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            pass
+        v = "v3" if (" avx2" in flags and " bmi2" in flags and " fma" in flags) else "v2"
+        p = os.path.join(_HERE, "_ref", f"libssw_ref_{v}.so")
+        _cache["ssw"] = SswReference(p) if os.path.exists(p) else None
+    return _cache["ssw"]

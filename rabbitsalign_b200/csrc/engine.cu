@@ -1,0 +1,874 @@
+// engine.cu -- host side of librsa_ext.so: the C ABI of include/rsa_ext.h.
+//
+// Replaces, for RabbitSAlign's extension step, the GASAL2 host runtime the reference drives from
+// src/gasal2_ssw.cpp:19-256: storage/stream construction (GASAL2/src/ctors.cpp:26-128), pinned batch
+// filling (GASAL2/src/host_batch.cpp:79-153), the launch path gasal_aln_async
+// (GASAL2/src/gasal_align.cu:29-307) and completion polling (:310-326).
+//
+// Shape of the engine (B200-first, not GASAL2's):
+//   * a batch of any size is cut into chunks whose direction-bit scratch fits the handle's budget;
+//   * two chunk slots are double-buffered over three streams (H2D, compute, D2H) so the copies of chunk
+//     k+1 overlap the kernels of chunk k; per chunk there is ONE metadata blob copy, two sequence copies
+//     in and one 64-byte-record copy out (the reference issues ~13 small copies per 512 pairs);
+//   * the host plans each chunk (length classes, equal-length pairing for the packed kernel, scratch
+//     offsets) while the GPU works on the previous one;
+//   * kernels: packed s16x2 DPX wavefront kernel (kernels_fast.cuh) for the bulk, exact int32 wavefront
+//     kernel (kernels_exact.cuh) for whatever the packed kernel declines, one traceback kernel
+//     (kernels_tb.cuh).  No CPU fallback exists here.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "fast_layout.cuh"
+#include "kernels_exact.cuh"
+#include "kernels_fast.cuh"
+#include "kernels_tb.cuh"
+
+using namespace rsa;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kSlots = 2;
+constexpr int64_t kMaxChunkPairs = 1 << 17;
+constexpr int64_t kMaxChunkSeqBytes = (int64_t)1 << 30;
+constexpr int64_t kDefaultScratch = (int64_t)8 << 30;  // both slots together
+constexpr int kMaxTargetLenCap = 8192;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+};
+struct PinBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+};
+
+// Host-side description of one planned chunk: where each section lives inside the metadata blob and how
+// many tasks each kernel gets.
+struct ChunkPlan {
+    int64_t lo = 0, hi = 0;  // pair range of the batch
+    int64_t n = 0;
+    size_t off_meta = 0, off_info = 0, off_diroff = 0, off_list = 0, off_groups = 0, off_redo = 0, blob_bytes = 0;
+    int n_exact[3] = {0, 0, 0};     // tasks per exact class (C = 4, 8, 16), consecutive in `list`
+    int max_tlen_exact[3] = {0, 0, 0};
+    int n_fast_classes = 0;
+    struct FastClass { int C; int group_begin; int n_groups; int max_tlen; };
+    std::vector<FastClass> fast;
+    int64_t n_fast_pairs = 0;
+    int64_t n_failed = 0;
+    uint64_t scratch_bytes = 0;
+    uint64_t arena_bytes = 0;
+    int64_t q_bytes = 0, t_bytes = 0;
+    int64_t cells = 0;
+};
+
+struct Slot {
+    PinBuf h_blob;
+    unsigned long long* h_arena_used = nullptr;  // pinned; [0] arena bytes used, [1] pairs the redo pass could not place
+    DevBuf d_blob, d_q, d_t, d_ends, d_res, d_scratch, d_arena;
+    unsigned long long* d_arena_used = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    ChunkPlan plan;
+    bool busy = false;
+};
+
+struct ResidentChunk {
+    ChunkPlan plan;
+    uint8_t* d_blob = nullptr;
+    size_t q_base = 0, t_base = 0;  // byte offsets into the resident sequence buffers
+};
+
+}  // namespace
+
+struct rsa_ext {
+    rsa_ext_config_t cfg{};
+    Scoring sc{};
+    FastConsts fk{};
+    bool fast_ok = false;
+    int n_sms = 148;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    Slot slots[kSlots];
+    size_t scratch_per_slot = 0;
+
+    // pending batch
+    bool pending = false;
+    int64_t n = 0;
+    const char* qbuf = nullptr;
+    const char* tbuf = nullptr;
+    const int64_t* qoff = nullptr;
+    const int64_t* toff = nullptr;
+    rsa_ext_result_t* results = nullptr;
+    int64_t next_pair = 0;
+    int head = 0, tail = 0, inflight = 0;
+    std::unordered_map<int64_t, std::vector<uint8_t>> overflow;
+    std::vector<int64_t> retry;  // pairs whose redo found no scratch (status 4): re-run exact-only at wait()
+
+    // submit_ptrs staging
+    PinBuf own_q, own_t;
+    std::vector<int64_t> own_qoff, own_toff;
+
+    // resident set
+    std::vector<ResidentChunk> res_chunks;
+    DevBuf r_q, r_t, r_res, r_blobs;
+    int64_t r_n = 0;
+    std::vector<cudaEvent_t> r_events;  // 3 per chunk: before DP, after DP, after TB
+    bool r_events_valid = false;
+
+    rsa_ext_stats_t stats{};
+    std::string err;
+    std::vector<uint32_t> tmp_list[3];
+    std::vector<uint32_t> tmp_sort, tmp_order;
+    std::vector<uint32_t> tmp_count;
+};
+
+namespace {
+
+#define CU_TRY(h, call)                                                                               \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return RSA_EXT_ERR_CUDA;                                                                  \
+        }                                                                                             \
+    } while (0)
+
+int ensure_dev(rsa_ext* h, DevBuf& b, size_t need) {
+    if (need <= b.cap) return RSA_EXT_OK;
+    size_t cap = std::max(need, b.cap + b.cap / 2);
+    cap = align_up(cap, 1 << 20);
+    if (b.p) CU_TRY(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CU_TRY(h, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return RSA_EXT_OK;
+}
+
+int ensure_pin(rsa_ext* h, PinBuf& b, size_t need) {
+    if (need <= b.cap) return RSA_EXT_OK;
+    size_t cap = std::max(need, b.cap + b.cap / 2);
+    cap = align_up(cap, 1 << 16);
+    if (b.p) CU_TRY(h, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CU_TRY(h, cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+    b.cap = cap;
+    return RSA_EXT_OK;
+}
+
+// ---- planning -------------------------------------------------------------------------------------
+//
+// Decide, for the pairs [lo, ...) of the pending batch, how many fit one chunk and lay out the metadata
+// blob in `blob` (host memory, grown as needed through `grow`).  Pure host code: unit-tested without a GPU
+// through rsa_ext_plan_debug().
+struct PlanInput {
+    int64_t n;
+    const int64_t* qoff;
+    const int64_t* toff;
+    const char* qbuf;
+    const char* tbuf;
+    int max_qlen, max_tlen;
+    size_t scratch_cap;
+    bool exact_only;
+};
+
+// A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
+inline bool fast_shape_ok(int qlen, int tlen) {
+    return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen;
+}
+
+int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std::vector<uint8_t>* vec_blob,
+               PinBuf* pin_blob) {
+    // 1) how many pairs: stop at the pair/sequence-byte caps or when the scratch budget is reached.
+    //    Scratch is budgeted with the larger of the two layouts' needs so any routing fits.
+    int64_t hi = lo;
+    uint64_t scratch = 0;
+    const int64_t q0 = in.qoff[lo], t0 = in.toff[lo];
+    while (hi < in.n && hi - lo < kMaxChunkPairs) {
+        const int64_t ql = in.qoff[hi + 1] - in.qoff[hi], tl = in.toff[hi + 1] - in.toff[hi];
+        if (ql < 0 || tl < 0) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
+        if (ql > in.max_qlen) {
+            h->err = "read size is too big, " + std::to_string(ql) + " > " + std::to_string(in.max_qlen);
+            return RSA_EXT_ERR_QUERY_LEN;
+        }
+        uint64_t need = 0;
+        if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
+            const uint64_t ex = align_up((size_t)tl * exact_row_bytes((int)ql), 16);
+            need = ex;
+            if (fast_shape_ok((int)ql, (int)tl)) {
+                const FastGeom g = fast_geom((int)ql);
+                need = std::max<uint64_t>(ex, fast_dir_bytes(g, (int)tl));  // a lone pair owns a whole group
+            }
+        }
+        if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
+                        in.toff[hi + 1] - t0 > kMaxChunkSeqBytes))
+            break;
+        scratch += need;
+        ++hi;
+    }
+    const int64_t n = hi - lo;
+    plan = ChunkPlan();
+    plan.lo = lo; plan.hi = hi; plan.n = n;
+    plan.q_bytes = in.qoff[hi] - q0;
+    plan.t_bytes = in.toff[hi] - t0;
+
+    // 2) blob layout
+    size_t off = 0;
+    plan.off_meta = off;   off = align_up(off + sizeof(PairMeta) * n, 16);
+    plan.off_info = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
+    plan.off_diroff = off; off = align_up(off + sizeof(uint64_t) * n, 16);
+    plan.off_list = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
+    plan.off_groups = off; off = align_up(off + sizeof(FastGroup) * (size_t)(n + 8 * 64), 16);
+    plan.off_redo = off;   off = align_up(off + sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4), 16);
+    plan.blob_bytes = off;
+    uint8_t* blob;
+    if (vec_blob) { vec_blob->assign(off, 0); blob = vec_blob->data(); }
+    else {
+        int rc = ensure_pin(h, *pin_blob, off);
+        if (rc) return rc;
+        blob = pin_blob->p;
+    }
+    PairMeta* meta = reinterpret_cast<PairMeta*>(blob + plan.off_meta);
+    uint32_t* info = reinterpret_cast<uint32_t*>(blob + plan.off_info);
+    uint64_t* diroff = reinterpret_cast<uint64_t*>(blob + plan.off_diroff);
+    uint32_t* list = reinterpret_cast<uint32_t*>(blob + plan.off_list);
+    FastGroup* groups = reinterpret_cast<FastGroup*>(blob + plan.off_groups);
+    memset(blob + plan.off_redo, 0, sizeof(RedoHeader));
+
+    for (int k = 0; k < 3; ++k) h->tmp_list[k].clear();
+    h->tmp_sort.clear();
+    uint64_t arena = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t ql = in.qoff[lo + i + 1] - in.qoff[lo + i], tl = in.toff[lo + i + 1] - in.toff[lo + i];
+        meta[i].qoff = (uint32_t)(in.qoff[lo + i] - q0);
+        meta[i].toff = (uint32_t)(in.toff[lo + i] - t0);
+        meta[i].qlen = (uint16_t)ql;
+        meta[i].tlen = (uint16_t)std::min<int64_t>(tl, 65535);
+        info[i] = 0;
+        diroff[i] = 0;
+        plan.cells += ql * tl;
+        if (ql == 0 || tl == 0) { info[i] = 3u << 16; plan.n_failed++; continue; }
+        if (tl > in.max_tlen) { info[i] = 1u << 16; plan.n_failed++; continue; }
+        arena += (uint64_t)(ql + tl + 1);
+        if (!in.exact_only && fast_shape_ok((int)ql, (int)tl)) h->tmp_sort.push_back((uint32_t)i);
+        else h->tmp_list[exact_class_cols((int)ql) == 4 ? 0 : (exact_class_cols((int)ql) == 8 ? 1 : 2)].push_back((uint32_t)i);
+    }
+    plan.arena_bytes = arena + 64;
+
+    // 3) packed-kernel groups: counting sort of the candidates by (qlen, tlen), then consecutive equal-qlen
+    //    pairs share a group (A = low halves, B = high halves); an odd one out runs with B = A.
+    uint64_t sc_off = 0;
+    int n_groups = 0;
+    plan.fast.clear();
+    if (!h->tmp_sort.empty()) {
+        const size_t m = h->tmp_sort.size();
+        // key = qlen * (kFastMaxTlen+1) + tlen, two-pass LSD counting sort (tlen then qlen)
+        h->tmp_order.resize(m);
+        {
+            std::vector<uint32_t>& cnt = h->tmp_count;
+            cnt.assign(kFastMaxTlen + 2, 0);
+            for (size_t k = 0; k < m; ++k) cnt[meta[h->tmp_sort[k]].tlen + 1]++;
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            for (size_t k = 0; k < m; ++k) h->tmp_order[cnt[meta[h->tmp_sort[k]].tlen]++] = h->tmp_sort[k];
+            cnt.assign(kFastMaxQlen + 2, 0);
+            for (size_t k = 0; k < m; ++k) cnt[meta[h->tmp_order[k]].qlen + 1]++;
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            for (size_t k = 0; k < m; ++k) h->tmp_sort[cnt[meta[h->tmp_order[k]].qlen]++] = h->tmp_order[k];
+        }
+        size_t k = 0;
+        int cur_C = -1;
+        while (k < m) {
+            const uint32_t a = h->tmp_sort[k];
+            const int ql = meta[a].qlen;
+            uint32_t b = a;
+            if (k + 1 < m && meta[h->tmp_sort[k + 1]].qlen == ql) { b = h->tmp_sort[k + 1]; k += 2; }
+            else k += 1;
+            const FastGeom g = fast_geom(ql);
+            if (g.C != cur_C) {
+                // close the previous class on a warp boundary (4 groups per warp) with empty groups
+                while (n_groups % kFastGroupsPerWarp) { groups[n_groups] = FastGroup{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0}; n_groups++; }
+                if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
+                plan.fast.push_back({g.C, n_groups, 0, 0});
+                cur_C = g.C;
+            }
+            const int rows = std::max<int>(meta[a].tlen, meta[b].tlen);
+            FastGroup fg;
+            fg.a = a; fg.b = b;
+            fg.dir_off = sc_off;
+            fg.qlen = (uint16_t)ql;
+            fg.rows = (uint16_t)rows;
+            groups[n_groups++] = fg;
+            diroff[a] = sc_off; info[a] |= 0u;
+            if (b != a) { diroff[b] = sc_off; info[b] |= 1u; }
+            sc_off += align_up(fast_dir_bytes(g, rows), 16);
+            plan.fast.back().max_tlen = std::max(plan.fast.back().max_tlen, rows);
+            plan.n_fast_pairs += (b != a) ? 2 : 1;
+        }
+        while (n_groups % kFastGroupsPerWarp) { groups[n_groups] = FastGroup{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0}; n_groups++; }
+        plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
+    }
+    plan.n_fast_classes = (int)plan.fast.size();
+
+    // 4) exact-kernel lists.  Pairs the packed kernel declines at run time are re-run by the exact kernel in
+    //    a second pass over the same scratch region of that pair (the fast layout of a lone pair is at
+    //    least as large, see the budget above), so only the statically exact pairs get fresh offsets here.
+    uint32_t pos = 0;
+    for (int c = 0; c < 3; ++c) {
+        plan.n_exact[c] = (int)h->tmp_list[c].size();
+        for (uint32_t i : h->tmp_list[c]) {
+            list[pos++] = i;
+            diroff[i] = sc_off;
+            sc_off += align_up((size_t)meta[i].tlen * exact_row_bytes(meta[i].qlen), 16);
+            plan.max_tlen_exact[c] = std::max<int>(plan.max_tlen_exact[c], meta[i].tlen);
+        }
+    }
+    plan.scratch_bytes = sc_off;
+    return RSA_EXT_OK;
+}
+
+// planned tiles + head-room for pairs the redo pass re-tiles (symbols outside ACGTN)
+inline size_t scratch_alloc_bytes(uint64_t planned) { return (size_t)align_up((size_t)planned, 256) + std::max<size_t>((size_t)16 << 20, (size_t)planned / 16); }
+
+// ---- launching -------------------------------------------------------------------------------------
+
+struct ChunkDev {
+    const uint8_t* blob;
+    const uint8_t* q;
+    const uint8_t* t;
+    DpEnd* ends;
+    rsa_ext_result_t* res;
+    uint8_t* scratch;
+    uint64_t scratch_cap;
+    uint8_t* arena;
+    unsigned long long* arena_used;
+    uint64_t arena_cap;
+};
+
+template <int C>
+void launch_exact(cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, int list_begin, int n_list, int max_tlen,
+                  const Scoring& sc) {
+    const int tlen_pad = (int)align_up((size_t)max_tlen, 16);
+    const int blocks = (n_list + kExactWarpsPerBlock - 1) / kExactWarpsPerBlock;
+    exact_dp_kernel<C><<<blocks, 32 * kExactWarpsPerBlock, (size_t)tlen_pad * kExactWarpsPerBlock, st>>>(
+        d.q, d.t, reinterpret_cast<const PairMeta*>(d.blob + p.off_meta),
+        reinterpret_cast<const uint32_t*>(d.blob + p.off_list) + list_begin, n_list,
+        reinterpret_cast<const uint64_t*>(d.blob + p.off_diroff), d.scratch, d.ends, sc, tlen_pad);
+}
+
+// Enqueue every kernel of one chunk on `st`.  ev[0..2], when given, bracket the DP and traceback phases.
+int enqueue_compute(rsa_ext* h, cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, cudaEvent_t* ev) {
+    CU_TRY(h, cudaMemsetAsync(d.ends, 0, sizeof(DpEnd) * p.n, st));
+    CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, 2 * sizeof(unsigned long long), st));
+    if (ev) CU_TRY(h, cudaEventRecord(ev[0], st));
+    const PairMeta* meta = reinterpret_cast<const PairMeta*>(d.blob + p.off_meta);
+    const uint32_t* info = reinterpret_cast<const uint32_t*>(d.blob + p.off_info);
+    uint64_t* diroff = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(d.blob) + p.off_diroff);
+    RedoHeader* redo = reinterpret_cast<RedoHeader*>(const_cast<uint8_t*>(d.blob) + p.off_redo);
+    uint32_t* redo_list = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(d.blob) + p.off_redo + sizeof(RedoHeader));
+    // packed kernel, one launch per column class
+    for (const auto& fc : p.fast) {
+        int rc = launch_fast_class(st, fc.C, d.q, d.t, meta,
+                                   reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
+                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen);
+        if (rc != 0) { h->err = "no packed-kernel instance for C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
+        h->stats.kernel_launches++;
+    }
+    // exact kernel: statically routed pairs
+    int begin = 0;
+    for (int c = 0; c < 3; ++c) {
+        const int nl = p.n_exact[c];
+        if (nl > 0) {
+            if (c == 0) launch_exact<4>(st, d, p, begin, nl, p.max_tlen_exact[c], h->sc);
+            else if (c == 1) launch_exact<8>(st, d, p, begin, nl, p.max_tlen_exact[c], h->sc);
+            else launch_exact<16>(st, d, p, begin, nl, p.max_tlen_exact[c], h->sc);
+            h->stats.kernel_launches++;
+        }
+        begin += nl;
+    }
+    // pairs the packed kernel declined: one warp-per-pair exact pass driven by the DPF_NEED_EXACT flags
+    if (!p.fast.empty()) {
+        int max_tlen = 0;
+        for (const auto& fc : p.fast) max_tlen = std::max(max_tlen, fc.max_tlen);
+        const unsigned long long redo_base = align_up((size_t)p.scratch_bytes, 256);
+        const unsigned long long redo_cap = d.scratch_cap > redo_base ? d.scratch_cap - redo_base : 0ull;
+        launch_exact_redo(st, d.q, d.t, meta, diroff, d.scratch, d.ends, redo, redo_list, h->sc, max_tlen, h->n_sms,
+                          redo_base, redo_cap, d.arena_used);
+        h->stats.kernel_launches++;
+    }
+    if (ev) CU_TRY(h, cudaEventRecord(ev[1], st));
+    tb_kernel<<<(unsigned)((p.n + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st>>>(
+        d.q, d.t, meta, info, (int)p.n, diroff, d.scratch, d.ends, d.res, h->sc, d.arena, d.arena_used, d.arena_cap);
+    h->stats.kernel_launches++;
+    if (ev) CU_TRY(h, cudaEventRecord(ev[2], st));
+    CU_TRY(h, cudaGetLastError());
+    return RSA_EXT_OK;
+}
+
+int enqueue_chunk(rsa_ext* h, Slot& s) {
+    PlanInput in{h->n, h->qoff, h->toff, h->qbuf, h->tbuf, h->cfg.max_query_len, h->cfg.max_target_len,
+                 h->scratch_per_slot, (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
+    int rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
+    if (rc) return rc;
+    const ChunkPlan& p = s.plan;
+    if ((rc = ensure_dev(h, s.d_blob, p.blob_bytes))) return rc;
+    if ((rc = ensure_dev(h, s.d_q, (size_t)p.q_bytes + 16))) return rc;
+    if ((rc = ensure_dev(h, s.d_t, (size_t)p.t_bytes + 16))) return rc;
+    if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * p.n))) return rc;
+    if ((rc = ensure_dev(h, s.d_res, sizeof(rsa_ext_result_t) * p.n))) return rc;
+    if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(p.scratch_bytes)))) return rc;
+    if ((rc = ensure_dev(h, s.d_arena, (size_t)p.arena_bytes))) return rc;
+
+    CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, s.h_blob.p, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    if (p.q_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_q.p, h->qbuf + h->qoff[p.lo], (size_t)p.q_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
+    h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
+
+    CU_TRY(h, cudaStreamWaitEvent(h->s_comp, s.ev_h2d, 0));
+    ChunkDev d{s.d_blob.p, s.d_q.p, s.d_t.p, reinterpret_cast<DpEnd*>(s.d_ends.p),
+               reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
+               s.d_arena_used, (uint64_t)s.d_arena.cap};
+    if ((rc = enqueue_compute(h, h->s_comp, d, p, nullptr))) return rc;
+    CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_comp));
+
+    CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
+    CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(h, cudaEventRecord(s.ev_d2h, h->s_d2h));
+    h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_result_t) * p.n + 8;
+
+    h->stats.pairs_fast += p.n_fast_pairs;
+    h->stats.pairs_exact += p.n_exact[0] + p.n_exact[1] + p.n_exact[2];
+    h->stats.pairs_failed += p.n_failed;
+    h->stats.cells += p.cells;
+    s.busy = true;
+    h->next_pair = p.hi;
+    h->inflight++;
+    return RSA_EXT_OK;
+}
+
+// After a chunk's D2H finished: pull the long-CIGAR arena (rare) and file the byte strings by pair index.
+int retire_chunk(rsa_ext* h, Slot& s) {
+    CU_TRY(h, cudaEventSynchronize(s.ev_d2h));
+    const unsigned long long used = *s.h_arena_used;
+    if (used > 0) {
+        std::vector<uint8_t> host(used);
+        CU_TRY(h, cudaMemcpy(host.data(), s.d_arena.p, used, cudaMemcpyDeviceToHost));
+        for (int64_t i = s.plan.lo; i < s.plan.hi; ++i) {
+            const rsa_ext_result_t& r = h->results[i];
+            if (r.n_ops > RSA_EXT_RLE_INLINE && r.status == 0) {
+                unsigned long long off;
+                memcpy(&off, &r.rle[RSA_EXT_RLE_INLINE - 8], 8);
+                if (off + (unsigned long long)r.n_ops <= used)
+                    h->overflow[i] = std::vector<uint8_t>(host.begin() + off, host.begin() + off + r.n_ops);
+            }
+        }
+    }
+    if (s.h_arena_used[1] > 0)
+        for (int64_t i = s.plan.lo; i < s.plan.hi; ++i)
+            if (h->results[i].status == 4) h->retry.push_back(i);
+    s.busy = false;
+    h->inflight--;
+    return RSA_EXT_OK;
+}
+
+int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
+                rsa_ext_result_t* results) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is already pending"; return RSA_EXT_ERR_STATE; }
+    if (n <= 0 || !qbuf || !qoff || !tbuf || !toff || !results) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    // the reference validates the whole slice before touching the GPU (gasal2_ssw.cpp:74-89)
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t ql = qoff[i + 1] - qoff[i];
+        if (ql > h->cfg.max_query_len) {
+            h->err = "gasal2 : read size is too big, " + std::to_string(ql) + " > " + std::to_string(h->cfg.max_query_len);
+            return RSA_EXT_ERR_QUERY_LEN;
+        }
+        if (ql < 0 || toff[i + 1] < toff[i]) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
+    }
+    h->n = n; h->qbuf = qbuf; h->qoff = qoff; h->tbuf = tbuf; h->toff = toff; h->results = results;
+    h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0;
+    h->overflow.clear();
+    h->retry.clear();
+    h->stats = rsa_ext_stats_t{};
+    h->pending = true;
+    while (h->next_pair < n && h->inflight < kSlots) {
+        int rc = enqueue_chunk(h, h->slots[h->tail]);
+        if (rc) { h->pending = false; return rc; }
+        h->tail = (h->tail + 1) % kSlots;
+    }
+    return RSA_EXT_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------------
+
+extern "C" int rsa_ext_version(void) { return 1; }
+
+extern "C" const char* rsa_ext_last_error(const rsa_ext_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
+    if (!out) return RSA_EXT_ERR_ARG;
+    *out = nullptr;
+    rsa_ext_config_t cfg{};
+    if (cfg_in) cfg = *cfg_in;
+    if (cfg.max_query_len <= 0) cfg.max_query_len = 500;   // gasal2_ssw.h:24
+    if (cfg.max_target_len <= 0) cfg.max_target_len = 2000; // gasal2_ssw.h:25
+    if (cfg.match == 0 && cfg.mismatch == 0 && cfg.gap_open == 0 && cfg.gap_extend == 0) {
+        cfg.match = 2; cfg.mismatch = 8; cfg.gap_open = 12; cfg.gap_extend = 1;  // cmdline.hpp:46-50
+    }
+    if (cfg.max_query_len > 512 || cfg.max_target_len > kMaxTargetLenCap) {
+        g_create_error = "max_query_len must be <= 512 and max_target_len <= 8192";
+        return RSA_EXT_ERR_ARG;
+    }
+    if (cfg.scratch_bytes <= 0) cfg.scratch_bytes = kDefaultScratch;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+        return RSA_EXT_ERR_CUDA;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) { g_create_error = "bad device ordinal"; return RSA_EXT_ERR_ARG; }
+    rsa_ext* h = new rsa_ext();
+    h->cfg = cfg;
+    h->sc.match = cfg.match;
+    h->sc.mismatch = cfg.mismatch;
+    h->sc.gap_oe = (cfg.gap_open - 1) + cfg.gap_extend;  // gasal2_ssw.cpp:54, gasal_align.cu:332-337
+    h->sc.gap_ext = cfg.gap_extend;
+    h->scratch_per_slot = (size_t)cfg.scratch_bytes / kSlots;
+    h->fk = make_fast_consts(h->sc);
+    h->fast_ok = fast_scoring_ok(h->sc);
+    auto fail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        rsa_ext_destroy(h);
+        return RSA_EXT_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    for (Slot& s : h->slots) {
+        if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaHostAlloc(&s.h_arena_used, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
+        if ((e = cudaMalloc(&s.d_arena_used, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+    }
+    {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+        h->n_sms = prop.multiProcessorCount;
+    }
+    *out = h;
+    return RSA_EXT_OK;
+}
+
+extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
+    for (Slot& s : h->slots) {
+        for (DevBuf* b : {&s.d_blob, &s.d_q, &s.d_t, &s.d_ends, &s.d_res, &s.d_scratch, &s.d_arena})
+            if (b->p) cudaFree(b->p);
+        if (s.h_blob.p) cudaFreeHost(s.h_blob.p);
+        if (s.h_arena_used) cudaFreeHost(s.h_arena_used);
+        if (s.d_arena_used) cudaFree(s.d_arena_used);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
+        if (b->p) cudaFree(b->p);
+    for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
+    if (h->own_q.p) cudaFreeHost(h->own_q.p);
+    if (h->own_t.p) cudaFreeHost(h->own_t.p);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+extern "C" int rsa_ext_submit(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf,
+                              const int64_t* toff, rsa_ext_result_t* results) {
+    return submit_core(h, n, qbuf, qoff, tbuf, toff, results);
+}
+
+extern "C" int rsa_ext_submit_ptrs(rsa_ext_t* h, int64_t n, const char* const* q, const int32_t* qlen,
+                                   const char* const* t, const int32_t* tlen, rsa_ext_result_t* results) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is already pending"; return RSA_EXT_ERR_STATE; }
+    if (n <= 0 || !q || !qlen || !t || !tlen || !results) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    h->own_qoff.resize(n + 1);
+    h->own_toff.resize(n + 1);
+    int64_t qs = 0, ts = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (qlen[i] < 0 || tlen[i] < 0) { h->err = "negative length"; return RSA_EXT_ERR_ARG; }
+        h->own_qoff[i] = qs; h->own_toff[i] = ts;
+        qs += qlen[i]; ts += tlen[i];
+    }
+    h->own_qoff[n] = qs; h->own_toff[n] = ts;
+    int rc;
+    if ((rc = ensure_pin(h, h->own_q, (size_t)qs + 16))) return rc;
+    if ((rc = ensure_pin(h, h->own_t, (size_t)ts + 16))) return rc;
+    // the copy gasal_host_batch_fill does into its pinned pages (host_batch.cpp:137-146), minus the padding
+    for (int64_t i = 0; i < n; ++i) {
+        memcpy(h->own_q.p + h->own_qoff[i], q[i], (size_t)qlen[i]);
+        memcpy(h->own_t.p + h->own_toff[i], t[i], (size_t)tlen[i]);
+    }
+    return submit_core(h, n, reinterpret_cast<const char*>(h->own_q.p), h->own_qoff.data(),
+                       reinterpret_cast<const char*>(h->own_t.p), h->own_toff.data(), results);
+}
+
+extern "C" int rsa_ext_poll(rsa_ext_t* h) {
+    if (!h || !h->pending) return 0;
+    if (h->next_pair < h->n) return 1;
+    for (int k = 0; k < kSlots; ++k)
+        if (h->slots[k].busy && cudaEventQuery(h->slots[k].ev_d2h) == cudaErrorNotReady) return 1;
+    return 0;
+}
+
+// Pairs the redo pass could not re-tile (status 4; only possible when a chunk holds more symbols outside
+// ACGTN than the scratch head-room covers): run them again as their own exact-only batch and splice the
+// records and long-CIGAR strings back.
+static int run_retry(rsa_ext* h) {
+    const std::vector<int64_t> idx = h->retry;
+    const int64_t m = (int64_t)idx.size();
+    std::vector<const char*> qp(m), tp(m);
+    std::vector<int32_t> ql(m), tl(m);
+    for (int64_t k = 0; k < m; ++k) {
+        qp[k] = h->qbuf + h->qoff[idx[k]]; ql[k] = (int32_t)(h->qoff[idx[k] + 1] - h->qoff[idx[k]]);
+        tp[k] = h->tbuf + h->toff[idx[k]]; tl[k] = (int32_t)(h->toff[idx[k] + 1] - h->toff[idx[k]]);
+    }
+    std::vector<rsa_ext_result_t> tmp(m);
+    rsa_ext_result_t* results = h->results;
+    auto overflow = std::move(h->overflow);
+    const rsa_ext_stats_t stats = h->stats;
+    const int32_t flags = h->cfg.flags;
+    h->cfg.flags |= RSA_EXT_FLAG_EXACT_ONLY;
+    int rc = rsa_ext_submit_ptrs(h, m, qp.data(), ql.data(), tp.data(), tl.data(), tmp.data());
+    if (rc == RSA_EXT_OK) rc = rsa_ext_wait(h);
+    h->cfg.flags = flags;
+    if (rc != RSA_EXT_OK) return rc;
+    for (int64_t k = 0; k < m; ++k) {
+        results[idx[k]] = tmp[k];
+        auto it = h->overflow.find(k);
+        if (it != h->overflow.end()) overflow[idx[k]] = std::move(it->second);
+    }
+    h->overflow = std::move(overflow);
+    rsa_ext_stats_t s2 = h->stats;
+    h->stats = stats;
+    h->stats.kernel_launches += s2.kernel_launches;
+    h->stats.pairs_exact += s2.pairs_exact;
+    h->stats.h2d_bytes += s2.h2d_bytes;
+    h->stats.d2h_bytes += s2.d2h_bytes;
+    h->results = results;
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_wait(rsa_ext_t* h) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (!h->pending) { h->err = "nothing submitted"; return RSA_EXT_ERR_STATE; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = RSA_EXT_OK;
+    while (h->inflight > 0) {
+        Slot& s = h->slots[h->head];
+        if ((rc = retire_chunk(h, s))) break;
+        h->head = (h->head + 1) % kSlots;
+        if (h->next_pair < h->n) {
+            if ((rc = enqueue_chunk(h, h->slots[h->tail]))) break;
+            h->tail = (h->tail + 1) % kSlots;
+        }
+    }
+    if (rc) {
+        cudaDeviceSynchronize();
+        for (Slot& s : h->slots) s.busy = false;
+        h->inflight = 0;
+    }
+    h->pending = false;
+    if (rc == RSA_EXT_OK && !h->retry.empty()) rc = run_retry(h);
+    return rc;
+}
+
+extern "C" int rsa_ext_rle_overflow(rsa_ext_t* h, int64_t i, uint8_t* out, int32_t cap) {
+    if (!h || !out) return RSA_EXT_ERR_ARG;
+    auto it = h->overflow.find(i);
+    if (it == h->overflow.end()) { h->err = "no overflow record for this pair"; return RSA_EXT_ERR_ARG; }
+    const int n = (int)std::min<size_t>(it->second.size(), (size_t)std::max(cap, 0));
+    memcpy(out, it->second.data(), (size_t)n);
+    return n;
+}
+
+extern "C" int rsa_ext_rle_to_text(const uint8_t* rle, int32_t n_ops, char* out, int32_t cap) {
+    // src/gasal2_ssw.cpp:184-243: bytes last-to-first, equal neighbours merged
+    static const char opc[4] = {'M', 'X', 'D', 'I'};
+    if (cap <= 0 || !out) return -1;
+    int pos = 0;
+    out[0] = 0;
+    if (n_ops <= 0 || !rle) return 0;
+    int last_op = rle[n_ops - 1] & 3;
+    long count = rle[n_ops - 1] >> 2;
+    auto put = [&](long cnt, int op) -> bool {
+        char tmp[24];
+        int w = snprintf(tmp, sizeof tmp, "%ld%c", cnt, opc[op]);
+        if (pos + w >= cap) return false;
+        memcpy(out + pos, tmp, (size_t)w);
+        pos += w;
+        out[pos] = 0;
+        return true;
+    };
+    for (int u = n_ops - 2; u >= 0; --u) {
+        const int op = rle[u] & 3;
+        if (op == last_op) count += rle[u] >> 2;
+        else {
+            if (!put(count, last_op)) return -1;
+            count = rle[u] >> 2;
+        }
+        last_op = op;
+    }
+    if (!put(count, last_op)) return -1;
+    return pos;
+}
+
+extern "C" void* rsa_ext_stream(rsa_ext_t* h) { return h ? (void*)h->s_comp : nullptr; }
+
+extern "C" int rsa_ext_get_stats(const rsa_ext_t* hc, rsa_ext_stats_t* out) {
+    if (!hc || !out) return RSA_EXT_ERR_ARG;
+    rsa_ext* h = const_cast<rsa_ext*>(hc);
+    if (h->r_events_valid) {
+        cudaSetDevice(h->cfg.device);
+        cudaStreamSynchronize(h->s_comp);
+        double dp = 0, tb = 0;
+        for (size_t c = 0; c < h->res_chunks.size(); ++c) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, h->r_events[3 * c], h->r_events[3 * c + 1]);
+            cudaEventElapsedTime(&b, h->r_events[3 * c + 1], h->r_events[3 * c + 2]);
+            dp += a; tb += b;
+        }
+        h->stats.dp_ms = dp;
+        h->stats.tb_ms = tb;
+    }
+    *out = h->stats;
+    return RSA_EXT_OK;
+}
+
+// ---- resident legs ------------------------------------------------------------------------------------
+
+extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
+                                      const char* tbuf, const int64_t* toff) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    if (n <= 0 || !qbuf || !qoff || !tbuf || !toff) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaDeviceSynchronize());
+    h->res_chunks.clear();
+    h->r_events_valid = false;
+    h->r_n = n;
+    h->stats = rsa_ext_stats_t{};
+    PlanInput in{n, qoff, toff, qbuf, tbuf, h->cfg.max_query_len, h->cfg.max_target_len, h->scratch_per_slot,
+                 (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
+    std::vector<std::vector<uint8_t>> blobs;
+    int64_t lo = 0;
+    size_t blob_total = 0, max_pairs = 0, max_scratch = 0, max_arena = 0;
+    while (lo < n) {
+        ResidentChunk rc_;
+        blobs.emplace_back();
+        int rc = plan_chunk(h, in, lo, rc_.plan, &blobs.back(), nullptr);
+        if (rc) return rc;
+        rc_.q_base = (size_t)(qoff[lo] - qoff[0]);
+        rc_.t_base = (size_t)(toff[lo] - toff[0]);
+        blob_total += align_up(rc_.plan.blob_bytes, 256);
+        max_pairs = std::max(max_pairs, (size_t)rc_.plan.n);
+        max_scratch = std::max(max_scratch, (size_t)rc_.plan.scratch_bytes);
+        max_arena = std::max(max_arena, (size_t)rc_.plan.arena_bytes);
+        lo = rc_.plan.hi;
+        h->res_chunks.push_back(rc_);
+    }
+    int rc;
+    const size_t qbytes = (size_t)(qoff[n] - qoff[0]), tbytes = (size_t)(toff[n] - toff[0]);
+    if ((rc = ensure_dev(h, h->r_q, qbytes + 16))) return rc;
+    if ((rc = ensure_dev(h, h->r_t, tbytes + 16))) return rc;
+    if ((rc = ensure_dev(h, h->r_res, sizeof(rsa_ext_result_t) * (size_t)n))) return rc;
+    if ((rc = ensure_dev(h, h->r_blobs, blob_total))) return rc;
+    Slot& s = h->slots[0];
+    if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * max_pairs))) return rc;
+    if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(max_scratch)))) return rc;
+    if ((rc = ensure_dev(h, s.d_arena, max_arena))) return rc;
+    CU_TRY(h, cudaMemcpy(h->r_q.p, qbuf + qoff[0], qbytes, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->r_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice));
+    size_t boff = 0;
+    for (size_t c = 0; c < h->res_chunks.size(); ++c) {
+        h->res_chunks[c].d_blob = h->r_blobs.p + boff;
+        CU_TRY(h, cudaMemcpy(h->r_blobs.p + boff, blobs[c].data(), blobs[c].size(), cudaMemcpyHostToDevice));
+        boff += align_up(h->res_chunks[c].plan.blob_bytes, 256);
+        h->stats.pairs_fast += h->res_chunks[c].plan.n_fast_pairs;
+        h->stats.pairs_exact += h->res_chunks[c].plan.n_exact[0] + h->res_chunks[c].plan.n_exact[1] + h->res_chunks[c].plan.n_exact[2];
+        h->stats.pairs_failed += h->res_chunks[c].plan.n_failed;
+        h->stats.cells += h->res_chunks[c].plan.cells;
+    }
+    h->stats.h2d_bytes = (int64_t)(qbytes + tbytes + blob_total);
+    while (h->r_events.size() < 3 * h->res_chunks.size()) {
+        cudaEvent_t ev;
+        CU_TRY(h, cudaEventCreate(&ev));
+        h->r_events.push_back(ev);
+    }
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    Slot& s = h->slots[0];
+    h->stats.kernel_launches = 0;
+    for (size_t c = 0; c < h->res_chunks.size(); ++c) {
+        const ResidentChunk& rcx = h->res_chunks[c];
+        ChunkDev d{rcx.d_blob, h->r_q.p + rcx.q_base, h->r_t.p + rcx.t_base, reinterpret_cast<DpEnd*>(s.d_ends.p),
+                   reinterpret_cast<rsa_ext_result_t*>(h->r_res.p) + rcx.plan.lo, s.d_scratch.p, (uint64_t)s.d_scratch.cap,
+                   s.d_arena.p, s.d_arena_used, (uint64_t)s.d_arena.cap};
+        int rc = enqueue_compute(h, h->s_comp, d, rcx.plan, &h->r_events[3 * c]);
+        if (rc) return rc;
+    }
+    h->r_events_valid = true;
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_fetch_resident(rsa_ext_t* h, rsa_ext_result_t* results) {
+    if (!h || !results) return RSA_EXT_ERR_ARG;
+    if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaStreamSynchronize(h->s_comp));
+    CU_TRY(h, cudaMemcpy(results, h->r_res.p, sizeof(rsa_ext_result_t) * (size_t)h->r_n, cudaMemcpyDeviceToHost));
+    return RSA_EXT_OK;
+}
+
+// Host-only planning probe for tests (no CUDA call is made): plans the first chunk of a batch and reports
+// how pairs were routed.  out[0]=pairs in chunk, [1]=fast pairs, [2]=exact pairs, [3]=failed, [4]=groups,
+// [5]=scratch bytes, [6]=fast classes.
+extern "C" int rsa_ext_plan_debug(int64_t n, const int64_t* qoff, const int64_t* toff, int64_t scratch_cap,
+                                  int exact_only, int64_t* out) {
+    rsa_ext h;
+    PlanInput in{n, qoff, toff, nullptr, nullptr, 500, 2000, (size_t)scratch_cap, exact_only != 0};
+    ChunkPlan p;
+    std::vector<uint8_t> blob;
+    int rc = plan_chunk(&h, in, 0, p, &blob, nullptr);
+    if (rc) return rc;
+    int groups = 0;
+    for (auto& fc : p.fast) groups += fc.n_groups;
+    out[0] = p.n; out[1] = p.n_fast_pairs; out[2] = p.n_exact[0] + p.n_exact[1] + p.n_exact[2];
+    out[3] = p.n_failed; out[4] = groups; out[5] = (int64_t)p.scratch_bytes; out[6] = p.n_fast_classes;
+    return RSA_EXT_OK;
+}

@@ -1,0 +1,57 @@
+// fast_layout.cuh -- geometry of the packed kernel's column ownership and direction-bit scratch.
+//
+// A "group" is 8 lanes working on TWO pairs of equal query length (pair A in the low 16-bit halves of every
+// packed register, pair B in the high halves).  The query's columns are dealt to the 8 lanes in order:
+// with C = ceil(qlen/8), the first `rem` lanes own C columns and the remaining lanes own C-1, so that
+// every owned column is a real query base (no padding columns exist).
+//
+// Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
+//     uint32 index = (r*8 + l)*W + w,   W = ceil(C/4)
+// low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
+//     bit3 open_f   (F of the next column opened from the diagonal; reference bit3 is the negation)
+//     bit2 open_e   (reference bit2 negated)
+//     bit1 not_diag (H != diag+sub)
+//     bit0 not_f    (max(F,E,0) != F, i.e. with not_diag: source is E -> code 2, else F -> code 3)
+#pragma once
+#include "common.cuh"
+
+namespace rsa {
+
+constexpr int kFastLanes = 8;
+
+struct FastGeom {
+    int C;    // columns of the widest lanes
+    int rem;  // number of lanes owning C columns (1..8); the rest own C-1
+    int W;    // 32-bit direction words per lane and row
+};
+
+__host__ __device__ inline FastGeom fast_geom(int qlen) {
+    FastGeom g;
+    g.C = (qlen + kFastLanes - 1) / kFastLanes;
+    g.rem = qlen - kFastLanes * (g.C - 1);
+    g.W = (g.C + 3) / 4;
+    return g;
+}
+
+// bytes of direction scratch of one group (two pairs) with `rows` target rows
+__host__ __device__ inline uint64_t fast_dir_bytes(const FastGeom& g, int rows) {
+    return (uint64_t)rows * kFastLanes * g.W * 4u;
+}
+
+// first column owned by lane l
+__host__ __device__ inline int fast_lane_col0(const FastGeom& g, int l) {
+    return l <= g.rem ? l * g.C : g.rem * g.C + (l - g.rem) * (g.C - 1);
+}
+
+__device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const uint8_t* dir, int i, int j,
+                                                     int half) {
+    int lane, cc;
+    const int wide = g.rem * g.C;
+    if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
+    else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((size_t)i * kFastLanes + lane) * g.W + (cc >> 2)];
+    const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
+    return (h16 >> (4 * (cc & 3))) & 0xFu;
+}
+
+}  // namespace rsa

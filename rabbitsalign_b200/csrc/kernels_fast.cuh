@@ -1,0 +1,508 @@
+// kernels_fast.cuh -- packed s16x2 DPX wavefront kernel for sm_100a (the bulk path).
+//
+// What it computes: the same DP and direction information as the reference's
+// gasal_local_kernel<LOCAL, WITH_TB, FALSE> (GASAL2/src/kernels/local_kernel_template.h:45-60,118-430)
+// for pairs over the alphabet {A,C,G,T,N} (any case).  How: nothing like the reference.
+//
+//   * inter-query packing: every 32-bit register holds the same DP quantity of TWO pairs of equal query
+//     length (pair A in the low 16 bits, pair B in the high 16 bits), so one DPX instruction
+//     (VIMNMX3.S16x2, VIADDMNMX.S16x2, VIMNMX.S16x2) advances two cells;
+//   * 8 lanes ("group") sweep one such double-pair as an anti-diagonal wavefront: lane l owns a contiguous
+//     run of query columns in registers (H of the previous row, E, column maximum) and is one target row
+//     behind lane l-1; H and F of a lane's last column reach the next lane with one shuffle each per row;
+//     a warp carries 4 groups = 8 pairs;
+//   * scores are kept BIASED (value + kBias in every half) so every half stays a non-negative 16-bit
+//     number: plain 32-bit IADD3 then adds/subtracts both halves at once with no cross-half borrow, and a
+//     "difference >= 1" predicate becomes one IADD3 with a constant that carries into a chosen bit;
+//   * the substitution score is ONE byte-permute per double-cell: per target row the two pairs' 4-entry
+//     score profiles sit in two registers (staged in shared memory once per group), and a per-column
+//     selector picks the byte of the query base of A and of B;
+//   * the four direction facts per cell (F opened, E opened, H != diagonal, max(F,E,0) != F) are gathered
+//     with bit-selects into one nibble per cell per pair and streamed to a global scratch tile
+//     (fast_layout.cuh); the match/mismatch bit is not stored (the traceback recomputes it from the bases);
+//   * the end cell: per lane the packed running maximum, the row where it last strictly improved and a
+//     sticky "same maximum seen again in a later row" flag, plus a per-column maximum.  If the maximum is
+//     unique in the sense the reference's first-maximum rule needs, the end cell follows
+//     from those; otherwise the pair is flagged and the exact kernel recomputes the end cell (score-only).
+//   * symbols outside {A,C,G,T,N}: the pair is flagged and fully redone by the exact kernel.
+#pragma once
+#include "common.cuh"
+#include "fast_layout.cuh"
+#include "kernels_exact.cuh"
+
+namespace rsa {
+
+constexpr int kFastMinQlen = 8;
+constexpr int kFastMaxC = 32;
+constexpr int kFastMaxQlen = kFastLanes * kFastMaxC;  // 256
+constexpr int kFastMaxTlen = 2047;
+constexpr int kFastGroupsPerWarp = 4;
+constexpr int kFastWarpsPerBlock = 4;
+constexpr int kBias = 64;  // every stored half = value + kBias; E,F >= -(mismatch+gap_oe) > -kBias
+
+struct FastGroup {
+    uint32_t a, b;      // pair indices in the chunk (b == a: lone pair; a == 0xFFFFFFFF: empty slot)
+    uint64_t dir_off;   // byte offset of the group's direction tile in the scratch
+    uint16_t qlen;
+    uint16_t rows;      // max(|t_a|, |t_b|)
+};
+
+// Per-chunk redo bookkeeping living in the metadata blob (host zeroes it before the upload).
+struct RedoHeader {
+    unsigned int count;             // number of entries in list[]
+    unsigned int pad;
+    unsigned long long scratch_used; // bytes handed out from the redo scratch region
+};
+
+struct FastConsts {
+    uint32_t zero;     // (kBias, kBias)
+    uint32_t neg_x;    // ring constant: subtract mismatch from both halves
+    uint32_t neg_xoe;  // subtract mismatch + gap_oe
+    uint32_t neg_e;    // per-half s16 (-gap_ext) for VIADDMNMX
+    uint32_t k_f, k_e, k_d, k_n;
+    uint32_t x_pair;   // (mismatch, mismatch): biased profile value of a zero-scoring cell
+    uint32_t prof_match;  // match + mismatch (byte)
+    int bias;
+};
+
+__host__ __device__ inline uint32_t pair16(int v) { return ((uint32_t)(v & 0xFFFF) << 16) | (uint32_t)(v & 0xFFFF); }
+
+__host__ inline FastConsts make_fast_consts(const Scoring& sc) {
+    FastConsts k;
+    k.bias = kBias;
+    k.zero = pair16(kBias);
+    k.neg_x = (uint32_t)(0u - (uint32_t)sc.mismatch * 0x00010001u);
+    k.neg_xoe = (uint32_t)(0u - (uint32_t)(sc.mismatch + sc.gap_oe) * 0x00010001u);
+    k.neg_e = pair16(-sc.gap_ext);
+    k.k_f = pair16(sc.gap_ext + 0x7FFF);
+    k.k_e = pair16(sc.gap_ext + 0x3FFF);
+    k.k_d = pair16(0x1FFF);
+    k.k_n = pair16(0x0FFF);
+    k.x_pair = pair16(sc.mismatch);
+    k.prof_match = (uint32_t)(sc.match + sc.mismatch);
+    return k;
+}
+
+// Can the packed kernel represent this scoring?  (biased halves must stay in [0, 2^12) for the flag trick)
+__host__ inline bool fast_scoring_ok(const Scoring& sc) {
+    return sc.match > 0 && sc.mismatch > 0 && sc.gap_ext >= 0 && sc.gap_oe >= sc.gap_ext &&
+           sc.mismatch + sc.gap_oe < kBias - 2 && sc.match + sc.mismatch < 128 &&
+           sc.match * kFastMaxQlen + kBias + sc.mismatch + sc.gap_oe < 0x0F00;
+}
+
+// nibble (ascii & 0xF) -> code: A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4, everything else 0xF
+__device__ __forceinline__ uint32_t base_code(uint32_t nib) {
+    uint32_t c = 0xFu;
+    c = (nib == 1u) ? 0u : c;
+    c = (nib == 3u) ? 1u : c;
+    c = (nib == 7u) ? 2u : c;
+    c = (nib == 4u) ? 3u : c;
+    c = (nib == 0xEu) ? 4u : c;
+    return c;
+}
+
+// 4-byte biased score profile of one target-row code: byte k = score(query code k, target) + mismatch.
+// code 0..3 = base, 4 = N (scores 0 against everything), 5 = row past the pair's own window (everything
+// mismatches, so H only decays there and can never reach the pair's maximum).
+__host__ __device__ inline uint32_t profile_word(uint32_t code, const FastConsts& k) {
+    if (code < 4u) return k.prof_match << (8u * code);
+    if (code == 4u) return (k.x_pair & 0xFFu) * 0x01010101u;
+    return 0u;
+}
+
+__device__ __forceinline__ uint32_t bitsel(uint32_t mask, uint32_t a, uint32_t b) {  // mask ? a : b, one LOP3
+    return (a & mask) | (b & ~mask);
+}
+
+__device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
+
+template <int C, bool HASN>
+struct FastDp {
+    // One group's sweep.  All 32 lanes of the warp call this together (shuffles inside).
+    __device__ static __forceinline__ void run(const FastConsts& k, const uint8_t* __restrict__ tcodes, const uint32_t* __restrict__ lut, int rows,
+                                               int nsteps, int gl, bool wide, const uint32_t (&qsel)[C],
+                                               const uint32_t (&nmask)[C], uint32_t* __restrict__ dir, int W,
+                                               uint32_t (&colbest)[C], uint32_t& best_out, int (&firstrow)[2],
+                                               bool (&tie)[2]) {
+        uint32_t Hp[C], E[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { Hp[c] = k.zero; E[c] = k.zero; colbest[c] = k.zero; }
+        uint32_t Hlast = k.zero, Fout = k.zero, Hl_prev = k.zero, best = k.zero;
+        firstrow[0] = firstrow[1] = 0;
+        tie[0] = tie[1] = false;
+        constexpr int NW = (C + 3) / 4;
+        for (int s = 0; s < nsteps; ++s) {
+            uint32_t Hl = __shfl_up_sync(0xFFFFFFFFu, Hlast, 1, kFastLanes);
+            uint32_t Fl = __shfl_up_sync(0xFFFFFFFFu, Fout, 1, kFastLanes);
+            if (gl == 0) { Hl = k.zero; Fl = k.zero; }
+            const int r = s - gl;
+            if (r >= 0 && r < rows) {
+                const uint32_t tc = tcodes[r];
+                uint2 pr;
+                pr.x = lut[tc & 0xFu];
+                pr.y = lut[tc >> 4];
+                uint32_t diag = Hl_prev, F = Fl, rowmax = k.zero;
+                uint32_t acc = 0;
+                uint32_t words[NW];
+                uint32_t Fsave = Fl;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
+                    if (c < C - 1 || wide) {
+                        uint32_t sub = __byte_perm(pr.x, pr.y, qsel[c]);
+                        if (HASN) sub = bitsel(nmask[c], sub, k.x_pair);
+                        const uint32_t tmp = diag + sub + k.neg_x;
+                        const uint32_t tg = diag + sub + k.neg_xoe;
+                        const uint32_t e = E[c];
+                        const uint32_t u = __vimax3_s16x2(F, e, k.zero);
+                        const uint32_t h = __vmaxs2(tmp, u);
+                        const uint32_t fn = __viaddmax_s16x2(F, k.neg_e, tg);
+                        const uint32_t en = __viaddmax_s16x2(e, k.neg_e, tg);
+                        const uint32_t fo = fn - F + k.k_f;   // bit15: F opened
+                        const uint32_t eo = en - e + k.k_e;   // bit14: E opened
+                        const uint32_t nd = h - tmp + k.k_d;  // bit13: H != diagonal
+                        const uint32_t nf = u - F + k.k_n;    // bit12: max(F,E,0) != F
+                        uint32_t fl = bitsel(0x80008000u, fo, eo);
+                        fl = bitsel(0xC000C000u, fl, nd);
+                        fl = bitsel(0xE000E000u, fl, nf);
+                        acc = bitsel(0xF000F000u, fl, acc >> 4);
+                        colbest[c] = __vmaxs2(colbest[c], h);
+                        rowmax = __vmaxs2(rowmax, h);
+                        diag = Hp[c];
+                        Hp[c] = h;
+                        E[c] = en;
+                        F = fn;
+                    } else {
+                        acc >>= 4;  // absent last column of a narrow lane: keep the nibble positions
+                    }
+                    if ((c & 3) == 3) { words[c >> 2] = acc; acc = 0; }
+                    else if (c == C - 1) words[c >> 2] = acc >> (4 * (3 - (c & 3)));  // right-align partial word
+                }
+                Hlast = wide ? Hp[C - 1] : Hp[(C >= 2) ? C - 2 : 0];
+                Fout = wide ? F : Fsave;
+                // direction words of this lane and row
+                uint32_t* drow = dir + ((size_t)r * kFastLanes + gl) * W;
+#pragma unroll
+                for (int wv = 0; wv < NW; ++wv) drow[wv] = words[wv];
+                // running maximum bookkeeping (per half)
+                bool ge_lo, ge_hi, le_lo, le_hi;
+                const uint32_t nb = __vibmax_s16x2(best, rowmax, &ge_hi, &ge_lo);  // ge: best >= rowmax
+                (void)__vibmax_s16x2(rowmax, best, &le_hi, &le_lo);               // le: rowmax >= best
+                if (!ge_lo) { firstrow[0] = r; tie[0] = false; } else if (le_lo) tie[0] = true;
+                if (!ge_hi) { firstrow[1] = r; tie[1] = false; } else if (le_hi) tie[1] = true;
+                best = nb;
+            }
+            Hl_prev = Hl;
+        }
+        best_out = best;
+    }
+};
+
+template <int C>
+__global__ void __launch_bounds__(32 * kFastWarpsPerBlock)
+fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
+               const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
+               uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
+               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad) {
+    extern __shared__ uint8_t fast_smem[];
+    uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 words
+    if (threadIdx.x < 8) lut[threadIdx.x] = profile_word(threadIdx.x, k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = lane >> 3, gl = lane & 7;
+    const int g_index = (blockIdx.x * kFastWarpsPerBlock + warp) * kFastGroupsPerWarp + gi;
+    FastGroup grp;
+    grp.a = 0xFFFFFFFFu; grp.b = 0xFFFFFFFFu; grp.dir_off = 0; grp.qlen = 0; grp.rows = 0;
+    if (g_index < n_groups) grp = groups[g_index];
+    const bool live = grp.a != 0xFFFFFFFFu;
+    uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * kFastGroupsPerWarp + gi) * rows_pad;
+
+    // ---- staging: target profiles into shared memory, query selectors into registers ----------------
+    bool bad_a = false, bad_b = false;
+    int rows = 0, tlen_a = 0, tlen_b = 0, qlen = 0;
+    const uint8_t *qa = nullptr, *qb = nullptr;
+    FastGeom geo = fast_geom(8 * C);
+    if (live) {
+        const PairMeta ma = meta[grp.a], mb = meta[grp.b];
+        qlen = grp.qlen;
+        geo = fast_geom(qlen);
+        rows = grp.rows;
+        tlen_a = ma.tlen; tlen_b = mb.tlen;
+        qa = qbuf + ma.qoff; qb = qbuf + mb.qoff;
+        const uint8_t* ta = tbuf + ma.toff;
+        const uint8_t* tb = tbuf + mb.toff;
+        for (int r = gl; r < rows; r += kFastLanes) {
+            uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
+            if (r < tlen_a) { ca = base_code(nibble_of(ta[r])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
+            if (r < tlen_b) { cb = base_code(nibble_of(tb[r])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
+            tcodes[r] = (uint8_t)(ca | (cb << 4));
+        }
+    }
+    const int ncols = live ? ((gl < geo.rem) ? geo.C : geo.C - 1) : 0;
+    const bool wide = live && (ncols == C);
+    const int col0 = live ? fast_lane_col0(geo, gl) : 0;
+    uint32_t qsel[C], nmask[C];
+    bool has_n = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        uint32_t ca = 0, cb = 0;
+        uint32_t nm = 0xFFFFFFFFu;
+        if (c < ncols) {
+            ca = base_code(nibble_of(qa[col0 + c]));
+            cb = base_code(nibble_of(qb[col0 + c]));
+            bad_a |= (ca == 0xFu);
+            bad_b |= (cb == 0xFu);
+            if (ca >= 4u) { nm &= 0xFFFF0000u; ca = 0; }
+            if (cb >= 4u) { nm &= 0x0000FFFFu; cb = 0; }
+            has_n |= (nm != 0xFFFFFFFFu);
+        }
+        // result bytes: [0] = X[ca], [1] = 0 (sign of a non-negative byte), [2] = Y[cb], [3] = 0
+        qsel[c] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
+        nmask[c] = nm;
+    }
+    const unsigned gmask = 0xFFu << (8 * gi);
+    bad_a = (__ballot_sync(0xFFFFFFFFu, bad_a) & gmask) != 0;
+    bad_b = (__ballot_sync(0xFFFFFFFFu, bad_b) & gmask) != 0;
+    const bool warp_has_n = __any_sync(0xFFFFFFFFu, has_n);
+    int nsteps = rows + kFastLanes - 1;
+    if (!live) nsteps = 0;
+#pragma unroll
+    for (int off = 16; off >= 8; off >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xFFFFFFFFu, nsteps, off));
+    __syncthreads();  // lut + this warp's target codes
+
+    uint32_t* dir = reinterpret_cast<uint32_t*>(scratch + grp.dir_off);
+    uint32_t colbest[C];
+    uint32_t best;
+    int firstrow[2];
+    bool tie[2];
+    if (warp_has_n) FastDp<C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, nmask, dir, geo.W, colbest, best, firstrow, tie);
+    else FastDp<C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, nmask, dir, geo.W, colbest, best, firstrow, tie);
+
+    // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t pi = h ? grp.b : grp.a;
+        const bool bad = h ? bad_b : bad_a;
+        const int mine = half_s(best, h) - k.bias;
+        int S = mine;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(0xFFFFFFFFu, S, off));
+        const bool cand = live && (mine == S) && (S > 0);
+        const bool any_tie = (__ballot_sync(0xFFFFFFFFu, cand && tie[h]) & gmask) != 0;
+        int key = cand ? (((firstrow[h] >> 3) << 8) | gl) : 0x7FFFFFFF;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
+        if (!live || (h == 1 && grp.b == grp.a)) continue;
+        const bool winner = (S > 0) ? ((key & 0xFF) == gl) : (gl == 0);
+        if (!winner) continue;
+        DpEnd e;
+        e.score = S; e.qend = 0; e.tend = 0;
+        e.flags = DPF_DONE | DPF_LAYOUT_FAST;
+        if (bad) {
+            e.flags = DPF_NEED_EXACT;  // symbols outside {A,C,G,T,N}: full exact redo (own direction tile)
+        } else if (S > 0) {
+            int cmin = 0;
+            bool found = false;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (!found && c < ncols && half_s(colbest[c], h) - k.bias == S) { cmin = c; found = true; }
+            }
+            e.qend = col0 + cmin;
+            e.tend = firstrow[h];
+            if (any_tie) e.flags = DPF_NEED_EXACT | DPF_LAYOUT_FAST;  // end cell ambiguous: score-only redo
+        }
+        ends[pi] = e;
+        if (e.flags & DPF_NEED_EXACT) {
+            const unsigned int slot = atomicAdd(&redo->count, 1u);
+            redo_list[slot] = pi;
+        }
+    }
+}
+
+// ---- redo pass: exact kernel over the pairs the packed kernel flagged --------------------------------
+//
+// Warps pull entries from the redo list.  DPF_LAYOUT_FAST set: only the end cell is recomputed (the packed
+// kernel's direction tile is valid); clear: the pair gets a fresh exact-layout tile from the redo scratch
+// region and diroff[pi] is redirected to it.
+
+template <int C, bool WRITE_DIR>
+__device__ __forceinline__ void exact_dp_warp(const uint8_t* q, const uint8_t* tn, int qlen, int tlen, uint8_t* dir,
+                                              const Scoring& sc, int lane, int& out_score, int& out_qend, int& out_tend) {
+    const int c0 = lane * C;
+    int qc[C], Hp[C], E[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int col = c0 + c;
+        qc[c] = col < qlen ? (int)nibble_of(q[col]) : (int)kWildcard;
+        Hp[c] = 0; E[c] = 0;
+    }
+    int Hlast = 0, Fout = 0, Hl_prev = 0, best = 0;
+    uint32_t bestkey = 0xFFFFFFFFu;
+    constexpr int kRowBytes = 16 * C;
+    const int nsteps = tlen + 31;
+    for (int s = 0; s < nsteps; ++s) {
+        int Hl = __shfl_up_sync(0xFFFFFFFFu, Hlast, 1);
+        int Fl = __shfl_up_sync(0xFFFFFFFFu, Fout, 1);
+        if (lane == 0) { Hl = 0; Fl = 0; }
+        const int r = s - lane;
+        if (r >= 0 && r < tlen) {
+            const int tb = tn[r];
+            int diag = Hl_prev, F = Fl;
+            uint32_t w[(C + 7) / 8];
+#pragma unroll
+            for (int kk = 0; kk < (C + 7) / 8; ++kk) w[kk] = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int qb = qc[c];
+                int sub = (qb == tb) ? sc.match : -sc.mismatch;
+                if (qb == (int)kWildcard || tb == (int)kWildcard) sub = 0;
+                const int tmp = diag + sub;
+                const int e = E[c];
+                const int h = max(max(max(tmp, F), e), 0);
+                const int tg = tmp - sc.gap_oe;
+                if (WRITE_DIR) {
+                    uint32_t d = (h == tmp) ? (tmp >= diag ? 0u : 1u) : (h == F ? 3u : 2u);
+                    if (!(tg > F - sc.gap_ext)) d |= 8u;
+                    if (!(tg > e - sc.gap_ext)) d |= 4u;
+                    w[c >> 3] |= d << ((c & 7) * 4);
+                }
+                F = max(tg, F - sc.gap_ext);
+                E[c] = max(tg, e - sc.gap_ext);
+                const int col = c0 + c;
+                if (col < qlen && h > 0) {
+                    const uint32_t key = ((uint32_t)(r >> 3) << 12) | ((uint32_t)col << 3) | (uint32_t)(r & 7);
+                    if (h > best) { best = h; bestkey = key; }
+                    else if (h == best && key < bestkey) bestkey = key;
+                }
+                diag = Hp[c];
+                Hp[c] = h;
+            }
+            Hlast = Hp[C - 1];
+            Fout = F;
+            if (WRITE_DIR) {
+                uint8_t* row = dir + (size_t)r * kRowBytes + lane * (C / 2);
+                if (C == 4) *reinterpret_cast<uint16_t*>(row) = (uint16_t)w[0];
+                else {
+#pragma unroll
+                    for (int kk = 0; kk < (C + 7) / 8; ++kk) reinterpret_cast<uint32_t*>(row)[kk] = w[kk];
+                }
+            }
+        }
+        Hl_prev = Hl;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const int ob = __shfl_down_sync(0xFFFFFFFFu, best, off);
+        const uint32_t ok = __shfl_down_sync(0xFFFFFFFFu, bestkey, off);
+        if (ob > best || (ob == best && ok < bestkey)) { best = ob; bestkey = ok; }
+    }
+    best = __shfl_sync(0xFFFFFFFFu, best, 0);
+    bestkey = __shfl_sync(0xFFFFFFFFu, bestkey, 0);
+    out_score = best;
+    if (best == 0) { out_qend = 0; out_tend = 0; }
+    else { out_qend = (int)((bestkey >> 3) & 0x1FFu); out_tend = (int)(((bestkey >> 12) << 3) | (bestkey & 7u)); }
+}
+
+constexpr int kRedoWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(32 * kRedoWarpsPerBlock)
+exact_redo_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
+                  const PairMeta* __restrict__ meta, uint64_t* __restrict__ diroff, uint8_t* __restrict__ scratch,
+                  DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo, const uint32_t* __restrict__ redo_list,
+                  Scoring sc, int tlen_pad, unsigned long long redo_base, unsigned long long redo_cap,
+                  unsigned long long* __restrict__ counters) {
+    extern __shared__ uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tn = smem + warp * tlen_pad;
+    const unsigned int total = redo->count;
+    const unsigned int stride = gridDim.x * kRedoWarpsPerBlock;
+    for (unsigned int it = blockIdx.x * kRedoWarpsPerBlock + warp; it < total; it += stride) {
+        const uint32_t pi = redo_list[it];
+        const PairMeta m = meta[pi];
+        const uint8_t* q = qbuf + m.qoff;
+        const uint8_t* t = tbuf + m.toff;
+        const int qlen = m.qlen, tlen = m.tlen;
+        const bool keep_fast_tile = (ends[pi].flags & DPF_LAYOUT_FAST) != 0;
+        __syncwarp();
+        for (int i = lane; i < tlen; i += 32) tn[i] = (uint8_t)nibble_of(t[i]);
+        __syncwarp();
+        uint8_t* dir = nullptr;
+        bool ok = true;
+        if (!keep_fast_tile) {
+            unsigned long long off = 0;
+            const unsigned long long need = ((unsigned long long)tlen * exact_row_bytes(qlen) + 15ull) & ~15ull;
+            if (lane == 0) off = atomicAdd(&redo->scratch_used, need);
+            off = __shfl_sync(0xFFFFFFFFu, off, 0);
+            ok = off + need <= redo_cap;
+            if (ok) {
+                dir = scratch + redo_base + off;
+                if (lane == 0) diroff[pi] = redo_base + off;
+            }
+        }
+        int score = 0, qend = 0, tend = 0;
+        if (ok) {
+            const int cls = exact_class_cols(qlen);
+            if (keep_fast_tile) {
+                if (cls == 4) exact_dp_warp<4, false>(q, tn, qlen, tlen, nullptr, sc, lane, score, qend, tend);
+                else if (cls == 8) exact_dp_warp<8, false>(q, tn, qlen, tlen, nullptr, sc, lane, score, qend, tend);
+                else exact_dp_warp<16, false>(q, tn, qlen, tlen, nullptr, sc, lane, score, qend, tend);
+            } else {
+                if (cls == 4) exact_dp_warp<4, true>(q, tn, qlen, tlen, dir, sc, lane, score, qend, tend);
+                else if (cls == 8) exact_dp_warp<8, true>(q, tn, qlen, tlen, dir, sc, lane, score, qend, tend);
+                else exact_dp_warp<16, true>(q, tn, qlen, tlen, dir, sc, lane, score, qend, tend);
+            }
+        }
+        if (lane == 0) {
+            DpEnd e;
+            e.score = score; e.qend = qend; e.tend = tend;
+            e.flags = ok ? (DPF_DONE | (keep_fast_tile ? DPF_LAYOUT_FAST : 0u)) : DPF_NO_SCRATCH;
+            if (!ok) atomicAdd(&counters[1], 1ull);
+            ends[pi] = e;
+        }
+    }
+}
+
+}  // namespace rsa
+
+// ---- host-side launchers ------------------------------------------------------------------------------
+namespace rsa {
+
+template <int C>
+inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
+                            const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
+                            uint32_t* redo_list, const FastConsts& k, int max_rows) {
+    const int rows_pad = (max_rows + 15) & ~15;
+    const int groups_per_block = kFastWarpsPerBlock * kFastGroupsPerWarp;
+    const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
+    const size_t smem = 32 + (size_t)groups_per_block * rows_pad;
+    fast_dp_kernel<C><<<blocks, 32 * kFastWarpsPerBlock, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
+                                                                     redo, redo_list, k, rows_pad);
+}
+
+// returns 0, or -1 when C is outside the instantiated range
+inline int launch_fast_class(cudaStream_t st, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
+                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
+                             uint32_t* redo_list, const FastConsts& k, int max_rows) {
+    switch (C) {
+#define RSA_FAST_CASE(c) case c: launch_fast_one<c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+        RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6)
+        RSA_FAST_CASE(7) RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12)
+        RSA_FAST_CASE(13) RSA_FAST_CASE(14) RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18)
+        RSA_FAST_CASE(19) RSA_FAST_CASE(20) RSA_FAST_CASE(21) RSA_FAST_CASE(22) RSA_FAST_CASE(23) RSA_FAST_CASE(24)
+        RSA_FAST_CASE(25) RSA_FAST_CASE(26) RSA_FAST_CASE(27) RSA_FAST_CASE(28) RSA_FAST_CASE(29) RSA_FAST_CASE(30)
+        RSA_FAST_CASE(31) RSA_FAST_CASE(32)
+#undef RSA_FAST_CASE
+        default: return -1;
+    }
+}
+
+inline void launch_exact_redo(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
+                              uint64_t* diroff, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
+                              const uint32_t* redo_list, const Scoring& sc, int max_tlen, int n_sms,
+                              unsigned long long redo_base, unsigned long long redo_cap,
+                              unsigned long long* counters) {
+    const int tlen_pad = (max_tlen + 15) & ~15;
+    exact_redo_kernel<<<n_sms * 2, 32 * kRedoWarpsPerBlock, (size_t)tlen_pad * kRedoWarpsPerBlock, st>>>(
+        q, t, meta, diroff, scratch, ends, redo, redo_list, sc, tlen_pad, redo_base, redo_cap, counters);
+}
+
+}  // namespace rsa

@@ -1,0 +1,145 @@
+// kernels_tb.cuh -- traceback walker: direction nibbles -> run-length CIGAR bytes + start cell.
+//
+// One thread per pair, following gasal_get_tb<LOCAL> (reference GASAL2/src/kernels/get_tb.h:16-147)
+// step for step: the two-variable mode machine (op_select/op_shift, :74-82), the 63-capped run bytes
+// emitted end-to-start (:87-98,113-117), the running score that stops the walk on equality with the
+// alignment score (:100-103, N cells are credited +match), the inclusive start cell (:142-145) and the
+// byte count (:146).  The direction nibble itself comes from whichever DP kernel produced it; both
+// layouts decode to the reference's 4-bit code (common.cuh).
+#pragma once
+#include "common.cuh"
+#include "kernels_exact.cuh"
+#include "fast_layout.cuh"
+
+namespace rsa {
+
+struct TbCtx {
+    const uint8_t* q;
+    const uint8_t* t;
+    const uint8_t* dir;
+    int qlen, tlen;
+    int row_bytes;       // exact layout
+    bool fast;
+    FastGeom fg;         // fast layout
+    int half;            // fast layout: which 16-bit half of the packed words
+};
+
+__device__ __forceinline__ uint32_t tb_fetch(const TbCtx& c, int i, int j) {
+    if (!c.fast) {
+        const uint8_t b = c.dir[(size_t)i * c.row_bytes + (j >> 1)];
+        return (j & 1) ? (b >> 4) : (b & 0xFu);
+    }
+    // fast layout stores [open_f, open_e, not_diag, not_f] per cell; rebuild the reference code.
+    const uint32_t f = fast_fetch_flags(c.fg, c.dir, i, j, c.half);
+    const bool not_diag = f & 2u, not_f = f & 1u, open_e = f & 4u, open_f = f & 8u;
+    uint32_t lo2;
+    if (!not_diag) {
+        const uint32_t qb = nibble_of(c.q[j]), tb = nibble_of(c.t[i]);
+        const bool mism = (qb != tb) && qb != kWildcard && tb != kWildcard;  // tmp < diag <=> sub < 0
+        lo2 = mism ? 1u : 0u;
+    } else {
+        lo2 = not_f ? 2u : 3u;
+    }
+    return lo2 | (open_e ? 0u : 4u) | (open_f ? 0u : 8u);
+}
+
+// One walk.  Bytes 0..inline_cap-1 go to `inl`; if `full` != nullptr every byte also goes there.
+__device__ inline int tb_walk(const TbCtx& c, int score, int tend, int qend, const Scoring& sc,
+                              uint8_t* inl, int inline_cap, uint8_t* full, int* out_i, int* out_j) {
+    int i = tend, j = qend;
+    int sel = 3, sh = 0;
+    uint32_t prev = 0;
+    int count = 0, n_ops = 0, cur = 0;
+    while (i >= 0 && j >= 0) {
+        const uint32_t cell = tb_fetch(c, i, j);
+        const uint32_t op = (cell >> sh) & (uint32_t)sel;
+        const uint32_t out = (op == 0 || sel == 3) ? op : (uint32_t)sh;
+        sel = (op == 0 || (op == 1 && sel == 3)) ? 3 : 1;
+        sh = (op == 0 || (op == 1 && sel == 3)) ? 0 : ((op == 2 || op == 3) ? (int)op : sh);
+        if (count < 63 && out == prev) {
+            count++;
+        } else {
+            if (count > 0) {
+                const uint8_t b = (uint8_t)(prev | (uint32_t)(count << 2));
+                if (n_ops < inline_cap) inl[n_ops] = b;
+                if (full) full[n_ops] = b;
+                n_ops++;
+            }
+            count = 1;
+        }
+        if ((out == 2 || out == 3) && prev != out) cur -= sc.gap_oe;
+        else if (out == 2 || out == 3) cur -= sc.gap_ext;
+        else if (out == 1) cur -= sc.mismatch;
+        else cur += sc.match;
+        if (cur == score) break;
+        prev = out;
+        if (out != 3) i--;
+        if (out != 2) j--;
+    }
+    const uint8_t b = (uint8_t)(prev | (uint32_t)(count << 2));
+    if (n_ops < inline_cap) inl[n_ops] = b;
+    if (full) full[n_ops] = b;
+    n_ops++;
+    *out_i = i;
+    *out_j = j;
+    return n_ops;
+}
+
+// info word of PairMeta-side planning (host): status for pairs no DP kernel ran on
+constexpr int kTbThreads = 128;
+
+__global__ void __launch_bounds__(kTbThreads)
+tb_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
+          const PairMeta* __restrict__ meta, const uint32_t* __restrict__ info, int n,
+          const uint64_t* __restrict__ dir_off, const uint8_t* __restrict__ scratch,
+          const DpEnd* __restrict__ ends, rsa_ext_result_t* __restrict__ res, Scoring sc,
+          uint8_t* __restrict__ arena, unsigned long long* __restrict__ arena_used,
+          unsigned long long arena_cap) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= n) return;
+    const DpEnd e = ends[pi];
+    rsa_ext_result_t r;
+#pragma unroll
+    for (int k = 0; k < RSA_EXT_RLE_INLINE; ++k) r.rle[k] = 0;
+    if (!(e.flags & DPF_DONE)) {
+        // not aligned: empty sequence / window longer than max_target_len (host decided)
+        r.score = 0; r.query_start = -1; r.query_end = -1; r.ref_start = -1; r.ref_end = -1;
+        r.n_ops = 0; r.status = (e.flags & DPF_NO_SCRATCH) ? (int16_t)4 : (int16_t)(info[pi] >> 16);
+        res[pi] = r;
+        return;
+    }
+    const PairMeta m = meta[pi];
+    TbCtx c;
+    c.q = qbuf + m.qoff;
+    c.t = tbuf + m.toff;
+    c.dir = scratch + dir_off[pi];
+    c.qlen = m.qlen;
+    c.tlen = m.tlen;
+    c.fast = (e.flags & DPF_LAYOUT_FAST) != 0;
+    c.row_bytes = exact_row_bytes(m.qlen);
+    c.half = (int)(info[pi] & 1u);
+    c.fg = fast_geom(m.qlen);
+    int si, sj;
+    int n_ops = tb_walk(c, e.score, e.tend, e.qend, sc, r.rle, RSA_EXT_RLE_INLINE, nullptr, &si, &sj);
+    r.status = 0;
+    if (n_ops > RSA_EXT_RLE_INLINE) {
+        // rare: long CIGAR.  Reserve n_ops bytes in the chunk's arena and walk again writing all of them;
+        // the arena offset rides in the last 8 inline bytes.
+        const unsigned long long off = atomicAdd(arena_used, (unsigned long long)n_ops);
+        if (off + (unsigned long long)n_ops <= arena_cap) {
+            tb_walk(c, e.score, e.tend, e.qend, sc, r.rle, 0, arena + off, &si, &sj);
+            memcpy(&r.rle[RSA_EXT_RLE_INLINE - 8], &off, 8);
+        } else {
+            r.status = 2;  // arena exhausted: the engine re-runs this pair alone
+        }
+    }
+    r.score = e.score;
+    r.query_start = sj;
+    r.query_end = e.qend;
+    r.ref_start = si;
+    r.ref_end = e.tend;
+    r.n_ops = (int16_t)n_ops;
+    res[pi] = r;
+}
+
+}  // namespace rsa

@@ -1,0 +1,263 @@
+"""ctypes binding of librsa_ext.so (include/rsa_ext.h) and the host-side mirror of the reference's
+batch interface for the extension step.
+
+`ExtensionEngine.solve_ssw_on_gpu(queries, refs, match, mismatch, gap_open, gap_extend)` has the argument
+meaning and the result fields of the reference's
+
+    void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res>&, std::vector<std::string>& querys,
+                          std::vector<std::string>& refs, int match, int mismatch, int gap_open,
+                          int gap_extend)                               (reference src/gasal2_ssw.h:31-47)
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, constructing an
+engine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsa_ext.so")
+
+RLE_INLINE = 40
+FLAG_EXACT_ONLY = 1
+
+RESULT_DTYPE = np.dtype([
+    ("score", "<i4"), ("query_start", "<i4"), ("query_end", "<i4"), ("ref_start", "<i4"),
+    ("ref_end", "<i4"), ("n_ops", "<i2"), ("status", "<i2"), ("rle", "u1", (RLE_INLINE,)),
+])
+assert RESULT_DTYPE.itemsize == 64
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_query_len", C.c_int32), ("max_target_len", C.c_int32),
+                ("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32),
+                ("gap_extend", C.c_int32), ("flags", C.c_int32), ("scratch_bytes", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("pairs_fast", C.c_int64), ("pairs_exact", C.c_int64),
+                ("pairs_failed", C.c_int64), ("cells", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("dp_ms", C.c_double), ("tb_ms", C.c_double)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/rsa_ext.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "rsa_ext_create", "rsa_ext_destroy", "rsa_ext_last_error", "rsa_ext_submit", "rsa_ext_submit_ptrs",
+    "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
+    "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
+    "rsa_ext_get_stats", "rsa_ext_version",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load librsa_ext.so; raises if it was not built (run `make` or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first (make / "
+                           "__graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.rsa_ext_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.rsa_ext_create.restype = C.c_int
+    lib.rsa_ext_destroy.argtypes = [vp]
+    lib.rsa_ext_destroy.restype = None
+    lib.rsa_ext_last_error.argtypes = [vp]
+    lib.rsa_ext_last_error.restype = C.c_char_p
+    lib.rsa_ext_submit.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.rsa_ext_submit.restype = C.c_int
+    lib.rsa_ext_submit_ptrs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.rsa_ext_submit_ptrs.restype = C.c_int
+    lib.rsa_ext_poll.argtypes = [vp]
+    lib.rsa_ext_poll.restype = C.c_int
+    lib.rsa_ext_wait.argtypes = [vp]
+    lib.rsa_ext_wait.restype = C.c_int
+    lib.rsa_ext_rle_overflow.argtypes = [vp, i64, vp, i32]
+    lib.rsa_ext_rle_overflow.restype = C.c_int
+    lib.rsa_ext_rle_to_text.argtypes = [vp, i32, vp, i32]
+    lib.rsa_ext_rle_to_text.restype = C.c_int
+    lib.rsa_ext_stage_resident.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.rsa_ext_stage_resident.restype = C.c_int
+    lib.rsa_ext_run_resident.argtypes = [vp]
+    lib.rsa_ext_run_resident.restype = C.c_int
+    lib.rsa_ext_fetch_resident.argtypes = [vp, vp]
+    lib.rsa_ext_fetch_resident.restype = C.c_int
+    lib.rsa_ext_stream.argtypes = [vp]
+    lib.rsa_ext_stream.restype = vp
+    lib.rsa_ext_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.rsa_ext_get_stats.restype = C.c_int
+    lib.rsa_ext_version.argtypes = []
+    lib.rsa_ext_version.restype = C.c_int
+    lib.rsa_ext_plan_debug.argtypes = [i64, vp, vp, i64, C.c_int, vp]
+    lib.rsa_ext_plan_debug.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+@dataclass
+class GasalTmpRes:
+    """Field-for-field mirror of `struct gasal_tmp_res` (reference src/gasal2_ssw.h:31-38)."""
+
+    score: int
+    query_start: int
+    query_end: int
+    ref_start: int
+    ref_end: int
+    cigar_str: str
+
+    def astuple(self):
+        return (self.score, self.query_start, self.query_end, self.ref_start, self.ref_end, self.cigar_str)
+
+
+class ExtensionError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"rsa_ext status {status}: {msg}")
+        self.status = status
+
+
+def rle_to_text(rle: np.ndarray, n_ops: int) -> str:
+    """reference src/gasal2_ssw.cpp:184-243 (host CIGAR text), done by the library."""
+    lib = load_library()
+    rle = np.ascontiguousarray(rle, dtype=np.uint8)
+    out = C.create_string_buffer(16 * max(1, int(n_ops)) + 16)
+    w = lib.rsa_ext_rle_to_text(rle.ctypes.data, int(n_ops), C.cast(out, C.c_void_p), len(out))
+    if w < 0:
+        raise ExtensionError(w, "rle_to_text buffer too small")
+    return out.raw[:w].decode()
+
+
+class ExtensionEngine:
+    """One handle = one host worker's GPU context (the reference's per-thread_id GASAL storage,
+    src/gasal2_ssw.cpp:29,92-102)."""
+
+    def __init__(self, device: int = 0, match: int = 2, mismatch: int = 8, gap_open: int = 12,
+                 gap_extend: int = 1, max_query_len: int = 500, max_target_len: int = 2000,
+                 exact_only: bool = False, scratch_bytes: int = 0):
+        self.lib = load_library()
+        self.cfg = Config(device, max_query_len, max_target_len, match, mismatch, gap_open, gap_extend,
+                          FLAG_EXACT_ONLY if exact_only else 0, scratch_bytes)
+        h = C.c_void_p()
+        rc = self.lib.rsa_ext_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0:
+            raise ExtensionError(rc, self.lib.rsa_ext_last_error(None).decode())
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsa_ext_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise ExtensionError(rc, self.lib.rsa_ext_last_error(self.h).decode())
+
+    # ---- asynchronous C-ABI legs on packed buffers --------------------------------------------------
+    def submit(self, qbuf: np.ndarray, qoff: np.ndarray, tbuf: np.ndarray, toff: np.ndarray,
+               results: Optional[np.ndarray] = None) -> np.ndarray:
+        n = len(qoff) - 1
+        if results is None:
+            results = np.zeros(n, dtype=RESULT_DTYPE)
+        assert qbuf.dtype == np.uint8 and tbuf.dtype == np.uint8
+        assert qoff.dtype == np.int64 and toff.dtype == np.int64
+        self._keep = (qbuf, qoff, tbuf, toff, results)
+        self._check(self.lib.rsa_ext_submit(self.h, n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data,
+                                            toff.ctypes.data, results.ctypes.data))
+        return results
+
+    def submit_raw(self, n, qbuf_ptr, qoff_ptr, tbuf_ptr, toff_ptr, res_ptr):
+        self._check(self.lib.rsa_ext_submit(self.h, n, qbuf_ptr, qoff_ptr, tbuf_ptr, toff_ptr, res_ptr))
+
+    def poll(self) -> int:
+        return self.lib.rsa_ext_poll(self.h)
+
+    def wait(self):
+        self._check(self.lib.rsa_ext_wait(self.h))
+
+    def align_packed(self, qbuf, qoff, tbuf, toff) -> np.ndarray:
+        res = self.submit(qbuf, qoff, tbuf, toff)
+        self.wait()
+        return res
+
+    def full_rle(self, results: np.ndarray, i: int) -> np.ndarray:
+        n_ops = int(results["n_ops"][i])
+        if n_ops <= RLE_INLINE:
+            return results["rle"][i][:n_ops]
+        out = np.zeros(n_ops, np.uint8)
+        w = self.lib.rsa_ext_rle_overflow(self.h, i, out.ctypes.data, n_ops)
+        if w != n_ops:
+            raise ExtensionError(w, self.lib.rsa_ext_last_error(self.h).decode())
+        return out
+
+    def cigar(self, results: np.ndarray, i: int) -> str:
+        n_ops = int(results["n_ops"][i])
+        if n_ops <= 0:
+            return ""
+        return rle_to_text(self.full_rle(results, i), n_ops)
+
+    # ---- reference-shaped call --------------------------------------------------------------------
+    def solve_ssw_on_gpu(self, querys: Sequence[bytes], refs: Sequence[bytes]) -> List[GasalTmpRes]:
+        """Blocking batch call with the reference's semantics; scores were fixed at construction like
+        the reference fixes them on the first call per thread_id (gasal2_ssw.cpp:49-57)."""
+        if len(querys) != len(refs):
+            raise ValueError("querys and refs differ in length")  # reference: assert (gasal2_ssw.cpp:31)
+        from .workload import from_lists
+        b = from_lists([bytes(q) for q in querys], [bytes(t) for t in refs])
+        qbuf = b.qbuf if b.qbuf.size else np.zeros(1, np.uint8)
+        tbuf = b.tbuf if b.tbuf.size else np.zeros(1, np.uint8)
+        res = self.align_packed(qbuf, b.qoff, tbuf, b.toff)
+        return [GasalTmpRes(int(res["score"][i]), int(res["query_start"][i]), int(res["query_end"][i]),
+                            int(res["ref_start"][i]), int(res["ref_end"][i]), self.cigar(res, i))
+                for i in range(len(querys))]
+
+    # ---- device-resident legs -----------------------------------------------------------------------
+    def stage_resident(self, qbuf, qoff, tbuf, toff):
+        self._keep = (qbuf, qoff, tbuf, toff)
+        self._check(self.lib.rsa_ext_stage_resident(self.h, len(qoff) - 1, qbuf.ctypes.data, qoff.ctypes.data,
+                                                    tbuf.ctypes.data, toff.ctypes.data))
+
+    def run_resident(self):
+        self._check(self.lib.rsa_ext_run_resident(self.h))
+
+    def fetch_resident(self, n: int) -> np.ndarray:
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        self._check(self.lib.rsa_ext_fetch_resident(self.h, res.ctypes.data))
+        return res
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.rsa_ext_stream(self.h) or 0)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.rsa_ext_get_stats(self.h, C.byref(s)))
+        return s.asdict()
+
+
+def plan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, exact_only: bool = False) -> dict:
+    """Host-only planning probe (no CUDA call): how the first chunk of a batch would be routed."""
+    lib = load_library()
+    out = np.zeros(8, np.int64)
+    rc = lib.rsa_ext_plan_debug(len(qoff) - 1, qoff.ctypes.data, toff.ctypes.data, scratch_cap, int(exact_only),
+                                out.ctypes.data)
+    if rc != 0:
+        raise ExtensionError(rc, "plan_debug failed")
+    keys = ["pairs", "fast_pairs", "exact_pairs", "failed", "groups", "scratch_bytes", "fast_classes"]
+    return dict(zip(keys, out.tolist()))

@@ -1,0 +1,132 @@
+"""GPU suite: the CUDA path through the C ABI against the oracle, bit-exact (score, start/end, n_ops,
+CIGAR text) on seeded inputs, plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+
+from rabbitsalign_b200 import workload as W
+from parity_util import compare, oracle_arrays
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("adv_acgtn", W.adversarial_pairs, dict(n=6000, seed=101)),
+    ("adv_ac", W.adversarial_pairs, dict(n=6000, seed=102, alphabet=b"AC")),
+    ("adv_iupac", W.adversarial_pairs, dict(n=4000, seed=103, alphabet=b"ACGTNacgtnRYKMSW.-")),
+    ("adv_mid", W.adversarial_pairs, dict(n=3000, seed=104, max_q=200, max_t=400)),
+    ("ext150", W.extension_pairs, dict(n=3000, seed=105)),
+    ("ext150_var", W.extension_pairs, dict(n=2000, seed=106, fixed_query_len=False, indel_rate=0.01)),
+    ("ext250_indel", W.extension_pairs, dict(n=1500, seed=107, read_len=250, indel_rate=0.05, max_indel=4, fixed_query_len=False)),
+    ("ext150_N", W.extension_pairs, dict(n=2000, seed=108, n_rate=0.01)),
+    ("long", W.adversarial_pairs, dict(n=200, seed=109, max_q=500, max_t=2000)),
+    ("homopolymer", W.adversarial_pairs, dict(n=4000, seed=110, alphabet=b"AAAC", max_q=120, max_t=200)),
+]
+
+
+@pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
+def test_exact_kernel_parity(engine_exact, oracle_lib, name, gen, kw):
+    b = gen(**kw)
+    res = engine_exact.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(engine_exact, res, oracle_arrays(oracle_lib, b), b)
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
+def test_packed_kernel_parity(engine, oracle_lib, name, gen, kw):
+    b = gen(**kw)
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(engine, res, oracle_arrays(oracle_lib, b), b)
+    assert not bad, "\n".join(bad)
+    st = engine.stats()
+    assert st["kernel_launches"] > 0
+
+
+def test_solve_ssw_on_gpu_shape(engine, oracle_lib):
+    qs = [b"ACGTNCGTAC", b"ACGTACGTAC", b"AAAA", b"NNNN", b"ACGT"]
+    ts = [b"ACGTACGTAC", b"ACGTACGTAC", b"CCCC", b"ACGT", b"TTACGTTT"]
+    got = engine.solve_ssw_on_gpu(qs, ts)
+    assert [g.astuple() for g in got] == [o.astuple() for o in oracle_lib.align(qs, ts)]
+
+
+def test_query_too_long_is_an_error(engine):
+    from rabbitsalign_b200 import ExtensionError
+    with pytest.raises(ExtensionError) as ei:
+        engine.solve_ssw_on_gpu([b"A" * 501], [b"A" * 600])
+    assert ei.value.status == -3
+    # the handle stays usable
+    assert engine.solve_ssw_on_gpu([b"ACGT"], [b"ACGT"])[0].score == 8
+
+
+def test_window_longer_than_max_is_flagged(engine):
+    b = W.from_lists([b"ACGT" * 10, b"ACGT" * 10], [b"ACGT" * 600, b"ACGT" * 20])
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    assert res["status"][0] == 1 and res["n_ops"][0] == 0 and res["status"][1] == 0 and res["score"][1] == 80
+
+
+def test_other_scoring(oracle_lib):
+    from rabbitsalign_b200 import ExtensionEngine
+    kw = dict(match=1, mismatch=4, gap_open=6, gap_extend=2)
+    e = ExtensionEngine(**kw)
+    b = W.adversarial_pairs(4000, seed=120, max_q=150, max_t=250)
+    res = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(e, res, oracle_arrays(oracle_lib, b, **kw), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+
+
+def test_chunked_batch_equals_single_chunks(oracle_lib):
+    """A batch forced through many small chunks (tiny scratch budget) gives the same records."""
+    from rabbitsalign_b200 import ExtensionEngine
+    b = W.extension_pairs(1500, seed=130, fixed_query_len=False)
+    e = ExtensionEngine(scratch_bytes=24 << 20)
+    res = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+
+
+def test_resident_legs_match_submit(engine):
+    b = W.extension_pairs(2000, seed=140)
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    engine.stage_resident(b.qbuf, b.qoff, b.tbuf, b.toff)
+    engine.run_resident()
+    engine.run_resident()  # idempotent: re-running the kernels over the same inputs
+    res2 = engine.fetch_resident(b.n)
+    assert res.tobytes() == res2.tobytes()
+    st = engine.stats()
+    assert st["dp_ms"] > 0 and st["cells"] == b.cells
+
+
+def test_large_batch_properties(engine):
+    """Full-size-style check without the oracle: every accepted record's CIGAR consumes exactly the
+    reported spans and re-scores to the reported score (N-free input; SURVEY.md 8a invariants)."""
+    import re
+    b = W.fixed_pairs_fast(200_000, qlen=150, tlen=250, sub_rate=0.02, seed=150)
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    assert (res["status"] == 0).all() and (res["score"] > 0).all()
+    # order independence: the same pairs reversed give the same records reversed
+    idx = np.arange(b.n)[::-1]
+    q2 = b.qbuf.reshape(b.n, 150)[idx].reshape(-1).copy()
+    t2 = b.tbuf.reshape(b.n, 250)[idx].reshape(-1).copy()
+    res2 = engine.align_packed(q2, b.qoff, t2, b.toff)
+    assert res2[::-1].tobytes() == res.tobytes()
+    rng = np.random.default_rng(1)
+    q = b.qbuf.reshape(b.n, 150)
+    t = b.tbuf.reshape(b.n, 250)
+    for i in rng.integers(0, b.n, size=3000):
+        cig = engine.cigar(res, int(i))
+        ii, jj, s = int(res["ref_start"][i]), int(res["query_start"][i]), 0
+        for cnt, op in re.findall(r"(\d+)([MXDI])", cig):
+            cnt = int(cnt)
+            if op in "MX":
+                eq = q[i, jj:jj + cnt] == t[i, ii:ii + cnt]
+                assert eq.all() if op == "M" else (~eq).all()
+                s += 2 * cnt if op == "M" else -8 * cnt
+                ii += cnt
+                jj += cnt
+            else:
+                s -= 12 + (cnt - 1)
+                if op == "D":
+                    ii += cnt
+                else:
+                    jj += cnt
+        assert s == res["score"][i] and ii == res["ref_end"][i] + 1 and jj == res["query_end"][i] + 1
