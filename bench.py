@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- extension hot path benchmark (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (packed/exact DP kernels + traceback -> 64-byte records) over one
+synthetic batch shaped like BASELINE.json configs[1] (150 bp reads vs their NAM windows, 1% error, 5%
+mate-rescue windows).  Metric: extension GCUPS, cells = sum |q|*|t|.
+
+  value      device-resident: inputs already in HBM, K x rsa_ext_run_resident, CUDA events on the engine's
+             compute stream, max over ranks.
+  e2e        the same batch through the C ABI from pinned HOST buffers (rsa_ext_submit + rsa_ext_wait):
+             H2D of the ASCII + plan, kernels, D2H of the records, every step, wall clock.
+  roofline   see DESIGN.md: the DP kernel is bound by the integer/DPX issue rate, so `roofline_issue` carries
+             the meaningful fraction (ceiling measured live by tools/dpx_microbench); `roofline` (contract
+             format, bound "hbm") reports the algorithmic HBM traffic of the DP kernel against the measured
+             copy bandwidth.
+  cpu_baseline / --impl reference
+             the reference's own CPU extension path (Aligner::align = SSW, compiled from /root/reference
+             into oracle/_ref) on the host cores, bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "extension_gcups"
+UNIT = "GCUPS"
+
+
+def workload_desc(pairs, read_len):
+    return (f"BASELINE configs[1]-shaped extension batch: {pairs} (query,window) pairs per GPU per step, "
+            f"{read_len} bp reads, windows read+flanks(0..50) (95%) / mate-rescue windows (5%), 1% substitutions, "
+            f"0.2%/bp indel events; cells = sum |q|*|t|")
+
+
+def make_batch(pairs, read_len, seed):
+    from rabbitsalign_b200 import workload as W
+    return W.extension_pairs_fast(pairs, read_len=read_len, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(batch, threads, steps=1, warmup=0):
+    """Time the reference's CPU extension path on `batch`; returns (gcups, kind, seconds_per_step)."""
+    import oracle
+    ssw = oracle.ssw_reference()
+    if ssw is not None:
+        kind = "reference"
+
+        def run():
+            ssw.align_packed(batch.qbuf, batch.qoff, batch.tbuf, batch.toff, threads=threads)
+    else:
+        kind = "port"
+        olib = oracle.restatement()
+        bounds = np.linspace(0, batch.n, threads + 1).astype(int)
+        parts = [batch.slice(int(bounds[k]), int(bounds[k + 1])) for k in range(threads) if bounds[k + 1] > bounds[k]]
+
+        def run():
+            ths = [threading.Thread(target=olib.align_packed, args=(p.qbuf, p.qoff, p.tbuf, p.toff)) for p in parts]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return batch.cells / dt / 1e9, kind, dt
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def issue_ceiling():
+    """Live integer/DPX issue-rate ceiling: tools/dpx_microbench runs the bare packed cell recipe (no memory,
+    no shuffles) on every SM; returns cells/clk/SM and the chip GCUPS it reached, or None."""
+    exe = os.path.join(ROOT, "tools", "dpx_microbench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "--quick"], capture_output=True, text=True, timeout=120).stdout
+    except Exception:  # noqa: BLE001
+        return None
+    best = None
+    dpx = None
+    for ln in out.splitlines():
+        try:
+            r = json.loads(ln)
+        except ValueError:
+            continue
+        if r.get("test", "").startswith("SW cell recipe"):
+            if best is None or r["cells_per_clk_per_sm"] > best["cells_per_clk_per_sm"]:
+                best = r
+        if r.get("test") == "VIMNMX3.S16x2":
+            dpx = max(dpx or 0.0, r["warp_instr_per_clk_per_sm"])
+    if best is None:
+        return None
+    best["dpx_warp_instr_per_clk_per_sm"] = dpx
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="pairs in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world) if world > 1 else args.gpus
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU) -------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = min(args.pairs, args.cpu_sample)
+        b = make_batch(sample, args.read_len, seed=43)
+        g, kind, dt = cpu_reference_run(b, cores, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": g, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s16/u8 SSE2", "data": "synthetic",
+            "config": {"workload": workload_desc(args.pairs, args.read_len),
+                       "note": "reference CPU path (Aligner::align: SSW striped SW + banded traceback + end bonus) "
+                               "on all host cores; no GPU involved, so the value does not grow with --gpus"},
+            "cpu_baseline": {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{sample} pairs of the step's batch per step"},
+            "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm ---------------------------
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this benchmark has no CPU path"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from rabbitsalign_b200 import ExtensionEngine
+    from rabbitsalign_b200.ext import RESULT_DTYPE
+
+    batch = make_batch(args.pairs, args.read_len, seed=43 + rank)
+    eng = ExtensionEngine(device=local_rank)
+
+    # pinned host copies (the C ABI copies straight from/to pinned memory)
+    def pinned(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return t, v
+    keep = []
+    tq, qbuf = pinned(batch.qbuf); keep.append(tq)
+    tt, tbuf = pinned(batch.tbuf); keep.append(tt)
+    tqo, qoff = pinned(batch.qoff); keep.append(tqo)
+    tto, toff = pinned(batch.toff); keep.append(tto)
+    tres = torch.empty(batch.n * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    results = tres.numpy().view(RESULT_DTYPE)
+
+    # ---- device-resident leg: `value` ------------------------------------------------------------------
+    eng.stage_resident(qbuf, qoff, tbuf, toff)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+    for _ in range(max(3, args.warmup)):
+        eng.run_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.run_resident()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    st = eng.stats()  # dp_ms / tb_ms of the last step (events around the kernels)
+    clocks = sampler.stop()
+    launches_per_step = st["kernel_launches"]
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    cells = torch.tensor([float(batch.cells)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+    ms_step = float(t_ms.item()) / args.steps
+    total_cells = float(cells.item())
+    value = total_cells / (ms_step * 1e-3) / 1e9
+    res_resident = eng.fetch_resident(batch.n)
+
+    # ---- end-to-end leg through the C ABI from host buffers ----------------------------------------------
+    for _ in range(2):
+        eng.submit(qbuf, qoff, tbuf, toff, results)
+        eng.wait()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.submit(qbuf, qoff, tbuf, toff, results)
+        eng.wait()
+    dt = time.perf_counter() - t0
+    st_e2e = eng.stats()
+    t_e = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = total_cells / (float(t_e.item()) / args.steps) / 1e9
+    same = bool(results.tobytes() == res_resident.tobytes())
+    ok = bool((results["status"] == 0).all() and (results["score"] > 0).mean() > 0.99)
+
+    if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline --------------------------------------------------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    dp_ms = st["dp_ms"]            # DP kernels of one step on this rank (CUDA events on the compute stream)
+    tb_ms = st["tb_ms"]
+    # algorithmic HBM bytes of the DP phase per pair: ASCII in, direction nibbles out, 16-byte end record
+    ql = np.diff(batch.qoff); tl = np.diff(batch.toff)
+    dp_bytes = float(np.sum(ql + tl) + np.sum(ql * tl) / 2 + 16 * batch.n)
+    hbm_achieved = dp_bytes / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "fast_dp_kernel<C> (packed s16x2 DP + direction nibbles)",
+                "achieved": hbm_achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": (hbm_achieved / peaks["hbm_gbs"]) if hbm_achieved else None, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "note": "issue-bound by design (SURVEY 8d): see roofline_issue for the binding ceiling"}
+    ceil = issue_ceiling()
+    dp_gcups = batch.cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+    roofline_issue = None
+    if ceil and dp_gcups:
+        roofline_issue = {
+            "bound": "int/DPX issue", "achieved": dp_gcups, "peak": ceil["chip_gcups"], "unit": "GCUPS",
+            "frac": dp_gcups / ceil["chip_gcups"],
+            "peak_source": "tools/dpx_microbench, same process tree, bare packed cell recipe on all SMs",
+            "ceiling_cells_per_clk_per_sm": ceil["cells_per_clk_per_sm"],
+            "dpx_warp_instr_per_clk_per_sm": ceil.get("dpx_warp_instr_per_clk_per_sm"),
+            "dp_ms": dp_ms, "tb_ms": tb_ms}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and n_gpus == 1:
+        sample = min(batch.n, args.cpu_sample)
+        g, kind, _ = cpu_reference_run(batch.slice(0, sample), cores)
+        cpu = {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {sample} pairs of the step's batch, one pass"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "s16x2", "data": "synthetic",
+        "config": {"workload": workload_desc(args.pairs, args.read_len), "pairs_per_gpu": batch.n,
+                   "cells_per_gpu_per_step": batch.cells, "l2": "inputs+direction tiles per step (>20 GB) exceed the 126 MB L2",
+                   "pairs_per_s": batch.n * n_gpus / (ms_step * 1e-3),
+                   "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"]},
+                   "resident_equals_e2e_records": same, "records_sane": ok},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
+                "d2h_bytes_per_step": st_e2e["d2h_bytes"]},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

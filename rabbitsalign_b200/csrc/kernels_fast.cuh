@@ -110,6 +110,14 @@ __host__ __device__ inline uint32_t profile_word(uint32_t code, const FastConsts
     return 0u;
 }
 
+// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the chosen byte (the
+// __byte_perm intrinsic masks that bit away).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t bitsel(uint32_t mask, uint32_t a, uint32_t b) {  // mask ? a : b, one LOP3
     return (a & mask) | (b & ~mask);
 }
@@ -149,7 +157,7 @@ struct FastDp {
                 for (int c = 0; c < C; ++c) {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
                     if (c < C - 1 || wide) {
-                        uint32_t sub = __byte_perm(pr.x, pr.y, qsel[c]);
+                        uint32_t sub = prmt(pr.x, pr.y, qsel[c]);
                         if (HASN) sub = bitsel(nmask[c], sub, k.x_pair);
                         const uint32_t tmp = diag + sub + k.neg_x;
                         const uint32_t tg = diag + sub + k.neg_xoe;

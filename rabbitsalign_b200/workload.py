@@ -174,3 +174,53 @@ def adversarial_pairs(n: int, seed: int = 7, max_q: int = 60, max_t: int = 90,
     qoff = np.zeros(n + 1, np.int64); qoff[1:] = np.cumsum([len(x) for x in qs])
     toff = np.zeros(n + 1, np.int64); toff[1:] = np.cumsum([len(x) for x in ts])
     return PairBatch(np.concatenate(qs), qoff, np.concatenate(ts), toff)
+
+
+def extension_pairs_fast(n: int, read_len: int = 150, sub_rate: float = 0.01, indel_rate: float = 0.002,
+                         max_indel: int = 3, rescue_frac: float = 0.05, seed: int = 43,
+                         chunk: int = 1 << 16) -> PairBatch:
+    """Vectorised version of extension_pairs for bench-sized batches (BASELINE.json configs[1] shape):
+    fixed-length reads; windows = 0..50 + read_len + 0..50 (90% of flanks are the full 50, as
+    src/pc.cpp:231-239 clips them only at contig ends), `rescue_frac` mate-rescue windows with longer
+    flanks; per read substitutions at `sub_rate` and at most one indel event (probability
+    read_len*indel_rate, length 1..max_indel)."""
+    rng = np.random.default_rng(seed)
+    qparts, tparts, tlens = [], [], []
+    maxw = read_len + 150 + 100 + max_indel
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        rescue = rng.random(m) < rescue_frac
+        left = np.where(rng.random(m) < 0.9, 50, rng.integers(0, 50, size=m))
+        right = np.where(rng.random(m) < 0.9, 50, rng.integers(0, 50, size=m))
+        left = np.where(rescue, rng.integers(0, 150, size=m), left)
+        right = np.where(rescue, rng.integers(50, 100, size=m), right)
+        tlen = left + read_len + right
+        T = _ACGT[rng.integers(0, 4, size=(m, maxw), dtype=np.uint8)]
+        # read = window[left + j + shift(j)]
+        ev = rng.random(m) < min(1.0, read_len * indel_rate)
+        is_del = rng.random(m) < 0.5
+        k = rng.integers(1, max_indel + 1, size=m)
+        p = rng.integers(1, read_len - max_indel - 1, size=m)
+        j = np.arange(read_len)[None, :]
+        shift = np.zeros((m, read_len), dtype=np.int64)
+        dmask = (ev & is_del)[:, None] & (j >= p[:, None])
+        shift = np.where(dmask, k[:, None], shift)                      # deletion: skip k window bases
+        imask = (ev & ~is_del)[:, None] & (j >= (p + k)[:, None])
+        shift = np.where(imask, -k[:, None], shift)                     # insertion: k extra read bases
+        idx = left[:, None] + j + shift
+        Q = np.take_along_axis(T, idx, axis=1)
+        ins = (ev & ~is_del)[:, None] & (j >= p[:, None]) & (j < (p + k)[:, None])
+        Q = np.where(ins, _ACGT[rng.integers(0, 4, size=(m, read_len), dtype=np.uint8)], Q)
+        if sub_rate > 0:
+            sm = rng.random((m, read_len)) < sub_rate
+            sh = rng.integers(1, 4, size=(m, read_len))
+            Q = np.where(sm, _ACGT[(_CODE[Q] + sh) % 4], Q)
+        keep = np.arange(maxw)[None, :] < tlen[:, None]
+        tparts.append(T[keep])
+        qparts.append(np.ascontiguousarray(Q, dtype=np.uint8).reshape(-1))
+        tlens.append(tlen)
+    tl = np.concatenate(tlens)
+    qoff = np.arange(n + 1, dtype=np.int64) * read_len
+    toff = np.zeros(n + 1, np.int64)
+    toff[1:] = np.cumsum(tl)
+    return PairBatch(np.concatenate(qparts), qoff, np.concatenate(tparts).astype(np.uint8), toff)

@@ -1,0 +1,188 @@
+// tools/dpx_microbench.cu -- issue-rate microbenchmark behind the "sm_100a integer/DPX GCUPS ceiling".
+//
+// MEASURED_PEAKS.json has HBM and bf16 numbers only; the packed Smith-Waterman kernel is bounded by the
+// integer/DPX issue rate instead.  Each test keeps 8 independent dependency chains per thread (latency
+// hidden) and runs on every SM with enough warps to saturate the schedulers; it reports warp-instructions
+// per clock per SM (from clock64 deltas) and per second for the whole chip (from CUDA events).
+//
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o dpx_microbench dpx_microbench.cu && ./dpx_microbench
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+static int g_iters = 32768;
+constexpr int CH = 8;
+
+enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL, N_OPS };
+static const char* kNames[N_OPS] = {"VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "IADD3", "LOP3", "PRMT",
+                                    "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (19 instr / 2 cells)"};
+static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0};
+
+template <int OP>
+__global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+    uint32_t a[CH], b = in[0], c = in[1], d = in[2];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) a[k] = in[3 + k] + threadIdx.x;
+    uint32_t m[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) m[k] = a[k] ^ 0x5555u;
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            if (OP == VIMNMX3) a[k] = __vimax3_s16x2(a[k], b, c);
+            else if (OP == VIADDMNMX) a[k] = __viaddmax_s16x2(a[k], b, c);
+            else if (OP == VIMNMX) a[k] = __vmaxs2(a[k], b);
+            else if (OP == VIADD16) a[k] = __vadd2(a[k], b);
+            else if (OP == IADD3) a[k] = a[k] + b - c;
+            else if (OP == LOP3) a[k] = (a[k] & b) | (c & ~a[k]);
+            else if (OP == PRMT) a[k] = __byte_perm(a[k], b, c);
+            else if (OP == IMAD) a[k] = a[k] * 3u + b;
+            else if (OP == SHF) a[k] = __funnelshift_r(a[k], b, 5);
+            else if (OP == MIX_ALU_IMAD) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = m[k] * 3u + b; }
+            else if (OP == MIX_DPX_IMAD) { a[k] = __vimax3_s16x2(a[k], b, c); m[k] = m[k] * 3u + b; }
+        }
+        b += d;  // loop-variant operand (1 extra instruction per iteration, amortised over CH)
+    }
+    const unsigned long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) s += a[k] + m[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// The packed cell recipe of kernels_fast.cuh, with the same data flow (biased halves, IADD3 flag trick,
+// bit-selects), on 8 independent columns per thread: what one lane does per target row.
+__global__ void bench_cell(uint32_t* out, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+    uint32_t Hp[CH], E[CH], cb[CH], qsel[CH];
+    const uint32_t zero = in[0], negx = in[1], negxoe = in[2], nege = in[3], kf = in[4], ke = in[5], kd = in[6], kn = in[7];
+    uint32_t px = in[8] + threadIdx.x, py = in[9];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) { Hp[k] = zero; E[k] = zero; cb[k] = zero; qsel[k] = in[10 + k]; }
+    uint32_t F = zero, diag = zero, acc = 0, rm = zero, sink = 0;
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            uint32_t sub; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sub) : "r"(px), "r"(py), "r"(qsel[k]));
+            const uint32_t tmp = diag + sub + negx;
+            const uint32_t tg = diag + sub + negxoe;
+            const uint32_t e = E[k];
+            const uint32_t u = __vimax3_s16x2(F, e, zero);
+            const uint32_t h = __vmaxs2(tmp, u);
+            const uint32_t fn = __viaddmax_s16x2(F, nege, tg);
+            const uint32_t en = __viaddmax_s16x2(e, nege, tg);
+            const uint32_t fo = fn - F + kf, eo = en - e + ke, nd = h - tmp + kd, nf = u - F + kn;
+            uint32_t fl = (fo & 0x80008000u) | (eo & ~0x80008000u);
+            fl = (fl & 0xC000C000u) | (nd & ~0xC000C000u);
+            fl = (fl & 0xE000E000u) | (nf & ~0xE000E000u);
+            acc = (fl & 0xF000F000u) | ((acc >> 4) & ~0xF000F000u);
+            cb[k] = __vmaxs2(cb[k], h);
+            rm = __vmaxs2(rm, h);
+            diag = Hp[k];
+            Hp[k] = h;
+            E[k] = en;
+            F = fn;
+            if ((k & 3) == 3) { sink ^= acc; acc = 0; }
+        }
+        px += py;
+    }
+    const unsigned long long t1 = clock64();
+    uint32_t s = sink + rm + F;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) s += Hp[k] + E[k] + cb[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d_in, unsigned long long* d_cyc, int sm_khz) {
+    const int blocks = n_sms * blocks_per_sm;
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0));
+    CHECK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 3; ++rep) {
+        CHECK(cudaEventRecord(e0));
+        if (OP == CELL) bench_cell<<<blocks, threads>>>(d_out, d_in, d_cyc, g_iters);
+        else bench<OP><<<blocks, threads>>>(d_out, d_in, d_cyc, g_iters);
+        CHECK(cudaEventRecord(e1));
+        CHECK(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<unsigned long long> cyc(blocks);
+    CHECK(cudaMemcpy(cyc.data(), d_cyc, sizeof(unsigned long long) * blocks, cudaMemcpyDeviceToHost));
+    double mean = 0;
+    for (auto c : cyc) mean += (double)c;
+    mean /= blocks;
+    const int ITERS = g_iters;
+    const double warps_per_sm = (double)blocks_per_sm * threads / 32.0;
+    if (OP == CELL) {
+        const double cellpairs = (double)ITERS * CH;  // per thread
+        const double cells_per_clk_sm = 2.0 * cellpairs * 32.0 * warps_per_sm / mean;
+        const double gcups = 2.0 * cellpairs * (double)blocks * threads / (ms * 1e-3) / 1e9;
+        printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"cells_per_clk_per_sm\": %.2f, \"clk_per_cellpair_per_smsp_warp\": %.2f, "
+               "\"chip_gcups\": %.1f, \"ms\": %.3f, \"eff_mhz\": %.0f}\n",
+               kNames[OP], warps_per_sm, cells_per_clk_sm, mean / cellpairs / (warps_per_sm / 4.0), gcups, ms,
+               mean / (ms * 1e-3) / 1e6);
+    } else {
+        const double instr = (double)ITERS * kInstrPerIter[OP];  // per warp
+        const double ipc_sm = instr * warps_per_sm / mean;
+        const double chip = instr * (double)blocks * threads / 32.0 / (ms * 1e-3);
+        printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"warp_instr_per_clk_per_sm\": %.3f, \"chip_warp_ginstr_per_s\": %.1f, "
+               "\"ms\": %.3f, \"eff_mhz\": %.0f}\n",
+               kNames[OP], warps_per_sm, ipc_sm, chip / 1e9, ms, mean / (ms * 1e-3) / 1e6);
+    }
+    (void)sm_khz;
+}
+
+int main(int argc, char** argv) {
+    const bool quick = argc > 1 && std::string(argv[1]) == "--quick";
+    cudaDeviceProp prop;
+    CHECK(cudaGetDeviceProperties(&prop, 0));
+    const int n_sms = prop.multiProcessorCount;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, n_sms, prop.clockRate);
+    uint32_t *d_out, *d_in;
+    unsigned long long* d_cyc;
+    CHECK(cudaMalloc(&d_out, sizeof(uint32_t) * n_sms * 8 * 1024));
+    CHECK(cudaMalloc(&d_cyc, sizeof(unsigned long long) * n_sms * 8));
+    std::vector<uint32_t> in(64);
+    in[0] = 0x00400040u; in[1] = 0u - 8u * 0x10001u; in[2] = 0u - 20u * 0x10001u; in[3] = 0xFFFFFFFFu;
+    in[4] = 0x80008000u; in[5] = 0x40004000u; in[6] = 0x1FFF1FFFu; in[7] = 0x0FFF0FFFu; in[8] = 0x0A000000u; in[9] = 0x00000A00u;
+    for (int k = 10; k < 64; ++k) in[k] = 0x9480u + (k & 3) + ((k & 3) << 4);
+    CHECK(cudaMalloc(&d_in, sizeof(uint32_t) * 64));
+    CHECK(cudaMemcpy(d_in, in.data(), sizeof(uint32_t) * 64, cudaMemcpyHostToDevice));
+    // ramp the clocks before measuring
+    g_iters = 1 << 18;
+    bench<IMAD><<<n_sms * 2, 256>>>(d_out, d_in, d_cyc, g_iters);
+    CHECK(cudaDeviceSynchronize());
+    g_iters = quick ? (1 << 16) : (1 << 15);
+    for (int threads : {256, 512}) {
+        const int bps = 2;
+        run<VIMNMX3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+        if (!quick) {
+            run<VIADDMNMX>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<VIMNMX>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<VIADD16>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<IADD3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<LOP3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<PRMT>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<SHF>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_DPX_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+        }
+        run<CELL>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+    }
+    return 0;
+}
