@@ -132,6 +132,10 @@ int rsa_ext_get_stats(const rsa_ext_t *h, rsa_ext_stats_t *out);
 
 int rsa_ext_version(void);
 
+/* Number of usable CUDA devices (0 without a driver/GPU): lets a host pipeline spread its workers over the
+ * GPUs of one box (the reference is single-device, src/gasal2_ssw.cpp:34). */
+int rsa_ext_device_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,115 @@
+// integration/gasal2_ssw.cpp -- solve_ssw_on_gpu on top of the C ABI (include/rsa_ext.h).
+//
+// Behaviour kept from the reference's src/gasal2_ssw.cpp:19-256:
+//   * one GPU context per worker `thread_id` (< THREAD_NUM_MAX), created on the first call with that call's
+//     scores (:29-57,92-102) and never re-configured afterwards;
+//   * the result vector is resized to the batch and overwritten (:33);
+//   * a query longer than MAX_QUERY_LEN prints the same message and exit(0)s (:84-87); a CUDA failure prints
+//     and exit(EXIT_FAILURE)s (GASAL2/src/gasal.h:15-22);
+//   * blocking call; CIGAR text as the reference prints it (:184-243).
+// Differences: any batch size, storage is released at process exit, and with several GPUs visible the
+// workers are spread over them (thread_id % device count; RSA_EXT_DEVICES=n caps the count) -- the
+// reference uses device 0 only (:34).
+#include "gasal2_ssw.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "rsa_ext.h"
+
+namespace {
+
+struct Worker {
+    rsa_ext_t *h = nullptr;
+    std::vector<const char *> qp, tp;
+    std::vector<int32_t> ql, tl;
+    std::vector<rsa_ext_result_t> res;
+    std::vector<uint8_t> rle;
+    ~Worker() { if (h) rsa_ext_destroy(h); }
+};
+
+Worker g_workers[THREAD_NUM_MAX];
+std::mutex g_create_mutex;
+
+[[noreturn]] void die(const char *what, rsa_ext_t *h) {
+    fprintf(stderr, "[RSA_EXT ERROR:] %s: %s\n", what, rsa_ext_last_error(h));
+    exit(EXIT_FAILURE);
+}
+
+int device_count_cap() {
+    const char *e = getenv("RSA_EXT_DEVICES");
+    return e ? atoi(e) : 0;
+}
+
+}  // namespace
+
+extern "C" int rsa_ext_device_count(void);  // small helper exported by librsa_ext.so
+
+void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
+                      std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
+                      int gap_extend_score) {
+    assert(thread_id >= 0 && thread_id < THREAD_NUM_MAX);
+    assert(query_seqs.size() == target_seqs.size());
+    Worker &w = g_workers[thread_id];
+    const size_t n = query_seqs.size();
+    gasal_results.resize(n);
+    if (n == 0) return;
+
+    if (!w.h) {
+        std::lock_guard<std::mutex> lock(g_create_mutex);
+        int ndev = rsa_ext_device_count();
+        const int cap = device_count_cap();
+        if (cap > 0 && cap < ndev) ndev = cap;
+        rsa_ext_config_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.device = ndev > 0 ? thread_id % ndev : 0;
+        cfg.max_query_len = MAX_QUERY_LEN;
+        cfg.max_target_len = MAX_TARGET_LEN;
+        cfg.match = match_score;
+        cfg.mismatch = mismatch_score;
+        cfg.gap_open = gap_open_score;
+        cfg.gap_extend = gap_extend_score;
+        if (rsa_ext_create(&cfg, &w.h) != RSA_EXT_OK) die("rsa_ext_create", nullptr);
+    }
+
+    w.qp.resize(n); w.tp.resize(n); w.ql.resize(n); w.tl.resize(n); w.res.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        w.qp[i] = query_seqs[i].data(); w.ql[i] = (int32_t)query_seqs[i].size();
+        w.tp[i] = target_seqs[i].data(); w.tl[i] = (int32_t)target_seqs[i].size();
+    }
+    int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
+    if (rc == RSA_EXT_ERR_QUERY_LEN) {
+        size_t mx = 0;
+        for (size_t i = 0; i < n; ++i) mx = MAX(mx, query_seqs[i].length());
+        std::cerr << "gasal2 : read size is too big, " << mx << " > " << MAX_QUERY_LEN << std::endl;
+        exit(0);
+    }
+    if (rc != RSA_EXT_OK) die("rsa_ext_submit_ptrs", w.h);
+    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+
+    char text[4096];
+    for (size_t i = 0; i < n; ++i) {
+        const rsa_ext_result_t &r = w.res[i];
+        const uint8_t *rle = r.rle;
+        if (r.n_ops > RSA_EXT_RLE_INLINE) {
+            w.rle.resize((size_t)r.n_ops);
+            if (rsa_ext_rle_overflow(w.h, (int64_t)i, w.rle.data(), r.n_ops) != r.n_ops) die("rsa_ext_rle_overflow", w.h);
+            rle = w.rle.data();
+        }
+        std::string cigar;
+        if (r.n_ops > 0) {
+            int len = rsa_ext_rle_to_text(rle, r.n_ops, text, (int32_t)sizeof text);
+            if (len < 0) {
+                std::vector<char> big((size_t)r.n_ops * 8 + 16);
+                len = rsa_ext_rle_to_text(rle, r.n_ops, big.data(), (int32_t)big.size());
+                cigar.assign(big.data(), (size_t)(len > 0 ? len : 0));
+            } else {
+                cigar.assign(text, (size_t)len);
+            }
+        }
+        gasal_results[i] = {r.score, r.query_start, r.query_end, r.ref_start, r.ref_end, std::move(cigar)};
+    }
+}

@@ -516,6 +516,12 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
 
 extern "C" int rsa_ext_version(void) { return 1; }
 
+// number of usable CUDA devices (0 when there is no driver/GPU)
+extern "C" int rsa_ext_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" const char* rsa_ext_last_error(const rsa_ext_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
