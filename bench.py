@@ -338,7 +338,8 @@ def main():
         "config": {"workload": workload_desc(args.pairs, args.read_len), "pairs_per_gpu": batch.n,
                    "cells_per_gpu_per_step": batch.cells, "l2": "inputs+direction tiles per step (>20 GB) exceed the 126 MB L2",
                    "pairs_per_s": batch.n * n_gpus / (ms_step * 1e-3),
-                   "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"]},
+                   "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"],
+                               "redo_last_chunk": st["pairs_redo"]},
                    "resident_equals_e2e_records": same, "records_sane": ok},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],

@@ -127,6 +127,8 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
     double dp_ms;         /* device time of the DP kernels of the last run_resident (CUDA events) */
     double tb_ms;         /* device time of the traceback kernels */
+    int64_t pairs_redo;   /* pairs the packed kernel handed to the exact kernel at run time (ties on the maximum,
+                             symbols outside ACGTN); resident runs: last chunk only */
 } rsa_ext_stats_t;
 int rsa_ext_get_stats(const rsa_ext_t *h, rsa_ext_stats_t *out);
 

@@ -1,0 +1,61 @@
+#!/bin/bash
+# integration/build.sh -- build the reference's host pipeline around the drop-in boundary.
+#
+# Compiles the reference's own host sources where they lie under $REF_ROOT (CMakeLists.txt:71-93 minus
+# src/gasal2_ssw.cpp; nothing is copied into this repo) and links them three ways into integration/_build/
+# (git-ignored, travels to the GPU box with the snapshot):
+#
+#   rabbitsalign_b200     integration/gasal2_ssw.cpp + librsa_ext.so     the product drop-in (needs a GPU)
+#   rabbitsalign_gasalref oracle/_ref/libgasal_ref512.so behind solve_ssw_on_gpu: the reference's own GASAL2
+#                         kernels compiled for the host = golden-SAM generator (CPU only, test infrastructure)
+#   rabbitsalign_cpussw   solve_ssw_on_gpu returns failed records -> every extension takes the reference's
+#                         CPU SSW path (Aligner::align): the end-to-end CPU baseline (test/bench infrastructure)
+#
+# The reference's src/gasal2_ssw.h is pre-empted by force-including integration/gasal2_ssw.h (same include
+# guard), so src/pc.cpp, src/aligner.hpp and ext/ssw/ssw_cpp.h compile unedited.  Three build-time stand-ins
+# are generated under _build/gen/: zstr.hpp (the reference fetches zstr from GitHub at configure time,
+# CMakeLists.txt:32-37; plain std::ifstream is enough for uncompressed FASTA), version.hpp and buildconfig.hpp
+# (configured from src/*.in by CMake).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(dirname "$HERE")"
+REF_ROOT="${REF_ROOT:-/root/reference}"
+OUT="$HERE/_build"
+CXX="${CXX:-/usr/bin/g++}"
+CC="${CC:-/usr/bin/gcc}"
+[ -d "$REF_ROOT/src" ] || { echo "integration/build.sh: $REF_ROOT absent - keeping prebuilt _build (if any)"; exit 0; }
+mkdir -p "$OUT/gen" "$OUT/obj"
+
+cat > "$OUT/gen/zstr.hpp" <<'EOS'
+#pragma once
+#include <fstream>
+namespace zstr { using ifstream = std::ifstream; }
+EOS
+sed 's/@PROJECT_VERSION@/0.11.0-b200/' "$REF_ROOT/src/version.hpp.in" > "$OUT/gen/version.hpp"
+sed 's/@CMAKE_BUILD_TYPE@/Release/' "$REF_ROOT/src/buildconfig.hpp.in" > "$OUT/gen/buildconfig.hpp"
+
+FLAGS="-O3 -march=x86-64-v3 -std=c++17 -w -pthread -DNDEBUG -I$OUT/gen -I$REF_ROOT/src -I$REF_ROOT/ext -I$ROOT/include -I$HERE -include $HERE/gasal2_ssw.h"
+SRCS="refs fastq cmdline index indexparameters sam paf pc aln cigar aligner nam randstrobes readlen version io main"
+pids=()
+for s in $SRCS; do
+  ( [ "$OUT/obj/$s.o" -nt "$REF_ROOT/src/$s.cpp" ] && [ "$OUT/obj/$s.o" -nt "$HERE/gasal2_ssw.h" ] || $CXX $FLAGS -c "$REF_ROOT/src/$s.cpp" -o "$OUT/obj/$s.o" ) &
+  pids+=($!)
+done
+( $CXX $FLAGS -c "$REF_ROOT/ext/ssw/ssw_cpp.cpp" -o "$OUT/obj/ssw_cpp.o" ) & pids+=($!)
+( $CC -O3 -march=x86-64-v3 -w -c "$REF_ROOT/ext/ssw/ssw.c" -o "$OUT/obj/ssw.o" ) & pids+=($!)
+( $CC -O3 -march=x86-64-v3 -w -c "$REF_ROOT/ext/xxhash.c" -o "$OUT/obj/xxhash.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+
+OBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do echo "$OUT/obj/$s.o"; done)
+# 1) the product drop-in
+$CXX $FLAGS -c "$HERE/gasal2_ssw.cpp" -o "$OUT/obj/veneer.o"
+$CXX -o "$OUT/rabbitsalign_b200" $OBJS "$OUT/obj/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# 2) golden generator: the reference's kernels compiled for the host
+$CXX $FLAGS -c "$HERE/solve_gasalref.cpp" -o "$OUT/obj/solve_gasalref.o"
+$CXX -o "$OUT/rabbitsalign_gasalref" $OBJS "$OUT/obj/solve_gasalref.o" "$ROOT/oracle/_ref/libgasal_ref512.so" \
+     -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+# 3) CPU-SSW path
+$CXX $FLAGS -c "$HERE/solve_cpussw.cpp" -o "$OUT/obj/solve_cpussw.o"
+$CXX -o "$OUT/rabbitsalign_cpussw" $OBJS "$OUT/obj/solve_cpussw.o" -lz -lpthread
+ls -la "$OUT"/rabbitsalign_*

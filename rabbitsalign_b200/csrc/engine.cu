@@ -367,7 +367,7 @@ void launch_exact(cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, int li
 // Enqueue every kernel of one chunk on `st`.  ev[0..2], when given, bracket the DP and traceback phases.
 int enqueue_compute(rsa_ext* h, cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, cudaEvent_t* ev) {
     CU_TRY(h, cudaMemsetAsync(d.ends, 0, sizeof(DpEnd) * p.n, st));
-    CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, 2 * sizeof(unsigned long long), st));
+    CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, 3 * sizeof(unsigned long long), st));
     if (ev) CU_TRY(h, cudaEventRecord(ev[0], st));
     const PairMeta* meta = reinterpret_cast<const PairMeta*>(d.blob + p.off_meta);
     const uint32_t* info = reinterpret_cast<const uint32_t*>(d.blob + p.off_info);
@@ -442,7 +442,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
     CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
-    CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(h, cudaEventRecord(s.ev_d2h, h->s_d2h));
     h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_result_t) * p.n + 8;
 
@@ -473,6 +473,7 @@ int retire_chunk(rsa_ext* h, Slot& s) {
             }
         }
     }
+    h->stats.pairs_redo += (int64_t)s.h_arena_used[2];
     if (s.h_arena_used[1] > 0)
         for (int64_t i = s.plan.lo; i < s.plan.hi; ++i)
             if (h->results[i].status == 4) h->retry.push_back(i);
@@ -568,8 +569,8 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
-        if ((e = cudaHostAlloc(&s.h_arena_used, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
-        if ((e = cudaMalloc(&s.d_arena_used, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaHostAlloc(&s.h_arena_used, 3 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
+        if ((e = cudaMalloc(&s.d_arena_used, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     }
     {
         cudaDeviceProp prop;
@@ -766,6 +767,9 @@ extern "C" int rsa_ext_get_stats(const rsa_ext_t* hc, rsa_ext_stats_t* out) {
         }
         h->stats.dp_ms = dp;
         h->stats.tb_ms = tb;
+        unsigned long long c3[3] = {0, 0, 0};
+        cudaMemcpy(c3, h->slots[0].d_arena_used, sizeof c3, cudaMemcpyDeviceToHost);
+        h->stats.pairs_redo = (int64_t)c3[2];  // last chunk only
     }
     *out = h->stats;
     return RSA_EXT_OK;

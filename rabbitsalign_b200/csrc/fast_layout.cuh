@@ -6,7 +6,7 @@
 // every owned column is a real query base (no padding columns exist).
 //
 // Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
-//     uint32 index = (r*8 + l)*W + w,   W = ceil(C/4)
+//     uint32 index = (r*W + w)*8 + l,   W = ceil(C/4)   (for a fixed word w the 8 lanes are contiguous)
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
 //     bit3 open_f   (F of the next column opened from the diagonal; reference bit3 is the negation)
 //     bit2 open_e   (reference bit2 negated)
@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const ui
     const int wide = g.rem * g.C;
     if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
     else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
-    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((size_t)i * kFastLanes + lane) * g.W + (cc >> 2)];
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((size_t)i * g.W + (cc >> 2)) * kFastLanes + lane];
     const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
     return (h16 >> (4 * (cc & 3))) & 0xFu;
 }

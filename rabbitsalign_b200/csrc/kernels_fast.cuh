@@ -87,7 +87,7 @@ __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
 __host__ inline bool fast_scoring_ok(const Scoring& sc) {
     return sc.match > 0 && sc.mismatch > 0 && sc.gap_ext >= 0 && sc.gap_oe >= sc.gap_ext &&
            sc.mismatch + sc.gap_oe < kBias - 2 && sc.match + sc.mismatch < 128 &&
-           sc.match * kFastMaxQlen + kBias + sc.mismatch + sc.gap_oe < 0x0F00;
+           sc.match * kFastMaxQlen + kBias < 1024;  // (H_biased << 5) must stay a positive s16
 }
 
 // nibble (ascii & 0xF) -> code: A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4, everything else 0xF
@@ -124,43 +124,68 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t mask, uint32_t a, uint32_t b
 
 __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
 
+// Column keys: the running maximum is tracked on key = (H_biased << 5) | (31 - column_in_lane), still one
+// 16-bit half per pair (H_biased < 1024).  The larger key wins, i.e. the larger H and, for equal H in one row,
+// the smaller column -- the reference's order inside a row (SURVEY.md 8a rule 3).  Building the key is one
+// IMAD (FMA pipe, otherwise idle); no per-column maximum registers are needed.
+constexpr uint32_t kColMask = 0x001F001Fu;
+
 template <int C, bool HASN>
 struct FastDp {
     // One group's sweep.  All 32 lanes of the warp call this together (shuffles inside).
-    __device__ static __forceinline__ void run(const FastConsts& k, const uint8_t* __restrict__ tcodes, const uint32_t* __restrict__ lut, int rows,
-                                               int nsteps, int gl, bool wide, const uint32_t (&qsel)[C],
-                                               const uint32_t (&nmask)[C], uint32_t* __restrict__ dir, int W,
-                                               uint32_t (&colbest)[C], uint32_t& best_out, int (&firstrow)[2],
-                                               bool (&tie)[2]) {
-        uint32_t Hp[C], E[C];
+    //
+    // Per step (= one target row per lane) the work is ordered so that nothing at the head of the step waits:
+    //   phase 0  issue the two shuffles (H and F of the left neighbour's last column) and the shared-memory
+    //            loads of the NEXT step's target profile;
+    //   phase 1  S[c] <- H(r-1, c-1) + sub(r, c) for all columns, in place and right-to-left: independent of
+    //            the shuffles, covers their latency;
+    //   phase 2  the F-dependent chain left-to-right (H, E', F', direction flags, keys).
+    __device__ static __forceinline__ void run(const FastConsts& k, const uint8_t* __restrict__ tcodes,
+                                               const uint32_t* __restrict__ lut, int rows, int nsteps, int gl,
+                                               bool wide, const uint32_t (&qsel)[C], uint32_t* __restrict__ dir,
+                                               uint32_t* __restrict__ ring, int lane, uint32_t& bestkey_out,
+                                               int (&firstrow)[2]) {
+        uint32_t S[C], E[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { Hp[c] = k.zero; E[c] = k.zero; colbest[c] = k.zero; }
-        uint32_t Hlast = k.zero, Fout = k.zero, Hl_prev = k.zero, best = k.zero;
+        for (int c = 0; c < C; ++c) { S[c] = k.zero; E[c] = k.zero; }
+        uint32_t Hlast = k.zero, Fout = k.zero, Hl_prev = k.zero;
+        uint32_t bestkey = k.zero << 5;
         firstrow[0] = firstrow[1] = 0;
-        tie[0] = tie[1] = false;
         constexpr int NW = (C + 3) / 4;
+        const int rmax = rows > 0 ? rows - 1 : 0;
+        uint2 pr;
+        {
+            const uint32_t tc = tcodes[0];
+            pr.x = lut[tc & 0xFu];
+            pr.y = lut[tc >> 4];
+        }
         for (int s = 0; s < nsteps; ++s) {
+            // ---- phase 0
             uint32_t Hl = __shfl_up_sync(0xFFFFFFFFu, Hlast, 1, kFastLanes);
             uint32_t Fl = __shfl_up_sync(0xFFFFFFFFu, Fout, 1, kFastLanes);
-            if (gl == 0) { Hl = k.zero; Fl = k.zero; }
             const int r = s - gl;
+            const uint32_t tcn = tcodes[min(max(r + 1, 0), rmax)];
+            uint2 prn;
+            prn.x = lut[tcn & 0xFu];
+            prn.y = lut[tcn >> 4];
             if (r >= 0 && r < rows) {
-                const uint32_t tc = tcodes[r];
-                uint2 pr;
-                pr.x = lut[tc & 0xFu];
-                pr.y = lut[tc >> 4];
-                uint32_t diag = Hl_prev, F = Fl, rowmax = k.zero;
-                uint32_t acc = 0;
+                // ---- phase 1
+#pragma unroll
+                for (int c = C - 1; c >= 0; --c) {
+                    uint32_t sub = prmt(pr.x, pr.y, qsel[c]);
+                    if (HASN) sub = bitsel(prmt(0xFFFFFFFFu, 0u, qsel[c] >> 16), sub, k.x_pair);
+                    S[c] = (c == 0 ? Hl_prev : S[c - 1]) + sub;
+                }
+                // ---- phase 2
+                uint32_t F = (gl == 0) ? k.zero : Fl;
+                uint32_t rowkey = 0, acc = 0, Fsave = F, key_prev = 0;
                 uint32_t words[NW];
-                uint32_t Fsave = Fl;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
                     if (c < C - 1 || wide) {
-                        uint32_t sub = prmt(pr.x, pr.y, qsel[c]);
-                        if (HASN) sub = bitsel(nmask[c], sub, k.x_pair);
-                        const uint32_t tmp = diag + sub + k.neg_x;
-                        const uint32_t tg = diag + sub + k.neg_xoe;
+                        const uint32_t tmp = S[c] + k.neg_x;
+                        const uint32_t tg = S[c] + k.neg_xoe;
                         const uint32_t e = E[c];
                         const uint32_t u = __vimax3_s16x2(F, e, k.zero);
                         const uint32_t h = __vmaxs2(tmp, u);
@@ -174,40 +199,61 @@ struct FastDp {
                         fl = bitsel(0xC000C000u, fl, nd);
                         fl = bitsel(0xE000E000u, fl, nf);
                         acc = bitsel(0xF000F000u, fl, acc >> 4);
-                        colbest[c] = __vmaxs2(colbest[c], h);
-                        rowmax = __vmaxs2(rowmax, h);
-                        diag = Hp[c];
-                        Hp[c] = h;
+                        const uint32_t key = h * 32u + pair16(31 - c);
+                        if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
+                        else if (c == C - 1) rowkey = __vmaxs2(rowkey, key);
+                        key_prev = key;
+                        S[c] = h;
                         E[c] = en;
                         F = fn;
                     } else {
                         acc >>= 4;  // absent last column of a narrow lane: keep the nibble positions
+                        if (!(c & 1)) {}  // (an even last column has no pending key)
+                        else rowkey = __vmaxs2(rowkey, key_prev);
                     }
                     if ((c & 3) == 3) { words[c >> 2] = acc; acc = 0; }
                     else if (c == C - 1) words[c >> 2] = acc >> (4 * (3 - (c & 3)));  // right-align partial word
                 }
-                Hlast = wide ? Hp[C - 1] : Hp[(C >= 2) ? C - 2 : 0];
+                Hlast = wide ? S[C - 1] : S[(C >= 2) ? C - 2 : 0];
                 Fout = wide ? F : Fsave;
-                // direction words of this lane and row
-                uint32_t* drow = dir + ((size_t)r * kFastLanes + gl) * W;
+                // direction words of this lane and row: parked in this lane's shared-memory ring until every
+                // lane of the group has reached the same row (see below)
 #pragma unroll
-                for (int wv = 0; wv < NW; ++wv) drow[wv] = words[wv];
-                // running maximum bookkeeping (per half)
-                bool ge_lo, ge_hi, le_lo, le_hi;
-                const uint32_t nb = __vibmax_s16x2(best, rowmax, &ge_hi, &ge_lo);  // ge: best >= rowmax
-                (void)__vibmax_s16x2(rowmax, best, &le_hi, &le_lo);               // le: rowmax >= best
-                if (!ge_lo) { firstrow[0] = r; tie[0] = false; } else if (le_lo) tie[0] = true;
-                if (!ge_hi) { firstrow[1] = r; tie[1] = false; } else if (le_hi) tie[1] = true;
-                best = nb;
+                for (int wv = 0; wv < NW; ++wv) ring[(((s & 7) * NW + wv) << 5) + lane] = words[wv];
+                // Running maximum of this lane, per half, kept as the FIRST cell in the reference's visiting order
+                // (8-row block, column, row in block) among the cells seen so far with the largest H:
+                //   row H > best H                      -> this row's key wins;
+                //   row H == best H, same 8-row block and smaller column (= larger key) -> this row's key wins;
+                //   otherwise the earlier cell stays (earlier block, or same block and smaller-or-equal column).
+                bool ge_lo, ge_hi, g2_lo, g2_hi;
+                (void)__vibmax_s16x2(bestkey | kColMask, rowkey, &ge_hi, &ge_lo);  // ge: best H >= row H
+                (void)__vibmax_s16x2(bestkey, rowkey, &g2_hi, &g2_lo);             // g2: best key >= row key
+                const int rb = r >> 3;
+                const bool up_lo = !g2_lo && (!ge_lo || rb == (firstrow[0] >> 3));
+                const bool up_hi = !g2_hi && (!ge_hi || rb == (firstrow[1] >> 3));
+                if (up_lo) firstrow[0] = r;
+                if (up_hi) firstrow[1] = r;
+                bestkey = bitsel((up_lo ? 0x0000FFFFu : 0u) | (up_hi ? 0xFFFF0000u : 0u), rowkey, bestkey);
             }
-            Hl_prev = Hl;
+            Hl_prev = (gl == 0) ? k.zero : Hl;
+            pr = prn;
+            // De-skewed store: at step s every lane of the group stores ITS OWN words of row s-7 (lane gl
+            // computed that row 7-gl steps ago), so each store instruction covers 8 consecutive words per
+            // group (one 32-byte sector) instead of 8 scattered ones.
+            const int rr = s - (kFastLanes - 1);
+            if (rr >= 0 && rr < rows) {
+                const int slot = (rr + gl) & 7;
+                uint32_t* drow = dir + (size_t)rr * (NW * kFastLanes) + gl;
+#pragma unroll
+                for (int wv = 0; wv < NW; ++wv) drow[wv * kFastLanes] = ring[((slot * NW + wv) << 5) + lane];
+            }
         }
-        best_out = best;
+        bestkey_out = bestkey;
     }
 };
 
 template <int C>
-__global__ void __launch_bounds__(32 * kFastWarpsPerBlock)
+__global__ void __launch_bounds__(32 * kFastWarpsPerBlock, (C <= 20 ? 4 : (C <= 27 ? 3 : 2)))
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
@@ -223,6 +269,8 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     if (g_index < n_groups) grp = groups[g_index];
     const bool live = grp.a != 0xFFFFFFFFu;
     uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * kFastGroupsPerWarp + gi) * rows_pad;
+    constexpr int kRingWords = 8 * ((C + 3) / 4) * 32;  // per warp
+    uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + 32 + (size_t)kFastWarpsPerBlock * kFastGroupsPerWarp * rows_pad) + warp * kRingWords;
 
     // ---- staging: target profiles into shared memory, query selectors into registers ----------------
     bool bad_a = false, bad_b = false;
@@ -248,24 +296,23 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     const int ncols = live ? ((gl < geo.rem) ? geo.C : geo.C - 1) : 0;
     const bool wide = live && (ncols == C);
     const int col0 = live ? fast_lane_col0(geo, gl) : 0;
-    uint32_t qsel[C], nmask[C];
+    uint32_t qsel[C];
     bool has_n = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        uint32_t ca = 0, cb = 0;
-        uint32_t nm = 0xFFFFFFFFu;
+        uint32_t ca = 0, cb = 0, msel = 0x4444u;  // mask selector: bytes of 0xFFFFFFFF (keep) / of 0 (N: replace)
         if (c < ncols) {
             ca = base_code(nibble_of(qa[col0 + c]));
             cb = base_code(nibble_of(qb[col0 + c]));
             bad_a |= (ca == 0xFu);
             bad_b |= (cb == 0xFu);
-            if (ca >= 4u) { nm &= 0xFFFF0000u; ca = 0; }
-            if (cb >= 4u) { nm &= 0x0000FFFFu; cb = 0; }
-            has_n |= (nm != 0xFFFFFFFFu);
+            if (ca >= 4u) { msel &= 0xFF00u; ca = 0; }
+            if (cb >= 4u) { msel &= 0x00FFu; cb = 0; }
+            has_n |= (msel != 0x4444u);
         }
-        // result bytes: [0] = X[ca], [1] = 0 (sign of a non-negative byte), [2] = Y[cb], [3] = 0
-        qsel[c] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12);
-        nmask[c] = nm;
+        // sub bytes: [0] = X[ca], [1] = 0 (sign of a non-negative byte), [2] = Y[cb], [3] = 0; the upper half
+        // carries the PRMT selector that expands to the per-half "query base is not N" mask
+        qsel[c] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12) | ((msel ^ 0x4444u) << 16);
     }
     const unsigned gmask = 0xFFu << (8 * gi);
     bad_a = (__ballot_sync(0xFFFFFFFFu, bad_a) & gmask) != 0;
@@ -278,24 +325,24 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     __syncthreads();  // lut + this warp's target codes
 
     uint32_t* dir = reinterpret_cast<uint32_t*>(scratch + grp.dir_off);
-    uint32_t colbest[C];
-    uint32_t best;
+    uint32_t bestkey;
     int firstrow[2];
-    bool tie[2];
-    if (warp_has_n) FastDp<C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, nmask, dir, geo.W, colbest, best, firstrow, tie);
-    else FastDp<C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, nmask, dir, geo.W, colbest, best, firstrow, tie);
+    if (warp_has_n) FastDp<C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
+    else FastDp<C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
 
     // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
+    // Every lane holds its first-in-reference-order maximum cell; lanes own increasing column ranges, so among
+    // the lanes reaching the pair's maximum the winner is the smallest (8-row block, lane).
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const uint32_t pi = h ? grp.b : grp.a;
         const bool bad = h ? bad_b : bad_a;
-        const int mine = half_s(best, h) - k.bias;
+        const int kh = half_s(bestkey, h);
+        const int mine = (kh >> 5) - k.bias;
         int S = mine;
 #pragma unroll
         for (int off = 4; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(0xFFFFFFFFu, S, off));
         const bool cand = live && (mine == S) && (S > 0);
-        const bool any_tie = (__ballot_sync(0xFFFFFFFFu, cand && tie[h]) & gmask) != 0;
         int key = cand ? (((firstrow[h] >> 3) << 8) | gl) : 0x7FFFFFFF;
 #pragma unroll
         for (int off = 4; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
@@ -303,26 +350,17 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         const bool winner = (S > 0) ? ((key & 0xFF) == gl) : (gl == 0);
         if (!winner) continue;
         DpEnd e;
-        e.score = S; e.qend = 0; e.tend = 0;
+        e.score = S; e.qend = 0; e.tend = 0;  // S == 0: the reference's maximum trackers stay at (0,0)
         e.flags = DPF_DONE | DPF_LAYOUT_FAST;
         if (bad) {
             e.flags = DPF_NEED_EXACT;  // symbols outside {A,C,G,T,N}: full exact redo (own direction tile)
-        } else if (S > 0) {
-            int cmin = 0;
-            bool found = false;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (!found && c < ncols && half_s(colbest[c], h) - k.bias == S) { cmin = c; found = true; }
-            }
-            e.qend = col0 + cmin;
-            e.tend = firstrow[h];
-            if (any_tie) e.flags = DPF_NEED_EXACT | DPF_LAYOUT_FAST;  // end cell ambiguous: score-only redo
-        }
-        ends[pi] = e;
-        if (e.flags & DPF_NEED_EXACT) {
             const unsigned int slot = atomicAdd(&redo->count, 1u);
             redo_list[slot] = pi;
+        } else if (S > 0) {
+            e.qend = col0 + (31 - (kh & 31));
+            e.tend = firstrow[h];
         }
+        ends[pi] = e;
     }
 }
 
@@ -422,6 +460,7 @@ exact_redo_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tn = smem + warp * tlen_pad;
     const unsigned int total = redo->count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[2] = total;  // diagnostics: pairs re-run by this pass
     const unsigned int stride = gridDim.x * kRedoWarpsPerBlock;
     for (unsigned int it = blockIdx.x * kRedoWarpsPerBlock + warp; it < total; it += stride) {
         const uint32_t pi = redo_list[it];
@@ -481,7 +520,7 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
     const int rows_pad = (max_rows + 15) & ~15;
     const int groups_per_block = kFastWarpsPerBlock * kFastGroupsPerWarp;
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-    const size_t smem = 32 + (size_t)groups_per_block * rows_pad;
+    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)kFastWarpsPerBlock * 8 * ((C + 3) / 4) * 32 * 4;
     fast_dp_kernel<C><<<blocks, 32 * kFastWarpsPerBlock, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
                                                                      redo, redo_list, k, rows_pad);
 }

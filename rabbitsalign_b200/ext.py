@@ -42,7 +42,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_fast", C.c_int64), ("pairs_exact", C.c_int64),
                 ("pairs_failed", C.c_int64), ("cells", C.c_int64), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("dp_ms", C.c_double), ("tb_ms", C.c_double)]
+                ("d2h_bytes", C.c_int64), ("dp_ms", C.c_double), ("tb_ms", C.c_double), ("pairs_redo", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
