@@ -130,3 +130,24 @@ def test_large_batch_properties(engine):
                 else:
                     jj += cnt
         assert s == res["score"][i] and ii == res["ref_end"][i] + 1 and jj == res["query_end"][i] + 1
+
+
+def _golden_files():
+    import os
+    d = os.path.join(os.path.dirname(__file__), "golden")
+    return sorted(f for f in os.listdir(d) if f.startswith("pairs_") and f.endswith(".json"))
+
+
+@pytest.mark.parametrize("name", _golden_files())
+@pytest.mark.parametrize("exact_only", [False, True], ids=["packed", "exact"])
+def test_golden_vectors_from_reference_kernels(name, exact_only):
+    """Committed vectors produced by the reference's own GASAL2 kernels (oracle/make_golden.py)."""
+    import json
+    import os
+    from rabbitsalign_b200 import ExtensionEngine
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name)))
+    e = ExtensionEngine(exact_only=exact_only, **g.get("scoring", {}))
+    got = e.solve_ssw_on_gpu([p["q"].encode("latin1") for p in g["pairs"]], [p["t"].encode("latin1") for p in g["pairs"]])
+    e.close()
+    bad = [(p["q"], p["t"], list(r.astuple()), p["res"]) for p, r in zip(g["pairs"], got) if list(r.astuple()) != p["res"]]
+    assert not bad, bad[:3]

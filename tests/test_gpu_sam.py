@@ -1,0 +1,37 @@
+"""GPU suite: byte-identical SAM.  The reference's UNMODIFIED host pipeline (seeding, NAMs, window
+construction, gasal_fail gate, align_gpu, SAM writer -- compiled from /root/reference by
+integration/build.sh) linked against the product (integration/gasal2_ssw.cpp -> librsa_ext.so) must write
+the same SAM as the same pipeline linked against the reference's own GASAL2 kernels (golden md5s in
+tests/golden/sam_golden.json, generated in the dev container by tests/golden/make_sam_golden.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_sam_golden import B, CONFIGS, ROOT, md5_file  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_golden.json")))
+BIN = os.path.join(B, "rabbitsalign_b200")
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_sam_is_byte_identical(name, tmp_path):
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_build/rabbitsalign_b200 not built (needs /root/reference at build time)")
+    g = GOLD[name]
+    d = str(tmp_path / name)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_reads.py"), d] + g["make_reads_args"])
+    files = sorted(g["inputs"])  # ref.fa, reads_1.fq[, reads_2.fq]
+    for f in files:
+        assert md5_file(os.path.join(d, f)) == g["inputs"][f], f"synthetic input {f} differs from the golden run"
+    out = os.path.join(d, "b200.sam")
+    args = [os.path.join(d, "ref.fa"), os.path.join(d, "reads_1.fq")] + ([os.path.join(d, "reads_2.fq")] if g["paired"] else [])
+    r = subprocess.run([BIN, "-t", str(g["threads"]), "-o", out] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = sum(1 for ln in open(out, "rb") if not ln.startswith(b"@"))
+    assert n == g["records"]
+    assert md5_file(out, skip_pg=True) == g["sam_md5_gasal_semantics"]
