@@ -521,6 +521,8 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
     const int groups_per_block = kFastWarpsPerBlock * kFastGroupsPerWarp;
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
     const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)kFastWarpsPerBlock * 8 * ((C + 3) / 4) * 32 * 4;
+    if (smem > 48 * 1024)  // long windows: opt in to more dynamic shared memory (per device, cheap to repeat)
+        cudaFuncSetAttribute(fast_dp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     fast_dp_kernel<C><<<blocks, 32 * kFastWarpsPerBlock, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
                                                                      redo, redo_list, k, rows_pad);
 }
