@@ -343,7 +343,8 @@ def main():
                    "resident_equals_e2e_records": same, "records_sane": ok},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
-                "d2h_bytes_per_step": st_e2e["d2h_bytes"]},
+                "d2h_bytes_per_step": st_e2e["d2h_bytes"],
+                "ms_per_step": float(t_e.item()) / args.steps * 1e3, "host_plan_ms_per_step": st_e2e["host_plan_ms"]},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
     }

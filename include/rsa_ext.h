@@ -129,6 +129,7 @@ typedef struct {
     double tb_ms;         /* device time of the traceback kernels */
     int64_t pairs_redo;   /* pairs the packed kernel handed to the exact kernel at run time (ties on the maximum,
                              symbols outside ACGTN); resident runs: last chunk only */
+    double host_plan_ms;  /* host time spent planning chunks during the last submit/wait */
 } rsa_ext_stats_t;
 int rsa_ext_get_stats(const rsa_ext_t *h, rsa_ext_stats_t *out);
 

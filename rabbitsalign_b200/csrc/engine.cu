@@ -16,6 +16,7 @@
 //     kernel (kernels_exact.cuh) for whatever the packed kernel declines, one traceback kernel
 //     (kernels_tb.cuh).  No CPU fallback exists here.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,7 +77,7 @@ struct Slot {
     unsigned long long* h_arena_used = nullptr;  // pinned; [0] arena bytes used, [1] pairs the redo pass could not place
     DevBuf d_blob, d_q, d_t, d_ends, d_res, d_scratch, d_arena;
     unsigned long long* d_arena_used = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_mid = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     ChunkPlan plan;
     bool busy = false;
 };
@@ -95,7 +96,7 @@ struct rsa_ext {
     FastConsts fk{};
     bool fast_ok = false;
     int n_sms = 148;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_tb = nullptr, s_d2h = nullptr;
     Slot slots[kSlots];
     size_t scratch_per_slot = 0;
 
@@ -109,6 +110,7 @@ struct rsa_ext {
     rsa_ext_result_t* results = nullptr;
     int64_t next_pair = 0;
     int head = 0, tail = 0, inflight = 0;
+    int chunks_enqueued = 0;
     std::unordered_map<int64_t, std::vector<uint8_t>> overflow;
     std::vector<int64_t> retry;  // pairs whose redo found no scratch (status 4): re-run exact-only at wait()
 
@@ -120,13 +122,13 @@ struct rsa_ext {
     std::vector<ResidentChunk> res_chunks;
     DevBuf r_q, r_t, r_res, r_blobs;
     int64_t r_n = 0;
-    std::vector<cudaEvent_t> r_events;  // 3 per chunk: before DP, after DP, after TB
+    std::vector<cudaEvent_t> r_events;  // 4 per chunk: DP begin/end (compute stream), traceback begin/end (tb stream)
     bool r_events_valid = false;
 
     rsa_ext_stats_t stats{};
     std::string err;
     std::vector<uint32_t> tmp_list[3];
-    std::vector<uint32_t> tmp_sort, tmp_order;
+    std::vector<uint32_t> tmp_sort, tmp_order, tmp_key, tmp_key2;
     std::vector<uint32_t> tmp_count;
 };
 
@@ -179,6 +181,7 @@ struct PlanInput {
     int max_qlen, max_tlen;
     size_t scratch_cap;
     bool exact_only;
+    int64_t max_pairs = kMaxChunkPairs;  // cap for this chunk (the first chunks of a batch ramp up)
 };
 
 // A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
@@ -186,14 +189,32 @@ inline bool fast_shape_ok(int qlen, int tlen) {
     return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen;
 }
 
+// per-query-length geometry, computed once
+struct LenTables {
+    uint32_t fast_row_bytes[kFastMaxQlen + 1];  // direction bytes per target row of a packed group
+    uint16_t fast_C[kFastMaxQlen + 1];
+    uint32_t exact_row_bytes_[513];
+    LenTables() {
+        for (int q = 0; q <= kFastMaxQlen; ++q) {
+            const FastGeom g = fast_geom(q < 1 ? 1 : q);
+            fast_row_bytes[q] = (uint32_t)(kFastLanes * g.W * 4);
+            fast_C[q] = (uint16_t)g.C;
+        }
+        for (int q = 0; q <= 512; ++q) exact_row_bytes_[q] = (uint32_t)exact_row_bytes(q);
+    }
+};
+const LenTables& len_tables() { static const LenTables t; return t; }
+
 int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std::vector<uint8_t>* vec_blob,
                PinBuf* pin_blob) {
+    const LenTables& LT = len_tables();
     // 1) how many pairs: stop at the pair/sequence-byte caps or when the scratch budget is reached.
     //    Scratch is budgeted with the larger of the two layouts' needs so any routing fits.
     int64_t hi = lo;
     uint64_t scratch = 0;
     const int64_t q0 = in.qoff[lo], t0 = in.toff[lo];
-    while (hi < in.n && hi - lo < kMaxChunkPairs) {
+    const int64_t hi_cap = std::min<int64_t>(in.n, lo + std::min<int64_t>(kMaxChunkPairs, in.max_pairs));
+    while (hi < hi_cap) {
         const int64_t ql = in.qoff[hi + 1] - in.qoff[hi], tl = in.toff[hi + 1] - in.toff[hi];
         if (ql < 0 || tl < 0) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
         if (ql > in.max_qlen) {
@@ -202,12 +223,9 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         }
         uint64_t need = 0;
         if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
-            const uint64_t ex = align_up((size_t)tl * exact_row_bytes((int)ql), 16);
-            need = ex;
-            if (fast_shape_ok((int)ql, (int)tl)) {
-                const FastGeom g = fast_geom((int)ql);
-                need = std::max<uint64_t>(ex, fast_dir_bytes(g, (int)tl));  // a lone pair owns a whole group
-            }
+            need = (uint64_t)tl * LT.exact_row_bytes_[ql] + 16;
+            if (fast_shape_ok((int)ql, (int)tl))  // a lone pair owns a whole group
+                need = std::max<uint64_t>(need, (uint64_t)tl * LT.fast_row_bytes[ql]);
         }
         if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
                         in.toff[hi + 1] - t0 > kMaxChunkSeqBytes))
@@ -231,7 +249,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     plan.off_redo = off;   off = align_up(off + sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4), 16);
     plan.blob_bytes = off;
     uint8_t* blob;
-    if (vec_blob) { vec_blob->assign(off, 0); blob = vec_blob->data(); }
+    if (vec_blob) { vec_blob->resize(off); blob = vec_blob->data(); }
     else {
         int rc = ensure_pin(h, *pin_blob, off);
         if (rc) return rc;
@@ -244,83 +262,114 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     FastGroup* groups = reinterpret_cast<FastGroup*>(blob + plan.off_groups);
     memset(blob + plan.off_redo, 0, sizeof(RedoHeader));
 
+    // 3) per-pair records; packed-kernel candidates collected as (key = qlen<<16 | tlen, index)
     for (int k = 0; k < 3; ++k) h->tmp_list[k].clear();
-    h->tmp_sort.clear();
+    std::vector<uint32_t>& cand_idx = h->tmp_sort;
+    std::vector<uint32_t>& cand_key = h->tmp_key;
+    cand_idx.resize((size_t)n);
+    cand_key.resize((size_t)n);
+    size_t m = 0;
     uint64_t arena = 0;
+    int64_t cells = 0;
+    uint32_t qmin = 0xFFFFFFFFu, qmax = 0;
     for (int64_t i = 0; i < n; ++i) {
-        const int64_t ql = in.qoff[lo + i + 1] - in.qoff[lo + i], tl = in.toff[lo + i + 1] - in.toff[lo + i];
-        meta[i].qoff = (uint32_t)(in.qoff[lo + i] - q0);
-        meta[i].toff = (uint32_t)(in.toff[lo + i] - t0);
+        const int64_t qo = in.qoff[lo + i], to = in.toff[lo + i];
+        const int64_t ql = in.qoff[lo + i + 1] - qo, tl = in.toff[lo + i + 1] - to;
+        meta[i].qoff = (uint32_t)(qo - q0);
+        meta[i].toff = (uint32_t)(to - t0);
         meta[i].qlen = (uint16_t)ql;
         meta[i].tlen = (uint16_t)std::min<int64_t>(tl, 65535);
         info[i] = 0;
         diroff[i] = 0;
-        plan.cells += ql * tl;
+        cells += ql * tl;
         if (ql == 0 || tl == 0) { info[i] = 3u << 16; plan.n_failed++; continue; }
         if (tl > in.max_tlen) { info[i] = 1u << 16; plan.n_failed++; continue; }
         arena += (uint64_t)(ql + tl + 1);
-        if (!in.exact_only && fast_shape_ok((int)ql, (int)tl)) h->tmp_sort.push_back((uint32_t)i);
-        else h->tmp_list[exact_class_cols((int)ql) == 4 ? 0 : (exact_class_cols((int)ql) == 8 ? 1 : 2)].push_back((uint32_t)i);
+        if (!in.exact_only && fast_shape_ok((int)ql, (int)tl)) {
+            cand_idx[m] = (uint32_t)i;
+            cand_key[m] = ((uint32_t)ql << 16) | (uint32_t)tl;
+            qmin = std::min(qmin, (uint32_t)ql);
+            qmax = std::max(qmax, (uint32_t)ql);
+            ++m;
+        } else {
+            const int cls = LT.exact_row_bytes_[ql] == 64 ? 0 : (LT.exact_row_bytes_[ql] == 128 ? 1 : 2);
+            h->tmp_list[cls].push_back((uint32_t)i);
+        }
     }
+    plan.cells = cells;
     plan.arena_bytes = arena + 64;
 
-    // 3) packed-kernel groups: counting sort of the candidates by (qlen, tlen), then consecutive equal-qlen
-    //    pairs share a group (A = low halves, B = high halves); an odd one out runs with B = A.
+    // 4) packed-kernel groups: stable counting sort of the candidates by target length, then (only if the
+    //    chunk mixes query lengths) by query length; consecutive equal-qlen pairs share a group (A = low
+    //    halves, B = high halves), an odd one out runs with B = A.  Groups of one column class are padded
+    //    to whole warps (4 groups) with empty slots.
     uint64_t sc_off = 0;
     int n_groups = 0;
     plan.fast.clear();
-    if (!h->tmp_sort.empty()) {
-        const size_t m = h->tmp_sort.size();
-        // key = qlen * (kFastMaxTlen+1) + tlen, two-pass LSD counting sort (tlen then qlen)
-        h->tmp_order.resize(m);
-        {
-            std::vector<uint32_t>& cnt = h->tmp_count;
-            cnt.assign(kFastMaxTlen + 2, 0);
-            for (size_t k = 0; k < m; ++k) cnt[meta[h->tmp_sort[k]].tlen + 1]++;
-            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
-            for (size_t k = 0; k < m; ++k) h->tmp_order[cnt[meta[h->tmp_sort[k]].tlen]++] = h->tmp_sort[k];
-            cnt.assign(kFastMaxQlen + 2, 0);
-            for (size_t k = 0; k < m; ++k) cnt[meta[h->tmp_order[k]].qlen + 1]++;
-            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
-            for (size_t k = 0; k < m; ++k) h->tmp_sort[cnt[meta[h->tmp_order[k]].qlen]++] = h->tmp_order[k];
+    if (m > 0) {
+        std::vector<uint32_t>& idx2 = h->tmp_order;
+        std::vector<uint32_t>& key2 = h->tmp_key2;
+        std::vector<uint32_t>& cnt = h->tmp_count;
+        idx2.resize(m);
+        key2.resize(m);
+        cnt.assign(kFastMaxTlen + 2, 0);
+        for (size_t k = 0; k < m; ++k) cnt[(cand_key[k] & 0xFFFFu) + 1]++;
+        for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+        for (size_t k = 0; k < m; ++k) {
+            const uint32_t p = cnt[cand_key[k] & 0xFFFFu]++;
+            idx2[p] = cand_idx[k];
+            key2[p] = cand_key[k];
         }
+        const uint32_t* sidx = idx2.data();
+        const uint32_t* skey = key2.data();
+        if (qmin != qmax) {
+            cnt.assign(kFastMaxQlen + 2, 0);
+            for (size_t k = 0; k < m; ++k) cnt[(key2[k] >> 16) + 1]++;
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            for (size_t k = 0; k < m; ++k) {
+                const uint32_t p = cnt[key2[k] >> 16]++;
+                cand_idx[p] = idx2[k];
+                cand_key[p] = key2[k];
+            }
+            sidx = cand_idx.data();
+            skey = cand_key.data();
+        }
+        const FastGroup empty{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
         size_t k = 0;
         int cur_C = -1;
         while (k < m) {
-            const uint32_t a = h->tmp_sort[k];
-            const int ql = meta[a].qlen;
-            uint32_t b = a;
-            if (k + 1 < m && meta[h->tmp_sort[k + 1]].qlen == ql) { b = h->tmp_sort[k + 1]; k += 2; }
+            const uint32_t a = sidx[k], ka = skey[k];
+            const uint32_t ql = ka >> 16;
+            uint32_t b = a, kb = ka;
+            if (k + 1 < m && (skey[k + 1] >> 16) == ql) { b = sidx[k + 1]; kb = skey[k + 1]; k += 2; }
             else k += 1;
-            const FastGeom g = fast_geom(ql);
-            if (g.C != cur_C) {
-                // close the previous class on a warp boundary (4 groups per warp) with empty groups
-                while (n_groups % kFastGroupsPerWarp) { groups[n_groups] = FastGroup{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0}; n_groups++; }
+            const int C = LT.fast_C[ql];
+            if (C != cur_C) {
+                while (n_groups % kFastGroupsPerWarp) groups[n_groups++] = empty;
                 if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
-                plan.fast.push_back({g.C, n_groups, 0, 0});
-                cur_C = g.C;
+                plan.fast.push_back({C, n_groups, 0, 0});
+                cur_C = C;
             }
-            const int rows = std::max<int>(meta[a].tlen, meta[b].tlen);
+            const uint32_t rows = std::max(ka & 0xFFFFu, kb & 0xFFFFu);
             FastGroup fg;
             fg.a = a; fg.b = b;
             fg.dir_off = sc_off;
             fg.qlen = (uint16_t)ql;
             fg.rows = (uint16_t)rows;
             groups[n_groups++] = fg;
-            diroff[a] = sc_off; info[a] |= 0u;
+            diroff[a] = sc_off;
             if (b != a) { diroff[b] = sc_off; info[b] |= 1u; }
-            sc_off += align_up(fast_dir_bytes(g, rows), 16);
-            plan.fast.back().max_tlen = std::max(plan.fast.back().max_tlen, rows);
+            sc_off += (uint64_t)rows * LT.fast_row_bytes[ql];
+            plan.fast.back().max_tlen = std::max<int>(plan.fast.back().max_tlen, (int)rows);
             plan.n_fast_pairs += (b != a) ? 2 : 1;
         }
-        while (n_groups % kFastGroupsPerWarp) { groups[n_groups] = FastGroup{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0}; n_groups++; }
+        while (n_groups % kFastGroupsPerWarp) groups[n_groups++] = empty;
         plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
     }
     plan.n_fast_classes = (int)plan.fast.size();
 
-    // 4) exact-kernel lists.  Pairs the packed kernel declines at run time are re-run by the exact kernel in
-    //    a second pass over the same scratch region of that pair (the fast layout of a lone pair is at
-    //    least as large, see the budget above), so only the statically exact pairs get fresh offsets here.
+    // 5) exact-kernel lists (statically routed pairs); pairs the packed kernel flags at run time get their
+    //    tiles from the head-room behind `scratch_bytes` (exact_redo_kernel).
     uint32_t pos = 0;
     for (int c = 0; c < 3; ++c) {
         plan.n_exact[c] = (int)h->tmp_list[c].size();
@@ -364,9 +413,13 @@ void launch_exact(cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, int li
         reinterpret_cast<const uint64_t*>(d.blob + p.off_diroff), d.scratch, d.ends, sc, tlen_pad);
 }
 
-// Enqueue every kernel of one chunk on `st`.  ev[0..2], when given, bracket the DP and traceback phases.
-int enqueue_compute(rsa_ext* h, cudaStream_t st, const ChunkDev& d, const ChunkPlan& p, cudaEvent_t* ev) {
+// Enqueue every kernel of one chunk: the DP kernels on `st`, the traceback on `st_tb` behind `ev_mid`, so the
+// traceback of chunk k (a latency-bound pointer chase) overlaps the DP kernels of chunk k+1 (issue-bound).
+// ev[0..3], when given, bracket the DP phase (on st) and the traceback (on st_tb).
+int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t ev_mid, const ChunkDev& d,
+                    const ChunkPlan& p, cudaEvent_t* ev) {
     CU_TRY(h, cudaMemsetAsync(d.ends, 0, sizeof(DpEnd) * p.n, st));
+    CU_TRY(h, cudaMemsetAsync(const_cast<uint8_t*>(d.blob) + p.off_redo, 0, sizeof(RedoHeader), st));
     CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, 3 * sizeof(unsigned long long), st));
     if (ev) CU_TRY(h, cudaEventRecord(ev[0], st));
     const PairMeta* meta = reinterpret_cast<const PairMeta*>(d.blob + p.off_meta);
@@ -405,10 +458,13 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, const ChunkDev& d, const ChunkP
         h->stats.kernel_launches++;
     }
     if (ev) CU_TRY(h, cudaEventRecord(ev[1], st));
-    tb_kernel<<<(unsigned)((p.n + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st>>>(
+    CU_TRY(h, cudaEventRecord(ev_mid, st));
+    CU_TRY(h, cudaStreamWaitEvent(st_tb, ev_mid, 0));
+    if (ev) CU_TRY(h, cudaEventRecord(ev[2], st_tb));
+    tb_kernel<<<(unsigned)((p.n + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st_tb>>>(
         d.q, d.t, meta, info, (int)p.n, diroff, d.scratch, d.ends, d.res, h->sc, d.arena, d.arena_used, d.arena_cap);
     h->stats.kernel_launches++;
-    if (ev) CU_TRY(h, cudaEventRecord(ev[2], st));
+    if (ev) CU_TRY(h, cudaEventRecord(ev[3], st_tb));
     CU_TRY(h, cudaGetLastError());
     return RSA_EXT_OK;
 }
@@ -416,7 +472,12 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, const ChunkDev& d, const ChunkP
 int enqueue_chunk(rsa_ext* h, Slot& s) {
     PlanInput in{h->n, h->qoff, h->toff, h->qbuf, h->tbuf, h->cfg.max_query_len, h->cfg.max_target_len,
                  h->scratch_per_slot, (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
+    // ramp: 16k, 32k, 64k, then full-size chunks, so the first kernels start while the host still plans
+    in.max_pairs = h->chunks_enqueued < 3 ? ((int64_t)16384 << h->chunks_enqueued) : kMaxChunkPairs;
+    h->chunks_enqueued++;
+    const auto t_plan0 = std::chrono::steady_clock::now();
     int rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
+    h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
     if (rc) return rc;
     const ChunkPlan& p = s.plan;
     if ((rc = ensure_dev(h, s.d_blob, p.blob_bytes))) return rc;
@@ -437,8 +498,8 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     ChunkDev d{s.d_blob.p, s.d_q.p, s.d_t.p, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
-    if ((rc = enqueue_compute(h, h->s_comp, d, p, nullptr))) return rc;
-    CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_comp));
+    if ((rc = enqueue_compute(h, h->s_comp, h->s_tb, s.ev_mid, d, p, nullptr))) return rc;
+    CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
     CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -498,7 +559,7 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
         if (ql < 0 || toff[i + 1] < toff[i]) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
     }
     h->n = n; h->qbuf = qbuf; h->qoff = qoff; h->tbuf = tbuf; h->toff = toff; h->results = results;
-    h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0;
+    h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0; h->chunks_enqueued = 0;
     h->overflow.clear();
     h->retry.clear();
     h->stats = rsa_ext_stats_t{};
@@ -564,10 +625,12 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_tb, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     for (Slot& s : h->slots) {
         if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaHostAlloc(&s.h_arena_used, 3 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
         if ((e = cudaMalloc(&s.d_arena_used, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -585,6 +648,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    if (h->s_tb) cudaStreamSynchronize(h->s_tb);
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
     for (Slot& s : h->slots) {
@@ -595,6 +659,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
         if (s.d_arena_used) cudaFree(s.d_arena_used);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_mid) cudaEventDestroy(s.ev_mid);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
     for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
@@ -604,6 +669,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->own_t.p) cudaFreeHost(h->own_t.p);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_tb) cudaStreamDestroy(h->s_tb);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
@@ -758,11 +824,12 @@ extern "C" int rsa_ext_get_stats(const rsa_ext_t* hc, rsa_ext_stats_t* out) {
     if (h->r_events_valid) {
         cudaSetDevice(h->cfg.device);
         cudaStreamSynchronize(h->s_comp);
+        cudaStreamSynchronize(h->s_tb);
         double dp = 0, tb = 0;
         for (size_t c = 0; c < h->res_chunks.size(); ++c) {
             float a = 0, b = 0;
-            cudaEventElapsedTime(&a, h->r_events[3 * c], h->r_events[3 * c + 1]);
-            cudaEventElapsedTime(&b, h->r_events[3 * c + 1], h->r_events[3 * c + 2]);
+            cudaEventElapsedTime(&a, h->r_events[4 * c], h->r_events[4 * c + 1]);
+            cudaEventElapsedTime(&b, h->r_events[4 * c + 2], h->r_events[4 * c + 3]);
             dp += a; tb += b;
         }
         h->stats.dp_ms = dp;
@@ -813,10 +880,12 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
     if ((rc = ensure_dev(h, h->r_t, tbytes + 16))) return rc;
     if ((rc = ensure_dev(h, h->r_res, sizeof(rsa_ext_result_t) * (size_t)n))) return rc;
     if ((rc = ensure_dev(h, h->r_blobs, blob_total))) return rc;
-    Slot& s = h->slots[0];
-    if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * max_pairs))) return rc;
-    if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(max_scratch)))) return rc;
-    if ((rc = ensure_dev(h, s.d_arena, max_arena))) return rc;
+    for (int k = 0; k < (h->res_chunks.size() > 1 ? kSlots : 1); ++k) {  // chunks alternate between the slots' scratch
+        Slot& s = h->slots[k];
+        if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * max_pairs))) return rc;
+        if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(max_scratch)))) return rc;
+        if ((rc = ensure_dev(h, s.d_arena, max_arena))) return rc;
+    }
     CU_TRY(h, cudaMemcpy(h->r_q.p, qbuf + qoff[0], qbytes, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->r_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice));
     size_t boff = 0;
@@ -830,7 +899,7 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
         h->stats.cells += h->res_chunks[c].plan.cells;
     }
     h->stats.h2d_bytes = (int64_t)(qbytes + tbytes + blob_total);
-    while (h->r_events.size() < 3 * h->res_chunks.size()) {
+    while (h->r_events.size() < 4 * h->res_chunks.size()) {
         cudaEvent_t ev;
         CU_TRY(h, cudaEventCreate(&ev));
         h->r_events.push_back(ev);
@@ -842,16 +911,22 @@ extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     if (!h) return RSA_EXT_ERR_ARG;
     if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    Slot& s = h->slots[0];
     h->stats.kernel_launches = 0;
+    const int nslots = h->res_chunks.size() > 1 ? kSlots : 1;
     for (size_t c = 0; c < h->res_chunks.size(); ++c) {
         const ResidentChunk& rcx = h->res_chunks[c];
+        Slot& s = h->slots[c % nslots];
+        // the slot's scratch/ends are free once the traceback that last used them has finished
+        CU_TRY(h, cudaStreamWaitEvent(h->s_comp, s.ev_comp, 0));
         ChunkDev d{rcx.d_blob, h->r_q.p + rcx.q_base, h->r_t.p + rcx.t_base, reinterpret_cast<DpEnd*>(s.d_ends.p),
                    reinterpret_cast<rsa_ext_result_t*>(h->r_res.p) + rcx.plan.lo, s.d_scratch.p, (uint64_t)s.d_scratch.cap,
                    s.d_arena.p, s.d_arena_used, (uint64_t)s.d_arena.cap};
-        int rc = enqueue_compute(h, h->s_comp, d, rcx.plan, &h->r_events[3 * c]);
+        int rc = enqueue_compute(h, h->s_comp, h->s_tb, s.ev_mid, d, rcx.plan, &h->r_events[4 * c]);
         if (rc) return rc;
+        CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
     }
+    // anything the caller records on the compute stream after this call comes after every traceback too
+    for (int k = 0; k < nslots; ++k) CU_TRY(h, cudaStreamWaitEvent(h->s_comp, h->slots[k].ev_comp, 0));
     h->r_events_valid = true;
     return RSA_EXT_OK;
 }
@@ -861,6 +936,7 @@ extern "C" int rsa_ext_fetch_resident(rsa_ext_t* h, rsa_ext_result_t* results) {
     if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     CU_TRY(h, cudaStreamSynchronize(h->s_comp));
+    CU_TRY(h, cudaStreamSynchronize(h->s_tb));
     CU_TRY(h, cudaMemcpy(results, h->r_res.p, sizeof(rsa_ext_result_t) * (size_t)h->r_n, cudaMemcpyDeviceToHost));
     return RSA_EXT_OK;
 }
@@ -876,6 +952,13 @@ extern "C" int rsa_ext_plan_debug(int64_t n, const int64_t* qoff, const int64_t*
     std::vector<uint8_t> blob;
     int rc = plan_chunk(&h, in, 0, p, &blob, nullptr);
     if (rc) return rc;
+    // out[7] (in/out): if > 0 on entry, re-plan that many times with warm buffers and report the mean ns
+    if (out[7] > 0) {
+        const int reps = (int)out[7];
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r) plan_chunk(&h, in, 0, p, &blob, nullptr);
+        out[7] = (int64_t)(std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / reps);
+    }
     int groups = 0;
     for (auto& fc : p.fast) groups += fc.n_groups;
     out[0] = p.n; out[1] = p.n_fast_pairs; out[2] = p.n_exact[0] + p.n_exact[1] + p.n_exact[2];

@@ -27,6 +27,7 @@
 //   * symbols outside {A,C,G,T,N}: the pair is flagged and fully redone by the exact kernel.
 #pragma once
 #include "common.cuh"
+#include "fast_cell.cuh"
 #include "fast_layout.cuh"
 #include "kernels_exact.cuh"
 
@@ -38,7 +39,6 @@ constexpr int kFastMaxQlen = kFastLanes * kFastMaxC;  // 256
 constexpr int kFastMaxTlen = 2047;
 constexpr int kFastGroupsPerWarp = 4;
 constexpr int kFastWarpsPerBlock = 4;
-constexpr int kBias = 64;  // every stored half = value + kBias; E,F >= -(mismatch+gap_oe) > -kBias
 
 struct FastGroup {
     uint32_t a, b;      // pair indices in the chunk (b == a: lone pair; a == 0xFFFFFFFF: empty slot)
@@ -53,35 +53,6 @@ struct RedoHeader {
     unsigned int pad;
     unsigned long long scratch_used; // bytes handed out from the redo scratch region
 };
-
-struct FastConsts {
-    uint32_t zero;     // (kBias, kBias)
-    uint32_t neg_x;    // ring constant: subtract mismatch from both halves
-    uint32_t neg_xoe;  // subtract mismatch + gap_oe
-    uint32_t neg_e;    // per-half s16 (-gap_ext) for VIADDMNMX
-    uint32_t k_f, k_e, k_d, k_n;
-    uint32_t x_pair;   // (mismatch, mismatch): biased profile value of a zero-scoring cell
-    uint32_t prof_match;  // match + mismatch (byte)
-    int bias;
-};
-
-__host__ __device__ inline uint32_t pair16(int v) { return ((uint32_t)(v & 0xFFFF) << 16) | (uint32_t)(v & 0xFFFF); }
-
-__host__ inline FastConsts make_fast_consts(const Scoring& sc) {
-    FastConsts k;
-    k.bias = kBias;
-    k.zero = pair16(kBias);
-    k.neg_x = (uint32_t)(0u - (uint32_t)sc.mismatch * 0x00010001u);
-    k.neg_xoe = (uint32_t)(0u - (uint32_t)(sc.mismatch + sc.gap_oe) * 0x00010001u);
-    k.neg_e = pair16(-sc.gap_ext);
-    k.k_f = pair16(sc.gap_ext + 0x7FFF);
-    k.k_e = pair16(sc.gap_ext + 0x3FFF);
-    k.k_d = pair16(0x1FFF);
-    k.k_n = pair16(0x0FFF);
-    k.x_pair = pair16(sc.mismatch);
-    k.prof_match = (uint32_t)(sc.match + sc.mismatch);
-    return k;
-}
 
 // Can the packed kernel represent this scoring?  (biased halves must stay in [0, 2^12) for the flag trick)
 __host__ inline bool fast_scoring_ok(const Scoring& sc) {
@@ -108,18 +79,6 @@ __host__ __device__ inline uint32_t profile_word(uint32_t code, const FastConsts
     if (code < 4u) return k.prof_match << (8u * code);
     if (code == 4u) return (k.x_pair & 0xFFu) * 0x01010101u;
     return 0u;
-}
-
-// PTX prmt in its default mode: selector nibble bit 3 replicates the sign of the chosen byte (the
-// __byte_perm intrinsic masks that bit away).
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
-
-__device__ __forceinline__ uint32_t bitsel(uint32_t mask, uint32_t a, uint32_t b) {  // mask ? a : b, one LOP3
-    return (a & mask) | (b & ~mask);
 }
 
 __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
@@ -184,22 +143,9 @@ struct FastDp {
                 for (int c = 0; c < C; ++c) {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
                     if (c < C - 1 || wide) {
-                        const uint32_t tmp = S[c] + k.neg_x;
-                        const uint32_t tg = S[c] + k.neg_xoe;
-                        const uint32_t e = E[c];
-                        const uint32_t u = __vimax3_s16x2(F, e, k.zero);
-                        const uint32_t h = __vmaxs2(tmp, u);
-                        const uint32_t fn = __viaddmax_s16x2(F, k.neg_e, tg);
-                        const uint32_t en = __viaddmax_s16x2(e, k.neg_e, tg);
-                        const uint32_t fo = fn - F + k.k_f;   // bit15: F opened
-                        const uint32_t eo = en - e + k.k_e;   // bit14: E opened
-                        const uint32_t nd = h - tmp + k.k_d;  // bit13: H != diagonal
-                        const uint32_t nf = u - F + k.k_n;    // bit12: max(F,E,0) != F
-                        uint32_t fl = bitsel(0x80008000u, fo, eo);
-                        fl = bitsel(0xC000C000u, fl, nd);
-                        fl = bitsel(0xE000E000u, fl, nf);
+                        uint32_t h, fn, en, fl, key;
+                        fast_cell(k, S[c], F, E[c], pair16(31 - c), h, fn, en, fl, key);
                         acc = bitsel(0xF000F000u, fl, acc >> 4);
-                        const uint32_t key = h * 32u + pair16(31 - c);
                         if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
                         else if (c == C - 1) rowkey = __vmaxs2(rowkey, key);
                         key_prev = key;

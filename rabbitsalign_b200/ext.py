@@ -42,7 +42,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_fast", C.c_int64), ("pairs_exact", C.c_int64),
                 ("pairs_failed", C.c_int64), ("cells", C.c_int64), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("dp_ms", C.c_double), ("tb_ms", C.c_double), ("pairs_redo", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("dp_ms", C.c_double), ("tb_ms", C.c_double), ("pairs_redo", C.c_int64), ("host_plan_ms", C.c_double)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -251,13 +251,15 @@ class ExtensionEngine:
         return s.asdict()
 
 
-def plan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, exact_only: bool = False) -> dict:
+def plan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, exact_only: bool = False,
+               time_reps: int = 0) -> dict:
     """Host-only planning probe (no CUDA call): how the first chunk of a batch would be routed."""
     lib = load_library()
     out = np.zeros(8, np.int64)
+    out[7] = time_reps
     rc = lib.rsa_ext_plan_debug(len(qoff) - 1, qoff.ctypes.data, toff.ctypes.data, scratch_cap, int(exact_only),
                                 out.ctypes.data)
     if rc != 0:
         raise ExtensionError(rc, "plan_debug failed")
-    keys = ["pairs", "fast_pairs", "exact_pairs", "failed", "groups", "scratch_bytes", "fast_classes"]
+    keys = ["pairs", "fast_pairs", "exact_pairs", "failed", "groups", "scratch_bytes", "fast_classes", "plan_ns"]
     return dict(zip(keys, out.tolist()))

@@ -12,15 +12,17 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include "../rabbitsalign_b200/csrc/fast_cell.cuh"
 
 #define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 static int g_iters = 32768;
+static rsa::FastConsts g_consts;
 constexpr int CH = 8;
 
 enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL, N_OPS };
 static const char* kNames[N_OPS] = {"VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "IADD3", "LOP3", "PRMT",
-                                    "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (19 instr / 2 cells)"};
+                                    "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (rsa::fast_cell, 2 cells per call)"};
 static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0};
 
 template <int OP>
@@ -59,48 +61,42 @@ __global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cyc
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-// The packed cell recipe of kernels_fast.cuh, with the same data flow (biased halves, IADD3 flag trick,
-// bit-selects), on 8 independent columns per thread: what one lane does per target row.
-__global__ void bench_cell(uint32_t* out, const uint32_t* in, unsigned long long* cycles, int ITERS) {
-    uint32_t Hp[CH], E[CH], cb[CH], qsel[CH];
-    const uint32_t zero = in[0], negx = in[1], negxoe = in[2], nege = in[3], kf = in[4], ke = in[5], kd = in[6], kn = in[7];
+// The packed cell recipe of the product kernel -- rsa::fast_cell() from csrc/fast_cell.cuh, the very same
+// function -- on 8 columns per thread with the kernel's per-row data flow (phase 1: S[c] = S[c-1] + PRMT(...);
+// phase 2: the F chain, direction-nibble packing, key maximum), but no shuffles, no shared/global memory, no
+// wavefront skew: what one lane could do per target row if nothing else existed.
+__global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+    uint32_t S[CH], E[CH], qsel[CH];
     uint32_t px = in[8] + threadIdx.x, py = in[9];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) { Hp[k] = zero; E[k] = zero; cb[k] = zero; qsel[k] = in[10 + k]; }
-    uint32_t F = zero, diag = zero, acc = 0, rm = zero, sink = 0;
+    for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = k.zero; qsel[c] = in[10 + c]; }
+    uint32_t F = k.zero, Hl = k.zero, rowkey = 0, sink = 0;
     __syncthreads();
     const unsigned long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            uint32_t sub; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sub) : "r"(px), "r"(py), "r"(qsel[k]));
-            const uint32_t tmp = diag + sub + negx;
-            const uint32_t tg = diag + sub + negxoe;
-            const uint32_t e = E[k];
-            const uint32_t u = __vimax3_s16x2(F, e, zero);
-            const uint32_t h = __vmaxs2(tmp, u);
-            const uint32_t fn = __viaddmax_s16x2(F, nege, tg);
-            const uint32_t en = __viaddmax_s16x2(e, nege, tg);
-            const uint32_t fo = fn - F + kf, eo = en - e + ke, nd = h - tmp + kd, nf = u - F + kn;
-            uint32_t fl = (fo & 0x80008000u) | (eo & ~0x80008000u);
-            fl = (fl & 0xC000C000u) | (nd & ~0xC000C000u);
-            fl = (fl & 0xE000E000u) | (nf & ~0xE000E000u);
-            acc = (fl & 0xF000F000u) | ((acc >> 4) & ~0xF000F000u);
-            cb[k] = __vmaxs2(cb[k], h);
-            rm = __vmaxs2(rm, h);
-            diag = Hp[k];
-            Hp[k] = h;
-            E[k] = en;
+        for (int c = CH - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
+        uint32_t acc = 0, key_prev = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uint32_t h, fn, en, fl, key;
+            rsa::fast_cell(k, S[c], F, E[c], rsa::pair16(31 - c), h, fn, en, fl, key);
+            acc = rsa::bitsel(0xF000F000u, fl, acc >> 4);
+            if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
+            key_prev = key;
+            S[c] = h;
+            E[c] = en;
             F = fn;
-            if ((k & 3) == 3) { sink ^= acc; acc = 0; }
+            if ((c & 3) == 3) { sink ^= acc; acc = 0; }
         }
+        Hl = F;
         px += py;
     }
     const unsigned long long t1 = clock64();
-    uint32_t s = sink + rm + F;
+    uint32_t s = sink + rowkey + F;
 #pragma unroll
-    for (int k = 0; k < CH; ++k) s += Hp[k] + E[k] + cb[k];
+    for (int c = 0; c < CH; ++c) s += S[c] + E[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -113,7 +109,7 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
     CHECK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 3; ++rep) {
         CHECK(cudaEventRecord(e0));
-        if (OP == CELL) bench_cell<<<blocks, threads>>>(d_out, d_in, d_cyc, g_iters);
+        if (OP == CELL) bench_cell<<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
         else bench<OP><<<blocks, threads>>>(d_out, d_in, d_cyc, g_iters);
         CHECK(cudaEventRecord(e1));
         CHECK(cudaEventSynchronize(e1));
@@ -152,6 +148,7 @@ int main(int argc, char** argv) {
     CHECK(cudaGetDeviceProperties(&prop, 0));
     const int n_sms = prop.multiProcessorCount;
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, n_sms, prop.clockRate);
+    g_consts = rsa::make_fast_consts(rsa::Scoring{2, 8, 12, 1});
     uint32_t *d_out, *d_in;
     unsigned long long* d_cyc;
     CHECK(cudaMalloc(&d_out, sizeof(uint32_t) * n_sms * 8 * 1024));
