@@ -226,7 +226,8 @@ def main():
     from rabbitsalign_b200 import ExtensionEngine
     from rabbitsalign_b200.ext import RESULT_DTYPE
 
-    batch = make_batch(args.pairs, args.read_len, seed=43 + rank)
+    from rabbitsalign_b200 import sharding
+    batch = make_batch(args.pairs, args.read_len, seed=sharding.rank_seed(43, rank))
     eng = ExtensionEngine(device=local_rank)
 
     # pinned host copies (the C ABI copies straight from/to pinned memory)
@@ -264,13 +265,8 @@ def main():
     st = eng.stats()  # dp_ms / tb_ms of the last step (events around the kernels)
     clocks = sampler.stop()
     launches_per_step = st["kernel_launches"]
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    cells = torch.tensor([float(batch.cells)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-    ms_step = float(t_ms.item()) / args.steps
-    total_cells = float(cells.item())
+    t_max, total_cells = sharding.reduce_step(ms_total, float(batch.cells), dist, device="cuda")
+    ms_step = t_max / args.steps
     value = total_cells / (ms_step * 1e-3) / 1e9
     res_resident = eng.fetch_resident(batch.n)
 
@@ -285,10 +281,8 @@ def main():
         eng.wait()
     dt = time.perf_counter() - t0
     st_e2e = eng.stats()
-    t_e = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = total_cells / (float(t_e.item()) / args.steps) / 1e9
+    dt_max, _ = sharding.reduce_step(dt, 0.0, dist, device="cuda")
+    e2e_value = total_cells / (dt_max / args.steps) / 1e9
     same = bool(results.tobytes() == res_resident.tobytes())
     ok = bool((results["status"] == 0).all() and (results["score"] > 0).mean() > 0.99)
 
@@ -344,7 +338,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"],
-                "ms_per_step": float(t_e.item()) / args.steps * 1e3, "host_plan_ms_per_step": st_e2e["host_plan_ms"]},
+                "ms_per_step": dt_max / args.steps * 1e3, "host_plan_ms_per_step": st_e2e["host_plan_ms"]},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
     }

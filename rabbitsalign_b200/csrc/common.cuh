@@ -33,7 +33,8 @@ enum : uint32_t {
     DPF_DONE = 1u,       // a DP kernel produced score/end and direction bits for this pair
     DPF_NEED_EXACT = 2u, // the fast kernel declined (tie on the maximum, unsupported symbol, ...)
     DPF_LAYOUT_FAST = 4u, // direction bits are in the fast kernel's layout
-    DPF_NO_SCRATCH = 8u   // the redo pass ran out of scratch for this pair: status 4, the host re-submits it
+    DPF_NO_SCRATCH = 8u,  // the redo pass ran out of scratch for this pair: status 4, the host re-submits it
+    DPF_TRACED = 16u      // the packed kernel already traced this pair back and wrote its record
 };
 
 // Direction-nibble code, identical to the reference's (local_kernel_template.h:45-60):

@@ -7,8 +7,8 @@
 //
 // Shape of the engine (B200-first, not GASAL2's):
 //   * a batch of any size is cut into chunks whose direction-bit scratch fits the handle's budget;
-//   * two chunk slots are double-buffered over three streams (H2D, compute, D2H) so the copies of chunk
-//     k+1 overlap the kernels of chunk k; per chunk there is ONE metadata blob copy, two sequence copies
+//   * three chunk slots rotate over four streams (H2D, DP, traceback, D2H) so the copies of chunk k+1 overlap
+//     the kernels of chunk k; per chunk there is ONE metadata blob copy, two sequence copies
 //     in and one 64-byte-record copy out (the reference issues ~13 small copies per 512 pairs);
 //   * the host plans each chunk (length classes, equal-length pairing for the packed kernel, scratch
 //     offsets) while the GPU works on the previous one;
@@ -36,10 +36,10 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;  // chunks in flight: one computing, one with its copies in flight, one being planned/retired
 constexpr int64_t kMaxChunkPairs = 1 << 17;
 constexpr int64_t kMaxChunkSeqBytes = (int64_t)1 << 30;
-constexpr int64_t kDefaultScratch = (int64_t)8 << 30;  // both slots together
+constexpr int64_t kDefaultScratch = (int64_t)12 << 30;  // all slots together (allocated lazily, per slot, as needed)
 constexpr int kMaxTargetLenCap = 8192;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -225,7 +225,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
             need = (uint64_t)tl * LT.exact_row_bytes_[ql] + 16;
             if (fast_shape_ok((int)ql, (int)tl))  // a lone pair owns a whole group
-                need = std::max<uint64_t>(need, (uint64_t)tl * LT.fast_row_bytes[ql]);
+                need = std::max<uint64_t>(need, (uint64_t)((tl + 3) & ~3) * LT.fast_row_bytes[ql]);
         }
         if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
                         in.toff[hi + 1] - t0 > kMaxChunkSeqBytes))
@@ -359,7 +359,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
             groups[n_groups++] = fg;
             diroff[a] = sc_off;
             if (b != a) { diroff[b] = sc_off; info[b] |= 1u; }
-            sc_off += (uint64_t)rows * LT.fast_row_bytes[ql];
+            sc_off += (uint64_t)((rows + 3) & ~3u) * LT.fast_row_bytes[ql];
             plan.fast.back().max_tlen = std::max<int>(plan.fast.back().max_tlen, (int)rows);
             plan.n_fast_pairs += (b != a) ? 2 : 1;
         }
@@ -427,11 +427,12 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     uint64_t* diroff = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(d.blob) + p.off_diroff);
     RedoHeader* redo = reinterpret_cast<RedoHeader*>(const_cast<uint8_t*>(d.blob) + p.off_redo);
     uint32_t* redo_list = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(d.blob) + p.off_redo + sizeof(RedoHeader));
-    // packed kernel, one launch per column class
+    TbArgs tba{d.q, d.t, meta, info, diroff, d.scratch, d.res, h->sc, d.arena, d.arena_used, d.arena_cap};
+    // packed kernel, one launch per column class (traces its own pairs back)
     for (const auto& fc : p.fast) {
         int rc = launch_fast_class(st, fc.C, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
-                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen);
+                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen, tba);
         if (rc != 0) { h->err = "no packed-kernel instance for C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
@@ -461,8 +462,16 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     CU_TRY(h, cudaEventRecord(ev_mid, st));
     CU_TRY(h, cudaStreamWaitEvent(st_tb, ev_mid, 0));
     if (ev) CU_TRY(h, cudaEventRecord(ev[2], st_tb));
-    tb_kernel<<<(unsigned)((p.n + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st_tb>>>(
-        d.q, d.t, meta, info, (int)p.n, diroff, d.scratch, d.ends, d.res, h->sc, d.arena, d.arena_used, d.arena_cap);
+    if (!p.fast.empty()) {
+        // the packed kernel's pairs, in group order (pairs a and b of a group walk the same words)
+        int total_groups = 0;
+        for (const auto& fc : p.fast) total_groups = std::max(total_groups, fc.group_begin + fc.n_groups);
+        tb_groups_kernel<<<(unsigned)((2 * total_groups + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st_tb>>>(
+            tba, reinterpret_cast<const FastGroupRef*>(d.blob + p.off_groups), total_groups, d.ends);
+        h->stats.kernel_launches++;
+    }
+    // everything else: exact-kernel pairs, redone pairs, failed records
+    tb_kernel<<<(unsigned)((p.n + kTbThreads - 1) / kTbThreads), kTbThreads, 0, st_tb>>>(tba, (int)p.n, d.ends);
     h->stats.kernel_launches++;
     if (ev) CU_TRY(h, cudaEventRecord(ev[3], st_tb));
     CU_TRY(h, cudaGetLastError());
@@ -625,7 +634,13 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
-    if ((e = cudaStreamCreateWithFlags(&h->s_tb, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    {
+        // the traceback stream outranks the DP stream: its small blocks are placed first whenever a DP block
+        // retires, so the records of chunk k are not held back by the DP kernel of chunk k+1
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&h->s_tb, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("stream", e);
+    }
     if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     for (Slot& s : h->slots) {
         if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
@@ -880,7 +895,7 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
     if ((rc = ensure_dev(h, h->r_t, tbytes + 16))) return rc;
     if ((rc = ensure_dev(h, h->r_res, sizeof(rsa_ext_result_t) * (size_t)n))) return rc;
     if ((rc = ensure_dev(h, h->r_blobs, blob_total))) return rc;
-    for (int k = 0; k < (h->res_chunks.size() > 1 ? kSlots : 1); ++k) {  // chunks alternate between the slots' scratch
+    for (int k = 0; k < (h->res_chunks.size() > 1 ? 2 : 1); ++k) {  // resident chunks alternate between two slots' scratch
         Slot& s = h->slots[k];
         if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * max_pairs))) return rc;
         if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(max_scratch)))) return rc;
@@ -912,7 +927,7 @@ extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     h->stats.kernel_launches = 0;
-    const int nslots = h->res_chunks.size() > 1 ? kSlots : 1;
+    const int nslots = h->res_chunks.size() > 1 ? 2 : 1;
     for (size_t c = 0; c < h->res_chunks.size(); ++c) {
         const ResidentChunk& rcx = h->res_chunks[c];
         Slot& s = h->slots[c % nslots];

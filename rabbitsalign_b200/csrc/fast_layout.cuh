@@ -6,7 +6,10 @@
 // every owned column is a real query base (no padding columns exist).
 //
 // Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
-//     uint32 index = (r*W + w)*8 + l,   W = ceil(C/4)   (for a fixed word w the 8 lanes are contiguous)
+//     uint32 index = (((r>>2)*W + w)*8 + l)*4 + (r&3),   W = ceil(C/4)
+// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); for a fixed (row block, w) the 8 lanes'
+// chunks are contiguous (one 128-byte line), so the DP kernel stores full lines with one STG.128 per lane and
+// the traceback, which moves diagonally, finds ~2-3 consecutive path cells in the chunk it just fetched.
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
 //     bit3 open_f   (F of the next column opened from the diagonal; reference bit3 is the negation)
 //     bit2 open_e   (reference bit2 negated)
@@ -35,7 +38,7 @@ __host__ __device__ inline FastGeom fast_geom(int qlen) {
 
 // bytes of direction scratch of one group (two pairs) with `rows` target rows
 __host__ __device__ inline uint64_t fast_dir_bytes(const FastGeom& g, int rows) {
-    return (uint64_t)rows * kFastLanes * g.W * 4u;
+    return (uint64_t)((rows + 3) & ~3) * kFastLanes * g.W * 4u;
 }
 
 // first column owned by lane l
@@ -49,7 +52,7 @@ __device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const ui
     const int wide = g.rem * g.C;
     if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
     else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
-    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((size_t)i * g.W + (cc >> 2)) * kFastLanes + lane];
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.W + (cc >> 2)) * kFastLanes + lane) << 2) + (i & 3)];
     const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
     return (h16 >> (4 * (cc & 3))) & 0xFu;
 }

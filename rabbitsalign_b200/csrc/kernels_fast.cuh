@@ -30,6 +30,7 @@
 #include "fast_cell.cuh"
 #include "fast_layout.cuh"
 #include "kernels_exact.cuh"
+#include "kernels_tb.cuh"
 
 namespace rsa {
 
@@ -39,6 +40,13 @@ constexpr int kFastMaxQlen = kFastLanes * kFastMaxC;  // 256
 constexpr int kFastMaxTlen = 2047;
 constexpr int kFastGroupsPerWarp = 4;
 constexpr int kFastWarpsPerBlock = 4;
+// Trace pairs back inside the DP kernel (lanes 0/1 of each group) instead of in tb_kernel.  Measured on B200:
+// 1.36 vs 1.50 TCUPS per step -- the 8 walking lanes keep the warp's registers for ~150 dependent HBM round trips
+// (the block's tiles are long out of L2), which costs the ALU-bound DP more latency hiding than the separate
+// kernel costs in time.  Kept for experiments.
+#ifndef RSA_FUSED_TRACEBACK
+#define RSA_FUSED_TRACEBACK 0
+#endif
 
 struct FastGroup {
     uint32_t a, b;      // pair indices in the chunk (b == a: lone pair; a == 0xFFFFFFFF: empty slot)
@@ -46,6 +54,8 @@ struct FastGroup {
     uint16_t qlen;
     uint16_t rows;      // max(|t_a|, |t_b|)
 };
+
+static_assert(sizeof(FastGroup) == sizeof(FastGroupRef), "FastGroupRef must mirror FastGroup");
 
 // Per-chunk redo bookkeeping living in the metadata blob (host zeroes it before the upload).
 struct RedoHeader {
@@ -165,7 +175,7 @@ struct FastDp {
                 // direction words of this lane and row: parked in this lane's shared-memory ring until every
                 // lane of the group has reached the same row (see below)
 #pragma unroll
-                for (int wv = 0; wv < NW; ++wv) ring[(((s & 7) * NW + wv) << 5) + lane] = words[wv];
+                for (int wv = 0; wv < NW; ++wv) ring[(((s & 15) * NW + wv) << 5) + lane] = words[wv];
                 // Running maximum of this lane, per half, kept as the FIRST cell in the reference's visiting order
                 // (8-row block, column, row in block) among the cells seen so far with the largest H:
                 //   row H > best H                      -> this row's key wins;
@@ -183,15 +193,23 @@ struct FastDp {
             }
             Hl_prev = (gl == 0) ? k.zero : Hl;
             pr = prn;
-            // De-skewed store: at step s every lane of the group stores ITS OWN words of row s-7 (lane gl
-            // computed that row 7-gl steps ago), so each store instruction covers 8 consecutive words per
-            // group (one 32-byte sector) instead of 8 scattered ones.
-            const int rr = s - (kFastLanes - 1);
-            if (rr >= 0 && rr < rows) {
-                const int slot = (rr + gl) & 7;
-                uint32_t* drow = dir + (size_t)rr * (NW * kFastLanes) + gl;
+            // De-skewed, row-blocked store: lane gl computed row r at step r+gl and parked its words in ring slot
+            // (r+gl)&15.  When the group's LAST lane has finished the last row of a 4-row block (step = 4b+3+7),
+            // every lane stores ITS OWN words of rows 4b..4b+3 as one 16-byte chunk per word: 8 lanes x 16 B = one
+            // full 128-byte line per store instruction and group.
+            const int rl = s - (kFastLanes - 1);          // row the last lane finished in this step
+            if (rl >= 0 && (rl & 3) == 3 && rl - 3 < rows) {
+                const int rb = rl >> 2;
+                uint4* dblk = reinterpret_cast<uint4*>(dir) + (size_t)rb * (NW * kFastLanes) + gl;
 #pragma unroll
-                for (int wv = 0; wv < NW; ++wv) drow[wv * kFastLanes] = ring[((slot * NW + wv) << 5) + lane];
+                for (int wv = 0; wv < NW; ++wv) {
+                    uint4 v;
+                    v.x = ring[((((rl - 3 + gl) & 15) * NW + wv) << 5) + lane];
+                    v.y = ring[((((rl - 2 + gl) & 15) * NW + wv) << 5) + lane];
+                    v.z = ring[((((rl - 1 + gl) & 15) * NW + wv) << 5) + lane];
+                    v.w = ring[((((rl + gl) & 15) * NW + wv) << 5) + lane];
+                    dblk[wv * kFastLanes] = v;
+                }
             }
         }
         bestkey_out = bestkey;
@@ -203,7 +221,7 @@ __global__ void __launch_bounds__(32 * kFastWarpsPerBlock, (C <= 20 ? 4 : (C <= 
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
-               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad) {
+               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad, TbArgs tba) {
     extern __shared__ uint8_t fast_smem[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 words
     if (threadIdx.x < 8) lut[threadIdx.x] = profile_word(threadIdx.x, k);
@@ -215,7 +233,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     if (g_index < n_groups) grp = groups[g_index];
     const bool live = grp.a != 0xFFFFFFFFu;
     uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * kFastGroupsPerWarp + gi) * rows_pad;
-    constexpr int kRingWords = 8 * ((C + 3) / 4) * 32;  // per warp
+    constexpr int kRingWords = 16 * ((C + 3) / 4) * 32;  // per warp: 16 row slots x words x lanes
     uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + 32 + (size_t)kFastWarpsPerBlock * kFastGroupsPerWarp * rows_pad) + warp * kRingWords;
 
     // ---- staging: target profiles into shared memory, query selectors into registers ----------------
@@ -264,7 +282,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     bad_a = (__ballot_sync(0xFFFFFFFFu, bad_a) & gmask) != 0;
     bad_b = (__ballot_sync(0xFFFFFFFFu, bad_b) & gmask) != 0;
     const bool warp_has_n = __any_sync(0xFFFFFFFFu, has_n);
-    int nsteps = rows + kFastLanes - 1;
+    int nsteps = ((rows + 3) & ~3) + kFastLanes - 1;  // rows rounded up: the last row block is flushed in-loop
     if (!live) nsteps = 0;
 #pragma unroll
     for (int off = 16; off >= 8; off >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xFFFFFFFFu, nsteps, off));
@@ -278,7 +296,12 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
 
     // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
     // Every lane holds its first-in-reference-order maximum cell; lanes own increasing column ranges, so among
-    // the lanes reaching the pair's maximum the winner is the smallest (8-row block, lane).
+    // the lanes reaching the pair's maximum the winner is the smallest (8-row block, lane).  Lane 0 of the group
+    // then owns pair a and lane 1 pair b: they publish the DpEnd and trace the pair back right away, while the
+    // group's direction tile is still in L2 (the stand-alone traceback kernel would fetch it from HBM).
+    DpEnd my_end;
+    my_end.score = 0; my_end.qend = 0; my_end.tend = 0; my_end.flags = 0;
+    int my_pair = -1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const uint32_t pi = h ? grp.b : grp.a;
@@ -292,21 +315,26 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         int key = cand ? (((firstrow[h] >> 3) << 8) | gl) : 0x7FFFFFFF;
 #pragma unroll
         for (int off = 4; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
-        if (!live || (h == 1 && grp.b == grp.a)) continue;
-        const bool winner = (S > 0) ? ((key & 0xFF) == gl) : (gl == 0);
-        if (!winner) continue;
-        DpEnd e;
-        e.score = S; e.qend = 0; e.tend = 0;  // S == 0: the reference's maximum trackers stay at (0,0)
-        e.flags = DPF_DONE | DPF_LAYOUT_FAST;
-        if (bad) {
-            e.flags = DPF_NEED_EXACT;  // symbols outside {A,C,G,T,N}: full exact redo (own direction tile)
+        const int wl = (S > 0) ? (key & 0xFF) : 0;  // winner lane of the group (S == 0: trackers stay at (0,0))
+        const int qend = __shfl_sync(0xFFFFFFFFu, col0 + (31 - (kh & 31)), wl, kFastLanes);
+        const int tend = __shfl_sync(0xFFFFFFFFu, firstrow[h], wl, kFastLanes);
+        if (!live || (h == 1 && grp.b == grp.a) || gl != h) continue;
+        my_pair = (int)pi;
+        my_end.score = S;
+        my_end.qend = S > 0 ? qend : 0;
+        my_end.tend = S > 0 ? tend : 0;
+        my_end.flags = bad ? DPF_NEED_EXACT : (DPF_DONE | DPF_LAYOUT_FAST | (RSA_FUSED_TRACEBACK ? DPF_TRACED : 0u));
+    }
+    __syncwarp();  // the group's direction words (stored by all 8 lanes) are visible to lanes 0 and 1 now
+    if (my_pair >= 0) {
+        ends[my_pair] = my_end;
+        if (my_end.flags & DPF_NEED_EXACT) {
+            // symbols outside {A,C,G,T,N}: full exact redo (own direction tile), traced by tb_kernel afterwards
             const unsigned int slot = atomicAdd(&redo->count, 1u);
-            redo_list[slot] = pi;
-        } else if (S > 0) {
-            e.qend = col0 + (31 - (kh & 31));
-            e.tend = firstrow[h];
+            redo_list[slot] = (uint32_t)my_pair;
+        } else if (RSA_FUSED_TRACEBACK) {
+            tb_one_pair(tba, my_pair, my_end);
         }
-        ends[pi] = e;
     }
 }
 
@@ -462,23 +490,23 @@ namespace rsa {
 template <int C>
 inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                            uint32_t* redo_list, const FastConsts& k, int max_rows) {
+                            uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
     const int rows_pad = (max_rows + 15) & ~15;
     const int groups_per_block = kFastWarpsPerBlock * kFastGroupsPerWarp;
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)kFastWarpsPerBlock * 8 * ((C + 3) / 4) * 32 * 4;
+    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)kFastWarpsPerBlock * 16 * ((C + 3) / 4) * 32 * 4;
     if (smem > 48 * 1024)  // long windows: opt in to more dynamic shared memory (per device, cheap to repeat)
         cudaFuncSetAttribute(fast_dp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     fast_dp_kernel<C><<<blocks, 32 * kFastWarpsPerBlock, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
-                                                                     redo, redo_list, k, rows_pad);
+                                                                     redo, redo_list, k, rows_pad, tba);
 }
 
 // returns 0, or -1 when C is outside the instantiated range
 inline int launch_fast_class(cudaStream_t st, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                              const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                             uint32_t* redo_list, const FastConsts& k, int max_rows) {
+                             uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
     switch (C) {
-#define RSA_FAST_CASE(c) case c: launch_fast_one<c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+#define RSA_FAST_CASE(c) case c: launch_fast_one<c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
         RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6)
         RSA_FAST_CASE(7) RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12)
         RSA_FAST_CASE(13) RSA_FAST_CASE(14) RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18)

@@ -85,52 +85,51 @@ __device__ inline int tb_walk(const TbCtx& c, int score, int tend, int qend, con
     return n_ops;
 }
 
-// info word of PairMeta-side planning (host): status for pairs no DP kernel ran on
-constexpr int kTbThreads = 128;
+// Everything the walker needs besides the pair's own DpEnd.
+struct TbArgs {
+    const uint8_t* qbuf;
+    const uint8_t* tbuf;
+    const PairMeta* meta;
+    const uint32_t* info;     // bit 0: which half of the packed words; bits 16..: status of pairs no kernel ran on
+    const uint64_t* dir_off;
+    const uint8_t* scratch;
+    rsa_ext_result_t* res;
+    Scoring sc;
+    uint8_t* arena;
+    unsigned long long* arena_used;
+    unsigned long long arena_cap;
+};
 
-__global__ void __launch_bounds__(kTbThreads)
-tb_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
-          const PairMeta* __restrict__ meta, const uint32_t* __restrict__ info, int n,
-          const uint64_t* __restrict__ dir_off, const uint8_t* __restrict__ scratch,
-          const DpEnd* __restrict__ ends, rsa_ext_result_t* __restrict__ res, Scoring sc,
-          uint8_t* __restrict__ arena, unsigned long long* __restrict__ arena_used,
-          unsigned long long arena_cap) {
-    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= n) return;
-    const DpEnd e = ends[pi];
+// Trace one pair back and write its 64-byte record.  Shared (not inlined) by the stand-alone traceback
+// kernel and by the packed DP kernel, which traces its own pairs right after computing them while their
+// direction tiles are still in L2.
+__device__ __noinline__ void tb_one_pair(const TbArgs& a, int pi, DpEnd e) {
     rsa_ext_result_t r;
 #pragma unroll
     for (int k = 0; k < RSA_EXT_RLE_INLINE; ++k) r.rle[k] = 0;
-    if (!(e.flags & DPF_DONE)) {
-        // not aligned: empty sequence / window longer than max_target_len (host decided)
-        r.score = 0; r.query_start = -1; r.query_end = -1; r.ref_start = -1; r.ref_end = -1;
-        r.n_ops = 0; r.status = (e.flags & DPF_NO_SCRATCH) ? (int16_t)4 : (int16_t)(info[pi] >> 16);
-        res[pi] = r;
-        return;
-    }
-    const PairMeta m = meta[pi];
+    const PairMeta m = a.meta[pi];
     TbCtx c;
-    c.q = qbuf + m.qoff;
-    c.t = tbuf + m.toff;
-    c.dir = scratch + dir_off[pi];
+    c.q = a.qbuf + m.qoff;
+    c.t = a.tbuf + m.toff;
+    c.dir = a.scratch + a.dir_off[pi];
     c.qlen = m.qlen;
     c.tlen = m.tlen;
     c.fast = (e.flags & DPF_LAYOUT_FAST) != 0;
     c.row_bytes = exact_row_bytes(m.qlen);
-    c.half = (int)(info[pi] & 1u);
+    c.half = (int)(a.info[pi] & 1u);
     c.fg = fast_geom(m.qlen);
     int si, sj;
-    int n_ops = tb_walk(c, e.score, e.tend, e.qend, sc, r.rle, RSA_EXT_RLE_INLINE, nullptr, &si, &sj);
+    int n_ops = tb_walk(c, e.score, e.tend, e.qend, a.sc, r.rle, RSA_EXT_RLE_INLINE, nullptr, &si, &sj);
     r.status = 0;
     if (n_ops > RSA_EXT_RLE_INLINE) {
         // rare: long CIGAR.  Reserve n_ops bytes in the chunk's arena and walk again writing all of them;
         // the arena offset rides in the last 8 inline bytes.
-        const unsigned long long off = atomicAdd(arena_used, (unsigned long long)n_ops);
-        if (off + (unsigned long long)n_ops <= arena_cap) {
-            tb_walk(c, e.score, e.tend, e.qend, sc, r.rle, 0, arena + off, &si, &sj);
+        const unsigned long long off = atomicAdd(a.arena_used, (unsigned long long)n_ops);
+        if (off + (unsigned long long)n_ops <= a.arena_cap) {
+            tb_walk(c, e.score, e.tend, e.qend, a.sc, r.rle, 0, a.arena + off, &si, &sj);
             memcpy(&r.rle[RSA_EXT_RLE_INLINE - 8], &off, 8);
         } else {
-            r.status = 2;  // arena exhausted: the engine re-runs this pair alone
+            r.status = 2;  // cannot happen: the arena is sized for the worst case of the chunk
         }
     }
     r.score = e.score;
@@ -139,7 +138,49 @@ tb_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
     r.ref_start = si;
     r.ref_end = e.tend;
     r.n_ops = (int16_t)n_ops;
-    res[pi] = r;
+    a.res[pi] = r;
+}
+
+constexpr int kTbThreads = 128;
+
+// Stand-alone traceback: every pair of the chunk that is not traced yet (exact-kernel pairs, redone pairs)
+// and the failed records of pairs no kernel ran on.
+__global__ void __launch_bounds__(kTbThreads) tb_kernel(TbArgs a, int n, const DpEnd* __restrict__ ends) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= n) return;
+    const DpEnd e = ends[pi];
+    if (e.flags & DPF_TRACED) return;
+    if (!(e.flags & DPF_DONE)) {
+        // not aligned: empty sequence / window longer than max_target_len (host decided), or no scratch (redo)
+        rsa_ext_result_t r;
+#pragma unroll
+        for (int k = 0; k < RSA_EXT_RLE_INLINE; ++k) r.rle[k] = 0;
+        r.score = 0; r.query_start = -1; r.query_end = -1; r.ref_start = -1; r.ref_end = -1;
+        r.n_ops = 0; r.status = (e.flags & DPF_NO_SCRATCH) ? (int16_t)4 : (int16_t)(a.info[pi] >> 16);
+        a.res[pi] = r;
+        return;
+    }
+    tb_one_pair(a, pi, e);
+}
+
+// Traceback of the packed kernel's pairs in GROUP order: threads 2g and 2g+1 trace pairs a and b of group g.
+// The two pairs share every direction word (low/high halves) and, with equal flanks, walk the same cells, so
+// their loads hit the same 16-byte chunks: one HBM sector serves both walkers.
+struct FastGroupRef { uint32_t a, b; uint64_t dir_off; uint16_t qlen, rows; };  // == FastGroup (kernels_fast.cuh)
+
+__global__ void __launch_bounds__(kTbThreads) tb_groups_kernel(TbArgs a, const FastGroupRef* __restrict__ groups,
+                                                               int n_groups, DpEnd* __restrict__ ends) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = t >> 1;
+    if (g >= n_groups) return;
+    const FastGroupRef grp = groups[g];
+    if (grp.a == 0xFFFFFFFFu) return;
+    if ((t & 1) && grp.b == grp.a) return;
+    const int pi = (int)((t & 1) ? grp.b : grp.a);
+    const DpEnd e = ends[pi];
+    if ((e.flags & (DPF_DONE | DPF_LAYOUT_FAST | DPF_TRACED)) != (DPF_DONE | DPF_LAYOUT_FAST)) return;
+    tb_one_pair(a, pi, e);
+    ends[pi].flags = e.flags | DPF_TRACED;
 }
 
 }  // namespace rsa
