@@ -216,7 +216,18 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces itself on stdout ("NCCL version ..."); keep stdout clean for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if dist is not None:
@@ -283,6 +294,16 @@ def main():
     st_e2e = eng.stats()
     dt_max, _ = sharding.reduce_step(dt, 0.0, dist, device="cuda")
     e2e_value = total_cells / (dt_max / args.steps) / 1e9
+    # ---- the reference's own call shape: blocking 512-pair slices (STREAM_BATCH_SIZE, src/pc.cpp:644-672) -----
+    n_slices = min(200, batch.n // 512)
+    t0 = time.perf_counter()
+    for k in range(n_slices):
+        eng.submit_raw(512, qbuf.ctypes.data, qoff.ctypes.data + 8 * 512 * k, tbuf.ctypes.data,
+                       toff.ctypes.data + 8 * 512 * k, results.ctypes.data + 64 * 512 * k)
+        eng.wait()
+    slice_dt = (time.perf_counter() - t0) / max(1, n_slices)
+    eng.submit(qbuf, qoff, tbuf, toff, results)  # restore the full-batch records for the check below
+    eng.wait()
     same = bool(results.tobytes() == res_resident.tobytes())
     ok = bool((results["status"] == 0).all() and (results["score"] > 0).mean() > 0.99)
 
@@ -334,7 +355,8 @@ def main():
                    "pairs_per_s": batch.n * n_gpus / (ms_step * 1e-3),
                    "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"],
                                "redo_last_chunk": st["pairs_redo"]},
-                   "resident_equals_e2e_records": same, "records_sane": ok},
+                   "resident_equals_e2e_records": same, "records_sane": ok,
+                   "slice512_one_worker": {"us_per_call": slice_dt * 1e6, "pairs_per_s": 512 / slice_dt if slice_dt > 0 else None}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"],
