@@ -151,3 +151,40 @@ def test_golden_vectors_from_reference_kernels(name, exact_only):
     e.close()
     bad = [(p["q"], p["t"], list(r.astuple()), p["res"]) for p, r in zip(g["pairs"], got) if list(r.astuple()) != p["res"]]
     assert not bad, bad[:3]
+
+
+def test_redo_scratch_exhaustion_is_retried(oracle_lib):
+    """Every query carries a symbol outside ACGTN, so the packed kernel flags all pairs for the exact redo pass;
+    their tiles (32 KB each) exceed the redo head-room, the surplus comes back with status 4 inside the engine
+    and rsa_ext_wait re-submits it exact-only.  The caller must see plain, exact records."""
+    from rabbitsalign_b200 import ExtensionEngine
+    b = W.extension_pairs(3000, seed=160)
+    q = b.qbuf.copy()
+    q[b.qoff[:-1] + 75] = ord("R")  # IUPAC purine: nibble 2, equal to nothing in ACGT
+    b = W.PairBatch(q, b.qoff, b.tbuf, b.toff)
+    e = ExtensionEngine()
+    res = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    st = e.stats()
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+    assert st["pairs_redo"] >= 3000  # all pairs went through the redo pass at least once
+
+
+def test_concurrent_handles_from_threads(oracle_lib):
+    """Several host workers, one handle each (the reference: one GASAL stream per worker thread)."""
+    import threading
+    from rabbitsalign_b200 import ExtensionEngine
+    batches = [W.extension_pairs(700, seed=170 + k, fixed_query_len=(k % 2 == 0)) for k in range(4)]
+    out = [None] * 4
+
+    def work(k):
+        e = ExtensionEngine()
+        for _ in range(3):
+            res = e.align_packed(batches[k].qbuf, batches[k].qoff, batches[k].tbuf, batches[k].toff)
+        out[k] = compare(e, res, oracle_arrays(oracle_lib, batches[k]), batches[k])
+        e.close()
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert all(o == [] for o in out), out
