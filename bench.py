@@ -321,9 +321,19 @@ def main():
     ql = np.diff(batch.qoff); tl = np.diff(batch.toff)
     dp_bytes = float(np.sum(ql + tl) + np.sum(ql * tl) / 2 + 16 * batch.n)
     hbm_achieved = dp_bytes / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+    # measured DRAM traffic of that kernel: ncu --set full capture of this round (profiles/*_traffic.json), scaled from
+    # bytes per cell to the bytes of one average launch of this run
+    traffic = None
+    n_dp_launches = max(1, (launches_per_step - 0) // 4)  # per chunk: packed DP, redo, group traceback, traceback
+    try:
+        tj = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))[-1]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tj)))["dram_bytes_per_cell"] * batch.cells / n_dp_launches
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": "fast_dp_kernel<C> (packed s16x2 DP + direction nibbles)",
                 "achieved": hbm_achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": (hbm_achieved / peaks["hbm_gbs"]) if hbm_achieved else None, "traffic": None,
+                "frac": (hbm_achieved / peaks["hbm_gbs"]) if hbm_achieved else None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": dp_bytes / n_dp_launches, "launches_per_step": n_dp_launches,
                 "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "note": "issue-bound by design (SURVEY 8d): see roofline_issue for the binding ceiling"}
     ceil = issue_ceiling()
