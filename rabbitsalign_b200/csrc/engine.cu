@@ -96,7 +96,10 @@ struct rsa_ext {
     FastConsts fk{};
     bool fast_ok = false;
     int n_sms = 148;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_tb = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_tb = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_fork = nullptr;  // orders the second DP stream behind what the caller put on the first
+    int dp_toggle = 0;              // consecutive chunks alternate between the two DP streams so that the next
+                                    // chunk's blocks fill the SMs while the previous kernel's last wave drains
     Slot slots[kSlots];
     size_t scratch_per_slot = 0;
 
@@ -503,11 +506,12 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
     h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
 
-    CU_TRY(h, cudaStreamWaitEvent(h->s_comp, s.ev_h2d, 0));
+    cudaStream_t s_dp = (h->dp_toggle++ & 1) ? h->s_comp2 : h->s_comp;
+    CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_h2d, 0));
     ChunkDev d{s.d_blob.p, s.d_q.p, s.d_t.p, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
-    if ((rc = enqueue_compute(h, h->s_comp, h->s_tb, s.ev_mid, d, p, nullptr))) return rc;
+    if ((rc = enqueue_compute(h, s_dp, h->s_tb, s.ev_mid, d, p, nullptr))) return rc;
     CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
@@ -634,6 +638,8 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     {
         // the traceback stream outranks the DP stream: its small blocks are placed first whenever a DP block
         // retires, so the records of chunk k are not held back by the DP kernel of chunk k+1
@@ -663,6 +669,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    if (h->s_comp2) cudaStreamSynchronize(h->s_comp2);
     if (h->s_tb) cudaStreamSynchronize(h->s_tb);
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
@@ -684,6 +691,8 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->own_t.p) cudaFreeHost(h->own_t.p);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_tb) cudaStreamDestroy(h->s_tb);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
@@ -839,6 +848,7 @@ extern "C" int rsa_ext_get_stats(const rsa_ext_t* hc, rsa_ext_stats_t* out) {
     if (h->r_events_valid) {
         cudaSetDevice(h->cfg.device);
         cudaStreamSynchronize(h->s_comp);
+        cudaStreamSynchronize(h->s_comp2);
         cudaStreamSynchronize(h->s_tb);
         double dp = 0, tb = 0;
         for (size_t c = 0; c < h->res_chunks.size(); ++c) {
@@ -928,15 +938,19 @@ extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     h->stats.kernel_launches = 0;
     const int nslots = h->res_chunks.size() > 1 ? 2 : 1;
+    // whatever the caller recorded on the handle's stream (rsa_ext_stream) precedes the work on both DP streams
+    CU_TRY(h, cudaEventRecord(h->ev_fork, h->s_comp));
+    CU_TRY(h, cudaStreamWaitEvent(h->s_comp2, h->ev_fork, 0));
     for (size_t c = 0; c < h->res_chunks.size(); ++c) {
         const ResidentChunk& rcx = h->res_chunks[c];
         Slot& s = h->slots[c % nslots];
+        cudaStream_t s_dp = (c & 1) ? h->s_comp2 : h->s_comp;
         // the slot's scratch/ends are free once the traceback that last used them has finished
-        CU_TRY(h, cudaStreamWaitEvent(h->s_comp, s.ev_comp, 0));
+        CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_comp, 0));
         ChunkDev d{rcx.d_blob, h->r_q.p + rcx.q_base, h->r_t.p + rcx.t_base, reinterpret_cast<DpEnd*>(s.d_ends.p),
                    reinterpret_cast<rsa_ext_result_t*>(h->r_res.p) + rcx.plan.lo, s.d_scratch.p, (uint64_t)s.d_scratch.cap,
                    s.d_arena.p, s.d_arena_used, (uint64_t)s.d_arena.cap};
-        int rc = enqueue_compute(h, h->s_comp, h->s_tb, s.ev_mid, d, rcx.plan, &h->r_events[4 * c]);
+        int rc = enqueue_compute(h, s_dp, h->s_tb, s.ev_mid, d, rcx.plan, &h->r_events[4 * c]);
         if (rc) return rc;
         CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
     }
@@ -951,6 +965,7 @@ extern "C" int rsa_ext_fetch_resident(rsa_ext_t* h, rsa_ext_result_t* results) {
     if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     CU_TRY(h, cudaStreamSynchronize(h->s_comp));
+    CU_TRY(h, cudaStreamSynchronize(h->s_comp2));
     CU_TRY(h, cudaStreamSynchronize(h->s_tb));
     CU_TRY(h, cudaMemcpy(results, h->r_res.p, sizeof(rsa_ext_result_t) * (size_t)h->r_n, cudaMemcpyDeviceToHost));
     return RSA_EXT_OK;
