@@ -53,6 +53,8 @@ typedef struct {
 } rsa_ext_config_t;
 
 #define RSA_EXT_FLAG_EXACT_ONLY 1 /* route every pair through the exact int32 kernel (testing) */
+#define RSA_EXT_FLAG_SERIALIZE 2  /* one stream, no kernel overlap: per-kernel CUDA-event times (dp_ms, tb_ms) are then
+                                     clean kernel durations (roofline measurements); slower than the default */
 
 /* One result per pair: the integer fields of `struct gasal_tmp_res` (src/gasal2_ssw.h:31-38; starts and
  * ends 0-based inclusive, starts may be -1) plus the traceback's run-length bytes exactly as

@@ -506,13 +506,15 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
     h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
 
-    cudaStream_t s_dp = (h->dp_toggle++ & 1) ? h->s_comp2 : h->s_comp;
+    const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
+    cudaStream_t s_dp = (!serial && (h->dp_toggle++ & 1)) ? h->s_comp2 : h->s_comp;
     CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_h2d, 0));
     ChunkDev d{s.d_blob.p, s.d_q.p, s.d_t.p, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
-    if ((rc = enqueue_compute(h, s_dp, h->s_tb, s.ev_mid, d, p, nullptr))) return rc;
-    CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
+    cudaStream_t s_trace = serial ? s_dp : h->s_tb;
+    if ((rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, p, nullptr))) return rc;
+    CU_TRY(h, cudaEventRecord(s.ev_comp, s_trace));
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
     CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -944,15 +946,17 @@ extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     for (size_t c = 0; c < h->res_chunks.size(); ++c) {
         const ResidentChunk& rcx = h->res_chunks[c];
         Slot& s = h->slots[c % nslots];
-        cudaStream_t s_dp = (c & 1) ? h->s_comp2 : h->s_comp;
+        const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
+        cudaStream_t s_dp = (!serial && (c & 1)) ? h->s_comp2 : h->s_comp;
+        cudaStream_t s_trace = serial ? s_dp : h->s_tb;
         // the slot's scratch/ends are free once the traceback that last used them has finished
         CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_comp, 0));
         ChunkDev d{rcx.d_blob, h->r_q.p + rcx.q_base, h->r_t.p + rcx.t_base, reinterpret_cast<DpEnd*>(s.d_ends.p),
                    reinterpret_cast<rsa_ext_result_t*>(h->r_res.p) + rcx.plan.lo, s.d_scratch.p, (uint64_t)s.d_scratch.cap,
                    s.d_arena.p, s.d_arena_used, (uint64_t)s.d_arena.cap};
-        int rc = enqueue_compute(h, s_dp, h->s_tb, s.ev_mid, d, rcx.plan, &h->r_events[4 * c]);
+        int rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, rcx.plan, &h->r_events[4 * c]);
         if (rc) return rc;
-        CU_TRY(h, cudaEventRecord(s.ev_comp, h->s_tb));
+        CU_TRY(h, cudaEventRecord(s.ev_comp, s_trace));
     }
     // anything the caller records on the compute stream after this call comes after every traceback too
     for (int k = 0; k < nslots; ++k) CU_TRY(h, cudaStreamWaitEvent(h->s_comp, h->slots[k].ev_comp, 0));
