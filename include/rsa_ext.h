@@ -107,6 +107,32 @@ int rsa_ext_rle_overflow(rsa_ext_t *h, int64_t i, uint8_t *out, int32_t cap);
  * neighbours, "<count><M|X|D|I>".  Returns text length (no NUL counted) or -1 if cap is too small. */
 int rsa_ext_rle_to_text(const uint8_t *rle, int32_t n_ops, char *out, int32_t cap);
 
+/* ---- SURVEY 8(f) "next" rows 1 and 3: the host post-processing of every GPU record, on the device -----------
+ *
+ * What src/pc.cpp:735-744 does per pair on the host -- gasal_fail (src/pc.cpp:466-478), then Aligner::align_gpu
+ * (src/aligner.cpp:13-112: CIGAR text -> ops, soft clips, M -> '=', NM = X+I+D via ext/ssw/ssw_cpp.cpp:54-90,
+ * 212-247,396-429, and the greedy end-bonus extension to both read ends) -- computed by a kernel behind the
+ * traceback.  The record mirrors `AlignmentInfo` (src/aligner.hpp:20-30); CIGAR ops are BAM-style
+ * (len << 4 | op, op codes of src/cigar.hpp:11-21: 1 I, 2 D, 4 S, 7 =, 8 X).
+ * status: 0 accepted (fields as align_gpu returns them); 1 gasal_fail -> the caller runs Aligner::align on the CPU
+ * like the reference; 2 window > max_target_len -> the sentinel of src/aligner.cpp:18-24; 3 CIGAR longer than
+ * RSA_EXT_CIGAR_INLINE ops -> use the rsa_ext_result_t record and the host path for this pair. */
+#define RSA_EXT_CIGAR_INLINE 25
+typedef struct {
+    int32_t sw_score;
+    int32_t edit_distance;
+    int32_t ref_start, ref_end;     /* end exclusive */
+    int32_t query_start, query_end; /* end exclusive */
+    int16_t n_cigar;
+    int16_t status;
+    uint32_t cigar[RSA_EXT_CIGAR_INLINE];
+} rsa_ext_alninfo_t; /* 128 bytes */
+
+/* Ask the following rsa_ext_submit/_ptrs calls to also fill out[0..n) (valid after rsa_ext_wait); out == NULL
+ * switches it off.  The pointer must cover the largest batch submitted while it is set.
+ * end_bonus is strobealign's -L (src/cmdline.hpp:50, default 10). */
+int rsa_ext_request_alninfo(rsa_ext_t *h, rsa_ext_alninfo_t *out, int32_t end_bonus);
+
 /* ---- device-resident legs (bench.py `value`, roofline): inputs already in HBM ---------------- */
 
 /* Upload + plan a batch once; afterwards rsa_ext_run_resident() re-runs only the GPU kernels on the

@@ -29,6 +29,7 @@
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_tb.cuh"
+#include "kernels_finish.cuh"
 
 using namespace rsa;
 
@@ -75,7 +76,7 @@ struct ChunkPlan {
 struct Slot {
     PinBuf h_blob;
     unsigned long long* h_arena_used = nullptr;  // pinned; [0] arena bytes used, [1] pairs the redo pass could not place
-    DevBuf d_blob, d_q, d_t, d_ends, d_res, d_scratch, d_arena;
+    DevBuf d_blob, d_q, d_t, d_ends, d_res, d_scratch, d_arena, d_aln;
     unsigned long long* d_arena_used = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_mid = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     ChunkPlan plan;
@@ -111,6 +112,9 @@ struct rsa_ext {
     const int64_t* qoff = nullptr;
     const int64_t* toff = nullptr;
     rsa_ext_result_t* results = nullptr;
+    rsa_ext_alninfo_t* alninfo = nullptr;  // optional second output of the pending batch
+    rsa_ext_alninfo_t* alninfo_next = nullptr;
+    int end_bonus = 10;
     int64_t next_pair = 0;
     int head = 0, tail = 0, inflight = 0;
     int chunks_enqueued = 0;
@@ -514,10 +518,22 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
                s.d_arena_used, (uint64_t)s.d_arena.cap};
     cudaStream_t s_trace = serial ? s_dp : h->s_tb;
     if ((rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, p, nullptr))) return rc;
+    if (h->alninfo) {
+        if ((rc = ensure_dev(h, s.d_aln, sizeof(rsa_ext_alninfo_t) * p.n))) return rc;
+        finish_kernel<<<(unsigned)((p.n + kFinishThreads - 1) / kFinishThreads), kFinishThreads, 0, s_trace>>>(
+            s.d_q.p, s.d_t.p, reinterpret_cast<const PairMeta*>(s.d_blob.p + p.off_meta),
+            reinterpret_cast<const rsa_ext_result_t*>(s.d_res.p), (int)p.n, h->sc, h->end_bonus,
+            reinterpret_cast<rsa_ext_alninfo_t*>(s.d_aln.p));
+        h->stats.kernel_launches++;
+    }
     CU_TRY(h, cudaEventRecord(s.ev_comp, s_trace));
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
     CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (h->alninfo) {
+        CU_TRY(h, cudaMemcpyAsync(h->alninfo + p.lo, s.d_aln.p, sizeof(rsa_ext_alninfo_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
+        h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_alninfo_t) * p.n;
+    }
     CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(h, cudaEventRecord(s.ev_d2h, h->s_d2h));
     h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_result_t) * p.n + 8;
@@ -574,6 +590,7 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
         if (ql < 0 || toff[i + 1] < toff[i]) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
     }
     h->n = n; h->qbuf = qbuf; h->qoff = qoff; h->tbuf = tbuf; h->toff = toff; h->results = results;
+    h->alninfo = h->alninfo_next;
     h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0; h->chunks_enqueued = 0;
     h->overflow.clear();
     h->retry.clear();
@@ -676,7 +693,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
     for (Slot& s : h->slots) {
-        for (DevBuf* b : {&s.d_blob, &s.d_q, &s.d_t, &s.d_ends, &s.d_res, &s.d_scratch, &s.d_arena})
+        for (DevBuf* b : {&s.d_blob, &s.d_q, &s.d_t, &s.d_ends, &s.d_res, &s.d_scratch, &s.d_arena, &s.d_aln})
             if (b->p) cudaFree(b->p);
         if (s.h_blob.p) cudaFreeHost(s.h_blob.p);
         if (s.h_arena_used) cudaFreeHost(s.h_arena_used);
@@ -732,6 +749,14 @@ extern "C" int rsa_ext_submit_ptrs(rsa_ext_t* h, int64_t n, const char* const* q
                        reinterpret_cast<const char*>(h->own_t.p), h->own_toff.data(), results);
 }
 
+extern "C" int rsa_ext_request_alninfo(rsa_ext_t* h, rsa_ext_alninfo_t* out, int32_t end_bonus) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    h->alninfo_next = out;
+    h->end_bonus = end_bonus;
+    return RSA_EXT_OK;
+}
+
 extern "C" int rsa_ext_poll(rsa_ext_t* h) {
     if (!h || !h->pending) return 0;
     if (h->next_pair < h->n) return 1;
@@ -754,6 +779,10 @@ static int run_retry(rsa_ext* h) {
     }
     std::vector<rsa_ext_result_t> tmp(m);
     rsa_ext_result_t* results = h->results;
+    rsa_ext_alninfo_t* const aln_out = h->alninfo;
+    rsa_ext_alninfo_t* const aln_req = h->alninfo_next;
+    std::vector<rsa_ext_alninfo_t> tmpa(aln_out ? m : 0);
+    h->alninfo_next = aln_out ? tmpa.data() : nullptr;
     auto overflow = std::move(h->overflow);
     const rsa_ext_stats_t stats = h->stats;
     const int32_t flags = h->cfg.flags;
@@ -761,9 +790,12 @@ static int run_retry(rsa_ext* h) {
     int rc = rsa_ext_submit_ptrs(h, m, qp.data(), ql.data(), tp.data(), tl.data(), tmp.data());
     if (rc == RSA_EXT_OK) rc = rsa_ext_wait(h);
     h->cfg.flags = flags;
+    h->alninfo_next = aln_req;
+    h->alninfo = aln_out;
     if (rc != RSA_EXT_OK) return rc;
     for (int64_t k = 0; k < m; ++k) {
         results[idx[k]] = tmp[k];
+        if (aln_out) aln_out[idx[k]] = tmpa[k];
         auto it = h->overflow.find(k);
         if (it != h->overflow.end()) overflow[idx[k]] = std::move(it->second);
     }

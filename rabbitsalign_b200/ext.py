@@ -33,6 +33,14 @@ RESULT_DTYPE = np.dtype([
 ])
 assert RESULT_DTYPE.itemsize == 64
 
+CIGAR_INLINE = 25
+ALNINFO_DTYPE = np.dtype([
+    ("sw_score", "<i4"), ("edit_distance", "<i4"), ("ref_start", "<i4"), ("ref_end", "<i4"),
+    ("query_start", "<i4"), ("query_end", "<i4"), ("n_cigar", "<i2"), ("status", "<i2"),
+    ("cigar", "<u4", (CIGAR_INLINE,)),
+])
+assert ALNINFO_DTYPE.itemsize == 128
+
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_query_len", C.c_int32), ("max_target_len", C.c_int32),
@@ -54,7 +62,7 @@ ABI_SYMBOLS = [
     "rsa_ext_create", "rsa_ext_destroy", "rsa_ext_last_error", "rsa_ext_submit", "rsa_ext_submit_ptrs",
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
-    "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count",
+    "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo",
 ]
 
 _lib = None
@@ -100,6 +108,8 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_get_stats.restype = C.c_int
     lib.rsa_ext_version.argtypes = []
     lib.rsa_ext_version.restype = C.c_int
+    lib.rsa_ext_request_alninfo.argtypes = [vp, vp, i32]
+    lib.rsa_ext_request_alninfo.restype = C.c_int
     lib.rsa_ext_plan_debug.argtypes = [i64, vp, vp, i64, C.c_int, vp]
     lib.rsa_ext_plan_debug.restype = C.c_int
     _lib = lib
@@ -186,6 +196,11 @@ class ExtensionEngine:
     def submit_raw(self, n, qbuf_ptr, qoff_ptr, tbuf_ptr, toff_ptr, res_ptr):
         self._check(self.lib.rsa_ext_submit(self.h, n, qbuf_ptr, qoff_ptr, tbuf_ptr, toff_ptr, res_ptr))
 
+    def request_alninfo(self, out: Optional[np.ndarray], end_bonus: int = 10):
+        """Also produce `AlignmentInfo` records (ALNINFO_DTYPE) on the device for the following submits."""
+        self._aln_keep = out
+        self._check(self.lib.rsa_ext_request_alninfo(self.h, out.ctypes.data if out is not None else None, end_bonus))
+
     def poll(self) -> int:
         return self.lib.rsa_ext_poll(self.h)
 
@@ -250,6 +265,11 @@ class ExtensionEngine:
         s = Stats()
         self._check(self.lib.rsa_ext_get_stats(self.h, C.byref(s)))
         return s.asdict()
+
+
+def alninfo_cigar_string(rec) -> str:
+    """CIGAR text of one ALNINFO record, as Cigar::to_string prints it (reference src/cigar.cpp:47-53)."""
+    return "".join(f"{int(op) >> 4}{'MIDNSHP=X'[int(op) & 0xF]}" for op in rec["cigar"][:int(rec["n_cigar"])])
 
 
 def plan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, exact_only: bool = False,
