@@ -302,6 +302,23 @@ def main():
     st_e2e = eng.stats()
     dt_max, _ = sharding.reduce_step(dt, 0.0, dist, device="cuda")
     e2e_value = total_cells / (dt_max / args.steps) / 1e9
+    # ---- same end-to-end leg with the device-side gasal_fail + align_gpu post-processing (SURVEY 8f rows 1+3) ----
+    from rabbitsalign_b200.ext import ALNINFO_DTYPE
+    taln = torch.empty(batch.n * ALNINFO_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    aln = taln.numpy().view(ALNINFO_DTYPE)
+    eng.request_alninfo(aln, end_bonus=10)
+    eng.submit(qbuf, qoff, tbuf, toff, results)
+    eng.wait()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        eng.submit(qbuf, qoff, tbuf, toff, results)
+        eng.wait()
+    dt_aln = (time.perf_counter() - t0) / max(1, args.steps // 2)
+    eng.request_alninfo(None)
+    aln_stats = {"gcups": batch.cells / dt_aln / 1e9, "ms_per_step": dt_aln * 1e3,
+                 "accepted": int((aln["status"] == 0).sum()), "gasal_fail": int((aln["status"] == 1).sum()),
+                 "long_cigar": int((aln["status"] == 3).sum())}
+
     # ---- the reference's own call shape: blocking 512-pair slices (STREAM_BATCH_SIZE, src/pc.cpp:644-672) -----
     n_slices = min(200, batch.n // 512)
     t0 = time.perf_counter()
@@ -374,7 +391,8 @@ def main():
                    "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"],
                                "redo_last_chunk": st["pairs_redo"]},
                    "resident_equals_e2e_records": same, "records_sane": ok,
-                   "slice512_one_worker": {"us_per_call": slice_dt * 1e6, "pairs_per_s": 512 / slice_dt if slice_dt > 0 else None}},
+                   "slice512_one_worker": {"us_per_call": slice_dt * 1e6, "pairs_per_s": 512 / slice_dt if slice_dt > 0 else None},
+                   "e2e_with_device_align_gpu": aln_stats},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"],
