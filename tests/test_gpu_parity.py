@@ -188,3 +188,54 @@ def test_concurrent_handles_from_threads(oracle_lib):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert all(o == [] for o in out), out
+
+
+def _random_related_pairs(rng, shapes):
+    qs, ts = [], []
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for ql, tl in shapes:
+        t = acgt[rng.integers(0, 4, size=tl)]
+        if tl >= ql and rng.random() < 0.8:
+            a = int(rng.integers(0, tl - ql + 1))
+            q = t[a:a + ql].copy()
+        else:
+            q = acgt[rng.integers(0, 4, size=ql)]
+            k = min(ql, tl)
+            q[:k] = t[:k]
+        m = rng.random(ql) < 0.04
+        q[m] = acgt[rng.integers(0, 4, size=int(m.sum()))]
+        if ql > 12 and rng.random() < 0.5:  # one indel
+            p = int(rng.integers(3, ql - 3))
+            q = np.concatenate([q[:p], acgt[rng.integers(0, 4, size=2)], q[p:ql - 2]]) if rng.random() < 0.5 \
+                else np.concatenate([q[:p], q[p + 2:], acgt[rng.integers(0, 4, size=2)]])
+        qs.append(q.astype(np.uint8).tobytes())
+        ts.append(t.astype(np.uint8).tobytes())
+    return W.from_lists(qs, ts)
+
+
+def test_every_query_length(engine, oracle_lib):
+    """Each |q| in 1..300 (every column count C and every wide/narrow lane split of the packed kernel, plus the
+    shapes it hands to the exact kernel), four windows each."""
+    rng = np.random.default_rng(180)
+    shapes = [(ql, int(rng.integers(max(1, ql - 20), ql + 120))) for ql in range(1, 301) for _ in range(4)]
+    b = _random_related_pairs(rng, shapes)
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(engine, res, oracle_arrays(oracle_lib, b), b)
+    assert not bad, "\n".join(bad)
+
+
+def test_window_length_extremes(engine, oracle_lib):
+    """|t| from 1 (fewer rows than lanes, partial 4-row blocks) up to the packed kernel's limit and beyond."""
+    rng = np.random.default_rng(181)
+    shapes = [(int(rng.integers(8, 160)), tl) for tl in list(range(1, 80)) * 2]
+    shapes += [(150, tl) for tl in (1023, 1024, 1025, 1999, 2000)] + [(64, 2000), (8, 2000), (256, 1500)]
+    b = _random_related_pairs(rng, shapes)
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(engine, res, oracle_arrays(oracle_lib, b), b)
+    assert not bad, "\n".join(bad)
+
+
+def test_single_pair_batches(engine, oracle_lib):
+    for q, t in [(b"ACGTACGTACGTACGT", b"TTACGTACGTACGTACGTTT"), (b"A", b"A"), (b"ACGTACGTAC" * 25, b"ACGTACGTAC" * 30)]:
+        got = engine.solve_ssw_on_gpu([q], [t])[0].astuple()
+        assert got == oracle_lib.align([q], [t])[0].astuple()
