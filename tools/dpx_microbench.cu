@@ -101,6 +101,87 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ---- experimental recipe variants (same outputs as rsa::fast_cell; evaluated here before the kernel adopts one) ----
+// V2: F and E kept shifted by (mismatch + gap_oe), so that F' = max(F^ - e, S) and E' = max(E^ - e, S) need neither
+//     tmp nor tg; H^ = max(S + oe, max3(F^, E^, Z)), H = H^ - (x + oe).  One IMAD less per cell.
+// V3: V2 + the "max(F,E,0) != F" flag through two IMADs instead of one IADD3 (ALU -> FMA pipe).
+template <int V>
+__device__ __forceinline__ void cell_variant(const rsa::FastConsts& k, uint32_t oeP, uint32_t zS, uint32_t negD, uint32_t kd2,
+                                             uint32_t s, uint32_t F, uint32_t e, uint32_t colconst, uint32_t& h, uint32_t& fn,
+                                             uint32_t& en, uint32_t& fl, uint32_t& key) {
+    const uint32_t U = __vimax3_s16x2(F, e, zS);
+    const uint32_t hh = __viaddmax_s16x2(s, oeP, U);   // H + (x + oe)
+    h = hh + negD;                                      // ring add: back to the stored form
+    fn = __viaddmax_s16x2(F, k.neg_e, s);
+    en = __viaddmax_s16x2(e, k.neg_e, s);
+    const uint32_t fo = fn - F + k.k_f;
+    const uint32_t eo = en - e + k.k_e;
+    const uint32_t nd = rsa::imad(s, k.minus1, rsa::imad(hh, k.one, kd2));   // hh - s + (k_d - oe)
+    uint32_t nf;
+    if (V == 3) nf = rsa::imad(F, k.minus1, rsa::imad(U, k.one, k.k_n));
+    else nf = U - F + k.k_n;
+    fl = rsa::bitsel(0x80008000u, fo, eo);
+    fl = rsa::bitsel(0xC000C000u, fl, nd);
+    fl = rsa::bitsel(0xE000E000u, fl, nf);
+    key = rsa::imad(h, k.k32, colconst);
+}
+
+template <int V>
+__global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+    uint32_t S[CH], E[CH], qsel[CH];
+    uint32_t px = in[8] + threadIdx.x, py = in[9];
+    const uint32_t oeP = in[20], zS = in[21], negD = in[22], kd2 = in[23];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = zS; qsel[c] = in[10 + c]; }
+    uint32_t F = zS, Hl = k.zero, rowkey = 0, sink = 0;
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = CH - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
+        uint32_t acc = 0, key_prev = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uint32_t h, fn, en, fl, key;
+            cell_variant<V>(k, oeP, zS, negD, kd2, S[c], F, E[c], rsa::pair16(31 - c), h, fn, en, fl, key);
+            acc = rsa::bitsel(0xF000F000u, fl, acc >> 4);
+            if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
+            key_prev = key;
+            S[c] = h;
+            E[c] = en;
+            F = fn;
+            if ((c & 3) == 3) { sink ^= acc; acc = 0; }
+        }
+        Hl = F;
+        px += py;
+    }
+    const unsigned long long t1 = clock64();
+    uint32_t s = sink + rowkey + F;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s += S[c] + E[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run_variant(int n_sms, int threads, uint32_t* d_out, uint32_t* d_in, unsigned long long* d_cyc) {
+    const int blocks = n_sms * 2;
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0));
+    CHECK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 3; ++rep) {
+        CHECK(cudaEventRecord(e0));
+        bench_cell_variant<V><<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
+        CHECK(cudaEventRecord(e1));
+        CHECK(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double gcups = 2.0 * (double)g_iters * CH * (double)blocks * threads / (ms * 1e-3) / 1e9;
+    printf("{\"test\": \"experimental recipe V%d\", \"threads\": %d, \"chip_gcups\": %.1f, \"ms\": %.3f}\n", V, threads, gcups, ms);
+}
+
 template <int OP>
 void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d_in, unsigned long long* d_cyc, int sm_khz) {
     const int blocks = n_sms * blocks_per_sm;
@@ -157,6 +238,7 @@ int main(int argc, char** argv) {
     in[0] = 0x00400040u; in[1] = 0u - 8u * 0x10001u; in[2] = 0u - 20u * 0x10001u; in[3] = 0xFFFFFFFFu;
     in[4] = 0x80008000u; in[5] = 0x40004000u; in[6] = 0x1FFF1FFFu; in[7] = 0x0FFF0FFFu; in[8] = 0x0A000000u; in[9] = 0x00000A00u;
     for (int k = 10; k < 64; ++k) in[k] = 0x9480u + (k & 3) + ((k & 3) << 4);
+    in[20] = 0x000C000Cu; in[21] = 0x00540054u; in[22] = 0u - 20u * 0x10001u; in[23] = 0x1FFF1FFFu - 0x000C000Cu;
     CHECK(cudaMalloc(&d_in, sizeof(uint32_t) * 64));
     CHECK(cudaMemcpy(d_in, in.data(), sizeof(uint32_t) * 64, cudaMemcpyHostToDevice));
     // ramp the clocks before measuring
@@ -180,6 +262,10 @@ int main(int argc, char** argv) {
             run<MIX_DPX_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         }
         run<CELL>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+        if (!quick) {
+            run_variant<2>(n_sms, threads, d_out, d_in, d_cyc);
+            run_variant<3>(n_sms, threads, d_out, d_in, d_cyc);
+        }
     }
     return 0;
 }
