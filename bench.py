@@ -239,7 +239,8 @@ def main():
 
     from rabbitsalign_b200 import sharding
     batch = make_batch(args.pairs, args.read_len, seed=sharding.rank_seed(43, rank))
-    eng = ExtensionEngine(device=local_rank)
+    scratch_gb = int(os.environ.get("RSA_EXT_SCRATCH_GB", "0"))  # tuning knob (experiments)
+    eng = ExtensionEngine(device=local_rank, scratch_bytes=scratch_gb << 30)
 
     # pinned host copies (the C ABI copies straight from/to pinned memory)
     def pinned(a):
@@ -282,7 +283,7 @@ def main():
     res_resident = eng.fetch_resident(batch.n)
 
     # ---- clean per-kernel durations for the roofline: same batch, kernels serialised on one stream --------------
-    eng_s = ExtensionEngine(device=local_rank, serialize=True)
+    eng_s = ExtensionEngine(device=local_rank, serialize=True, scratch_bytes=scratch_gb << 30)
     eng_s.stage_resident(qbuf, qoff, tbuf, toff)
     for _ in range(3):
         eng_s.run_resident()

@@ -38,7 +38,17 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int kSlots = 3;  // chunks in flight: one computing, one with its copies in flight, one being planned/retired
-constexpr int64_t kMaxChunkPairs = 1 << 17;
+constexpr int64_t kMaxChunkPairsDefault = 1 << 17;
+// tuning knob (experiments): RSA_EXT_MAX_CHUNK_PAIRS overrides the chunk size cap
+inline int64_t max_chunk_pairs() {
+    static const int64_t v = [] {
+        const char* e = getenv("RSA_EXT_MAX_CHUNK_PAIRS");
+        const long long x = e ? atoll(e) : 0;
+        return (int64_t)(x >= 256 ? x : kMaxChunkPairsDefault);
+    }();
+    return v;
+}
+#define kMaxChunkPairs (max_chunk_pairs())
 constexpr int64_t kMaxChunkSeqBytes = (int64_t)1 << 30;
 constexpr int64_t kDefaultScratch = (int64_t)12 << 30;  // all slots together (allocated lazily, per slot, as needed)
 constexpr int kMaxTargetLenCap = 8192;
@@ -188,7 +198,7 @@ struct PlanInput {
     int max_qlen, max_tlen;
     size_t scratch_cap;
     bool exact_only;
-    int64_t max_pairs = kMaxChunkPairs;  // cap for this chunk (the first chunks of a batch ramp up)
+    int64_t max_pairs = kMaxChunkPairsDefault;  // cap for this chunk (the first chunks of a batch ramp up)
 };
 
 // A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
