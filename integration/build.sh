@@ -58,4 +58,30 @@ $CXX -o "$OUT/rabbitsalign_gasalref" $OBJS "$OUT/obj/solve_gasalref.o" "$ROOT/or
 # 3) CPU-SSW path
 $CXX $FLAGS -c "$HERE/solve_cpussw.cpp" -o "$OUT/obj/solve_cpussw.o"
 $CXX -o "$OUT/rabbitsalign_cpussw" $OBJS "$OUT/obj/solve_cpussw.o" -lz -lpthread
+
+# ---- the reference's SHIPPED configuration: RabbitFX chunk reader + OPT_NUMA_CLOSE (build.sh:49
+#      -DUSE_RABBITFX=ON -DCLOSE_NUMA_OPT=ON).  RabbitFX/io/*.cpp are compiled directly (its own CMake needs
+#      FindOpenMP), with `-include cstdint` for GCC 13; src/pc.cpp and src/main.cpp are rebuilt with the two macros.
+FXFLAGS="$FLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I$REF_ROOT/RabbitFX/io"
+mkdir -p "$OUT/obj_fx"
+pids=()
+for s in FastxStream Formater verbos_Formater; do
+  ( [ "$OUT/obj_fx/$s.o" -nt "$REF_ROOT/RabbitFX/io/$s.cpp" ] || $CXX -O3 -std=c++17 -w -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$REF_ROOT/RabbitFX/io/$s.cpp" -o "$OUT/obj_fx/$s.o" ) &
+  pids+=($!)
+done
+for s in pc main; do
+  ( [ "$OUT/obj_fx/$s.o" -nt "$REF_ROOT/src/$s.cpp" ] && [ "$OUT/obj_fx/$s.o" -nt "$HERE/gasal2_ssw.h" ] || $CXX $FXFLAGS -c "$REF_ROOT/src/$s.cpp" -o "$OUT/obj_fx/$s.o" ) &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+FXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do if [ "$s" = pc ] || [ "$s" = main ]; then echo "$OUT/obj_fx/$s.o"; else echo "$OUT/obj/$s.o"; fi; done)
+# like the reference (RabbitFX/io/CMakeLists.txt:19-20): a static archive, members pulled on demand
+rm -f "$OUT/obj_fx/librabbitfx.a"
+ar rcs "$OUT/obj_fx/librabbitfx.a" "$OUT/obj_fx/FastxStream.o" "$OUT/obj_fx/Formater.o" "$OUT/obj_fx/verbos_Formater.o"
+FXIO="$OUT/obj_fx/librabbitfx.a"
+$CXX -o "$OUT/rabbitsalign_fx_b200" $FXOBJS $FXIO "$OUT/obj/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+$CXX -o "$OUT/rabbitsalign_fx_gasalref" $FXOBJS $FXIO "$OUT/obj/solve_gasalref.o" "$ROOT/oracle/_ref/libgasal_ref512.so" \
+     -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+$CXX -o "$OUT/rabbitsalign_fx_cpussw" $FXOBJS $FXIO "$OUT/obj/solve_cpussw.o" -lz -lpthread
 ls -la "$OUT"/rabbitsalign_*

@@ -26,6 +26,12 @@ CONFIGS = {
     # configs[1] shape, scaled down: paired-end with mate rescue (one worker: the non-FX PE path keeps one
     # insert-size estimator per worker, reference src/pc.cpp:1581,1748)
     "pe150": dict(reads=["--ref-len", "1000000", "--contigs", "4", "--reads", "10000", "--paired", "--seed", "11"], paired=True, threads=1),
+    # the reference's SHIPPED build configuration (RabbitFX reader + OPT_NUMA_CLOSE, build.sh:49): several 4-MiB
+    # chunks per file, 4 workers (FX-PE keeps one insert-size estimator per chunk, so it is thread-count independent)
+    "fx_pe150_t4": dict(reads=["--ref-len", "2000000", "--contigs", "4", "--reads", "50000", "--paired", "--seed", "13"],
+                        paired=True, threads=4, fx=True),
+    "fx_se150_t4": dict(reads=["--ref-len", "1000000", "--contigs", "2", "--reads", "60000", "--indel", "0.006", "--seed", "15"],
+                        paired=False, threads=4, fx=True),
 }
 
 
@@ -54,9 +60,11 @@ if __name__ == "__main__":
     gold = {}
     with tempfile.TemporaryDirectory() as wd:
         for name, cfg in CONFIGS.items():
-            g = run_config(name, cfg, os.path.join(B, "rabbitsalign_gasalref"), wd)
-            c = run_config(name, cfg, os.path.join(B, "rabbitsalign_cpussw"), wd)
+            pre = "rabbitsalign_fx_" if cfg.get("fx") else "rabbitsalign_"
+            g = run_config(name, cfg, os.path.join(B, pre + "gasalref"), wd)
+            c = run_config(name, cfg, os.path.join(B, pre + "cpussw"), wd)
             gold[name] = {"make_reads_args": cfg["reads"], "paired": cfg["paired"], "threads": cfg["threads"],
+                          "fx": bool(cfg.get("fx")),
                           "inputs": g["inputs"], "records": g["records"], "sam_md5_gasal_semantics": g["sam_md5"],
                           "sam_md5_cpu_ssw_path": c["sam_md5"]}
             print(name, gold[name]["sam_md5_gasal_semantics"], gold[name]["sam_md5_cpu_ssw_path"])

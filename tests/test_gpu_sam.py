@@ -15,14 +15,14 @@ from make_sam_golden import B, CONFIGS, ROOT, md5_file  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_golden.json")))
-BIN = os.path.join(B, "rabbitsalign_b200")
 
 
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_sam_is_byte_identical(name, tmp_path):
-    if not os.path.exists(BIN):
-        pytest.skip("integration/_build/rabbitsalign_b200 not built (needs /root/reference at build time)")
     g = GOLD[name]
+    BIN = os.path.join(B, "rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200")
+    if not os.path.exists(BIN):
+        pytest.skip(f"{BIN} not built (needs /root/reference at build time)")
     d = str(tmp_path / name)
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_reads.py"), d] + g["make_reads_args"])
     files = sorted(g["inputs"])  # ref.fa, reads_1.fq[, reads_2.fq]
