@@ -73,7 +73,7 @@ struct ChunkPlan {
     int n_exact[3] = {0, 0, 0};     // tasks per exact class (C = 4, 8, 16), consecutive in `list`
     int max_tlen_exact[3] = {0, 0, 0};
     int n_fast_classes = 0;
-    struct FastClass { int C; int group_begin; int n_groups; int max_tlen; };
+    struct FastClass { int L; int C; int group_begin; int n_groups; int max_tlen; };
     std::vector<FastClass> fast;
     int64_t n_fast_pairs = 0;
     int64_t n_failed = 0;
@@ -199,22 +199,26 @@ struct PlanInput {
     size_t scratch_cap;
     bool exact_only;
     int64_t max_pairs = kMaxChunkPairsDefault;  // cap for this chunk (the first chunks of a batch ramp up)
+    int match = 2;
 };
 
 // A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
-inline bool fast_shape_ok(int qlen, int tlen) {
-    return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen;
+inline bool fast_shape_ok(int qlen, int tlen, int match = 2) {
+    return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen &&
+           match * qlen <= 1023;  // the maximum-tracking key holds (score << 5 | column) in a positive s16
 }
 
 // per-query-length geometry, computed once
 struct LenTables {
     uint32_t fast_row_bytes[kFastMaxQlen + 1];  // direction bytes per target row of a packed group
     uint16_t fast_C[kFastMaxQlen + 1];
+    uint8_t fast_L[kFastMaxQlen + 1];
     uint32_t exact_row_bytes_[513];
     LenTables() {
         for (int q = 0; q <= kFastMaxQlen; ++q) {
             const FastGeom g = fast_geom(q < 1 ? 1 : q);
-            fast_row_bytes[q] = (uint32_t)(kFastLanes * g.W * 4);
+            fast_row_bytes[q] = (uint32_t)(g.L * g.W * 4);
+            fast_L[q] = (uint8_t)g.L;
             fast_C[q] = (uint16_t)g.C;
         }
         for (int q = 0; q <= 512; ++q) exact_row_bytes_[q] = (uint32_t)exact_row_bytes(q);
@@ -241,7 +245,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         uint64_t need = 0;
         if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
             need = (uint64_t)tl * LT.exact_row_bytes_[ql] + 16;
-            if (fast_shape_ok((int)ql, (int)tl))  // a lone pair owns a whole group
+            if (fast_shape_ok((int)ql, (int)tl, in.match))  // a lone pair owns a whole group
                 need = std::max<uint64_t>(need, (uint64_t)((tl + 3) & ~3) * LT.fast_row_bytes[ql]);
         }
         if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
@@ -302,7 +306,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         if (ql == 0 || tl == 0) { info[i] = 3u << 16; plan.n_failed++; continue; }
         if (tl > in.max_tlen) { info[i] = 1u << 16; plan.n_failed++; continue; }
         arena += (uint64_t)(ql + tl + 1);
-        if (!in.exact_only && fast_shape_ok((int)ql, (int)tl)) {
+        if (!in.exact_only && fast_shape_ok((int)ql, (int)tl, in.match)) {
             cand_idx[m] = (uint32_t)i;
             cand_key[m] = ((uint32_t)ql << 16) | (uint32_t)tl;
             qmin = std::min(qmin, (uint32_t)ql);
@@ -353,19 +357,21 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         }
         const FastGroup empty{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
         size_t k = 0;
-        int cur_C = -1;
+        int cur_C = -1, cur_L = -1;
+        constexpr int kGroupPad = 4;  // classes start on a warp boundary for either group width (4 or 2 groups/warp)
         while (k < m) {
             const uint32_t a = sidx[k], ka = skey[k];
             const uint32_t ql = ka >> 16;
             uint32_t b = a, kb = ka;
             if (k + 1 < m && (skey[k + 1] >> 16) == ql) { b = sidx[k + 1]; kb = skey[k + 1]; k += 2; }
             else k += 1;
-            const int C = LT.fast_C[ql];
-            if (C != cur_C) {
-                while (n_groups % kFastGroupsPerWarp) groups[n_groups++] = empty;
+            const int C = LT.fast_C[ql], L = LT.fast_L[ql];
+            if (C != cur_C || L != cur_L) {
+                while (n_groups % kGroupPad) groups[n_groups++] = empty;
                 if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
-                plan.fast.push_back({C, n_groups, 0, 0});
+                plan.fast.push_back({L, C, n_groups, 0, 0});
                 cur_C = C;
+                cur_L = L;
             }
             const uint32_t rows = std::max(ka & 0xFFFFu, kb & 0xFFFFu);
             FastGroup fg;
@@ -380,7 +386,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
             plan.fast.back().max_tlen = std::max<int>(plan.fast.back().max_tlen, (int)rows);
             plan.n_fast_pairs += (b != a) ? 2 : 1;
         }
-        while (n_groups % kFastGroupsPerWarp) groups[n_groups++] = empty;
+        while (n_groups % kGroupPad) groups[n_groups++] = empty;
         plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
     }
     plan.n_fast_classes = (int)plan.fast.size();
@@ -447,10 +453,10 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     TbArgs tba{d.q, d.t, meta, info, diroff, d.scratch, d.res, h->sc, d.arena, d.arena_used, d.arena_cap};
     // packed kernel, one launch per column class (traces its own pairs back)
     for (const auto& fc : p.fast) {
-        int rc = launch_fast_class(st, fc.C, d.q, d.t, meta,
+        int rc = launch_fast_class(st, fc.L, fc.C, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
                                    fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen, tba);
-        if (rc != 0) { h->err = "no packed-kernel instance for C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
+        if (rc != 0) { h->err = "no packed-kernel instance for L=" + std::to_string(fc.L) + " C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
     // exact kernel: statically routed pairs
@@ -499,6 +505,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     PlanInput in{h->n, h->qoff, h->toff, h->qbuf, h->tbuf, h->cfg.max_query_len, h->cfg.max_target_len,
                  h->scratch_per_slot, (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
     // ramp: 16k, 32k, 64k, then full-size chunks, so the first kernels start while the host still plans
+    in.match = h->sc.match;
     in.max_pairs = h->chunks_enqueued < 3 ? ((int64_t)16384 << h->chunks_enqueued) : kMaxChunkPairs;
     h->chunks_enqueued++;
     const auto t_plan0 = std::chrono::steady_clock::now();
@@ -926,6 +933,7 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
     h->stats = rsa_ext_stats_t{};
     PlanInput in{n, qoff, toff, qbuf, tbuf, h->cfg.max_query_len, h->cfg.max_target_len, h->scratch_per_slot,
                  (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
+    in.match = h->sc.match;
     std::vector<std::vector<uint8_t>> blobs;
     int64_t lo = 0;
     size_t blob_total = 0, max_pairs = 0, max_scratch = 0, max_arena = 0;

@@ -23,6 +23,9 @@ struct FastConsts {
 
 __host__ __device__ inline uint32_t pair16(int v) { return ((uint32_t)(v & 0xFFFF) << 16) | (uint32_t)(v & 0xFFFF); }
 
+// per-column constant of the maximum-tracking key: (31 - column) - bias*32 in both halves, as a ring constant
+__host__ __device__ constexpr uint32_t key_colconst(int c) { return (uint32_t)(31 - c - kBias * 32) * 0x00010001u; }
+
 __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
     FastConsts k;
     k.bias = kBias;
@@ -66,7 +69,8 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 //   F, e   = F(r,c), E(r,c) entering the cell
 // out: h = H(r,c); fn, en = F(r,c+1), E(r+1,c); fl = direction facts in bits 15..12 of each half
 //      (15 F opened, 14 E opened, 13 H != diagonal, 12 max(F,E,0) != F; bits 11..0 are garbage);
-//      key = (h << 5) | colconst for the first-maximum tracking.
+//      key = ((h - bias) << 5) | (31 - column) for the first-maximum tracking; `colconst` carries both the column
+//      term and the -bias*32 correction (ring constant), so the key of an all-zero cell is just its column term.
 // ALU pipe: VIMNMX3, VIMNMX, 2x VIADDMNMX, 3x IADD3, 4x LOP3(-class).  FMA pipe: the adds below written as IMADs.
 __device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
                                           uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
@@ -83,7 +87,7 @@ __device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint3
     fl = bitsel(0x80008000u, fo, eo);
     fl = bitsel(0xC000C000u, fl, nd);
     fl = bitsel(0xE000E000u, fl, nf);
-    key = imad(h, k.k32, colconst);                               // (h << 5) | (31 - column), FMA pipe
+    key = imad(h, k.k32, colconst);                               // ((h-bias) << 5) | (31 - column), FMA pipe
 }
 
 }  // namespace rsa

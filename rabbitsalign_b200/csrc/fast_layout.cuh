@@ -1,13 +1,13 @@
 // fast_layout.cuh -- geometry of the packed kernel's column ownership and direction-bit scratch.
 //
-// A "group" is 8 lanes working on TWO pairs of equal query length (pair A in the low 16-bit halves of every
+// A "group" is L lanes (8 for |q| <= 256, 16 for 257..512) working on TWO pairs of equal query length (pair A in the low 16-bit halves of every
 // packed register, pair B in the high halves).  The query's columns are dealt to the 8 lanes in order:
-// with C = ceil(qlen/8), the first `rem` lanes own C columns and the remaining lanes own C-1, so that
+// with C = ceil(qlen/L), the first `rem` lanes own C columns and the remaining lanes own C-1, so that
 // every owned column is a real query base (no padding columns exist).
 //
 // Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
-//     uint32 index = (((r>>2)*W + w)*8 + l)*4 + (r&3),   W = ceil(C/4)
-// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); for a fixed (row block, w) the 8 lanes'
+//     uint32 index = (((r>>2)*W + w)*L + l)*4 + (r&3),   W = ceil(C/4)
+// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); for a fixed (row block, w) the L lanes'
 // chunks are contiguous (one 128-byte line), so the DP kernel stores full lines with one STG.128 per lane and
 // the traceback, which moves diagonally, finds ~2-3 consecutive path cells in the chunk it just fetched.
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
@@ -20,9 +20,11 @@
 
 namespace rsa {
 
-constexpr int kFastLanes = 8;
+// lanes per group as a function of the query length (one rule for planner, kernels and traceback)
+__host__ __device__ inline int fast_lanes_for(int qlen) { return qlen <= 256 ? 8 : 16; }
 
 struct FastGeom {
+    int L;    // lanes per group
     int C;    // columns of the widest lanes
     int rem;  // number of lanes owning C columns (1..8); the rest own C-1
     int W;    // 32-bit direction words per lane and row
@@ -30,15 +32,16 @@ struct FastGeom {
 
 __host__ __device__ inline FastGeom fast_geom(int qlen) {
     FastGeom g;
-    g.C = (qlen + kFastLanes - 1) / kFastLanes;
-    g.rem = qlen - kFastLanes * (g.C - 1);
+    g.L = fast_lanes_for(qlen);
+    g.C = (qlen + g.L - 1) / g.L;
+    g.rem = qlen - g.L * (g.C - 1);
     g.W = (g.C + 3) / 4;
     return g;
 }
 
 // bytes of direction scratch of one group (two pairs) with `rows` target rows
 __host__ __device__ inline uint64_t fast_dir_bytes(const FastGeom& g, int rows) {
-    return (uint64_t)((rows + 3) & ~3) * kFastLanes * g.W * 4u;
+    return (uint64_t)((rows + 3) & ~3) * g.L * g.W * 4u;
 }
 
 // first column owned by lane l
@@ -52,7 +55,7 @@ __device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const ui
     const int wide = g.rem * g.C;
     if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
     else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
-    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.W + (cc >> 2)) * kFastLanes + lane) << 2) + (i & 3)];
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.W + (cc >> 2)) * g.L + lane) << 2) + (i & 3)];
     const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
     return (h16 >> (4 * (cc & 3))) & 0xFu;
 }

@@ -36,10 +36,13 @@ namespace rsa {
 
 constexpr int kFastMinQlen = 8;
 constexpr int kFastMaxC = 32;
-constexpr int kFastMaxQlen = kFastLanes * kFastMaxC;  // 256
+constexpr int kFastMaxQlen = 16 * kFastMaxC;  // 512: 8 lanes x C<=32 up to 256 bases, 16 lanes x C<=32 beyond
 constexpr int kFastMaxTlen = 2047;
-constexpr int kFastGroupsPerWarp = 4;
-constexpr int kFastWarpsPerBlock = 4;
+// 8-lane groups: 4 groups per warp, 4 warps per block; 16-lane groups: 2 groups per warp, 2 warps per block
+// (their shared-memory ring is deeper and wider)
+__host__ __device__ constexpr int fast_groups_per_warp(int L) { return 32 / L; }
+__host__ __device__ constexpr int fast_warps_per_block(int L) { return L == 8 ? 4 : 2; }
+__host__ __device__ constexpr int fast_ring_slots(int L) { return L == 8 ? 16 : 32; }  // >= L - 1 + 4, power of two
 // Trace pairs back inside the DP kernel (lanes 0/1 of each group) instead of in tb_kernel.  Measured on B200:
 // 1.36 vs 1.50 TCUPS per step -- the 8 walking lanes keep the warp's registers for ~150 dependent HBM round trips
 // (the block's tiles are long out of L2), which costs the ALU-bound DP more latency hiding than the separate
@@ -68,7 +71,7 @@ struct RedoHeader {
 __host__ inline bool fast_scoring_ok(const Scoring& sc) {
     return sc.match > 0 && sc.mismatch > 0 && sc.gap_ext >= 0 && sc.gap_oe >= sc.gap_ext &&
            sc.mismatch + sc.gap_oe < kBias - 2 && sc.match + sc.mismatch < 128 &&
-           sc.match * kFastMaxQlen + kBias < 1024;  // (H_biased << 5) must stay a positive s16
+           sc.match * kFastMinQlen < 1024;  // per-pair bound match*|q| <= 1023 is applied by the planner
 }
 
 // nibble (ascii & 0xF) -> code: A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4, everything else 0xF
@@ -93,13 +96,13 @@ __host__ __device__ inline uint32_t profile_word(uint32_t code, const FastConsts
 
 __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
 
-// Column keys: the running maximum is tracked on key = (H_biased << 5) | (31 - column_in_lane), still one
-// 16-bit half per pair (H_biased < 1024).  The larger key wins, i.e. the larger H and, for equal H in one row,
+// Column keys: the running maximum is tracked on key = (H << 5) | (31 - column_in_lane), still one 16-bit half
+// per pair (H = unbiased score < 1024, i.e. match * |q| <= 1023: checked per pair by the planner).  The larger key wins, i.e. the larger H and, for equal H in one row,
 // the smaller column -- the reference's order inside a row (SURVEY.md 8a rule 3).  Building the key is one
 // IMAD (FMA pipe, otherwise idle); no per-column maximum registers are needed.
 constexpr uint32_t kColMask = 0x001F001Fu;
 
-template <int C, bool HASN>
+template <int L, int C, bool HASN>
 struct FastDp {
     // One group's sweep.  All 32 lanes of the warp call this together (shuffles inside).
     //
@@ -118,9 +121,10 @@ struct FastDp {
 #pragma unroll
         for (int c = 0; c < C; ++c) { S[c] = k.zero; E[c] = k.zero; }
         uint32_t Hlast = k.zero, Fout = k.zero, Hl_prev = k.zero;
-        uint32_t bestkey = k.zero << 5;
+        uint32_t bestkey = 0;  // key of "no positive cell yet"
         firstrow[0] = firstrow[1] = 0;
         constexpr int NW = (C + 3) / 4;
+        constexpr int RS = fast_ring_slots(L);
         const int rmax = rows > 0 ? rows - 1 : 0;
         uint2 pr;
         {
@@ -130,8 +134,8 @@ struct FastDp {
         }
         for (int s = 0; s < nsteps; ++s) {
             // ---- phase 0
-            uint32_t Hl = __shfl_up_sync(0xFFFFFFFFu, Hlast, 1, kFastLanes);
-            uint32_t Fl = __shfl_up_sync(0xFFFFFFFFu, Fout, 1, kFastLanes);
+            uint32_t Hl = __shfl_up_sync(0xFFFFFFFFu, Hlast, 1, L);
+            uint32_t Fl = __shfl_up_sync(0xFFFFFFFFu, Fout, 1, L);
             const int r = s - gl;
             const uint32_t tcn = tcodes[min(max(r + 1, 0), rmax)];
             uint2 prn;
@@ -154,7 +158,7 @@ struct FastDp {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
                     if (c < C - 1 || wide) {
                         uint32_t h, fn, en, fl, key;
-                        fast_cell(k, S[c], F, E[c], pair16(31 - c), h, fn, en, fl, key);
+                        fast_cell(k, S[c], F, E[c], key_colconst(c), h, fn, en, fl, key);
                         acc = bitsel(0xF000F000u, fl, acc >> 4);
                         if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
                         else if (c == C - 1) rowkey = __vmaxs2(rowkey, key);
@@ -175,7 +179,7 @@ struct FastDp {
                 // direction words of this lane and row: parked in this lane's shared-memory ring until every
                 // lane of the group has reached the same row (see below)
 #pragma unroll
-                for (int wv = 0; wv < NW; ++wv) ring[(((s & 15) * NW + wv) << 5) + lane] = words[wv];
+                for (int wv = 0; wv < NW; ++wv) ring[(((s & (RS - 1)) * NW + wv) << 5) + lane] = words[wv];
                 // Running maximum of this lane, per half, kept as the FIRST cell in the reference's visiting order
                 // (8-row block, column, row in block) among the cells seen so far with the largest H:
                 //   row H > best H                      -> this row's key wins;
@@ -194,21 +198,21 @@ struct FastDp {
             Hl_prev = (gl == 0) ? k.zero : Hl;
             pr = prn;
             // De-skewed, row-blocked store: lane gl computed row r at step r+gl and parked its words in ring slot
-            // (r+gl)&15.  When the group's LAST lane has finished the last row of a 4-row block (step = 4b+3+7),
-            // every lane stores ITS OWN words of rows 4b..4b+3 as one 16-byte chunk per word: 8 lanes x 16 B = one
-            // full 128-byte line per store instruction and group.
-            const int rl = s - (kFastLanes - 1);          // row the last lane finished in this step
+            // (r+gl)&(RS-1).  When the group's LAST lane has finished the last row of a 4-row block (step = 4b+3+L-1),
+            // every lane stores ITS OWN words of rows 4b..4b+3 as one 16-byte chunk per word: L lanes x 16 B = one
+            // (two) full 128-byte line(s) per store instruction and group.
+            const int rl = s - (L - 1);                   // row the last lane finished in this step
             if (rl >= 0 && (rl & 3) == 3 && rl - 3 < rows) {
                 const int rb = rl >> 2;
-                uint4* dblk = reinterpret_cast<uint4*>(dir) + (size_t)rb * (NW * kFastLanes) + gl;
+                uint4* dblk = reinterpret_cast<uint4*>(dir) + (size_t)rb * (NW * L) + gl;
 #pragma unroll
                 for (int wv = 0; wv < NW; ++wv) {
                     uint4 v;
-                    v.x = ring[((((rl - 3 + gl) & 15) * NW + wv) << 5) + lane];
-                    v.y = ring[((((rl - 2 + gl) & 15) * NW + wv) << 5) + lane];
-                    v.z = ring[((((rl - 1 + gl) & 15) * NW + wv) << 5) + lane];
-                    v.w = ring[((((rl + gl) & 15) * NW + wv) << 5) + lane];
-                    dblk[wv * kFastLanes] = v;
+                    v.x = ring[((((rl - 3 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
+                    v.y = ring[((((rl - 2 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
+                    v.z = ring[((((rl - 1 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
+                    v.w = ring[((((rl + gl) & (RS - 1)) * NW + wv) << 5) + lane];
+                    dblk[wv * L] = v;
                 }
             }
         }
@@ -216,8 +220,8 @@ struct FastDp {
     }
 };
 
-template <int C>
-__global__ void __launch_bounds__(32 * kFastWarpsPerBlock, (C <= 20 ? 4 : (C <= 27 ? 3 : 2)))
+template <int L, int C>
+__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
@@ -226,21 +230,22 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 words
     if (threadIdx.x < 8) lut[threadIdx.x] = profile_word(threadIdx.x, k);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gi = lane >> 3, gl = lane & 7;
-    const int g_index = (blockIdx.x * kFastWarpsPerBlock + warp) * kFastGroupsPerWarp + gi;
+    constexpr int GPW = fast_groups_per_warp(L), WPB = fast_warps_per_block(L);
+    const int gi = lane / L, gl = lane % L;
+    const int g_index = (blockIdx.x * WPB + warp) * GPW + gi;
     FastGroup grp;
     grp.a = 0xFFFFFFFFu; grp.b = 0xFFFFFFFFu; grp.dir_off = 0; grp.qlen = 0; grp.rows = 0;
     if (g_index < n_groups) grp = groups[g_index];
     const bool live = grp.a != 0xFFFFFFFFu;
-    uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * kFastGroupsPerWarp + gi) * rows_pad;
-    constexpr int kRingWords = 16 * ((C + 3) / 4) * 32;  // per warp: 16 row slots x words x lanes
-    uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + 32 + (size_t)kFastWarpsPerBlock * kFastGroupsPerWarp * rows_pad) + warp * kRingWords;
+    uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * GPW + gi) * rows_pad;
+    constexpr int kRingWords = fast_ring_slots(L) * ((C + 3) / 4) * 32;  // per warp: row slots x words x lanes
+    uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + 32 + (size_t)WPB * GPW * rows_pad) + warp * kRingWords;
 
     // ---- staging: target profiles into shared memory, query selectors into registers ----------------
     bool bad_a = false, bad_b = false;
     int rows = 0, tlen_a = 0, tlen_b = 0, qlen = 0;
     const uint8_t *qa = nullptr, *qb = nullptr;
-    FastGeom geo = fast_geom(8 * C);
+    FastGeom geo = fast_geom(L * C);
     if (live) {
         const PairMeta ma = meta[grp.a], mb = meta[grp.b];
         qlen = grp.qlen;
@@ -250,7 +255,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         qa = qbuf + ma.qoff; qb = qbuf + mb.qoff;
         const uint8_t* ta = tbuf + ma.toff;
         const uint8_t* tb = tbuf + mb.toff;
-        for (int r = gl; r < rows; r += kFastLanes) {
+        for (int r = gl; r < rows; r += L) {
             uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
             if (r < tlen_a) { ca = base_code(nibble_of(ta[r])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
             if (r < tlen_b) { cb = base_code(nibble_of(tb[r])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
@@ -278,21 +283,21 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         // carries the PRMT selector that expands to the per-half "query base is not N" mask
         qsel[c] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12) | ((msel ^ 0x4444u) << 16);
     }
-    const unsigned gmask = 0xFFu << (8 * gi);
+    const unsigned gmask = (L == 16 ? 0xFFFFu : 0xFFu) << (L * gi);
     bad_a = (__ballot_sync(0xFFFFFFFFu, bad_a) & gmask) != 0;
     bad_b = (__ballot_sync(0xFFFFFFFFu, bad_b) & gmask) != 0;
     const bool warp_has_n = __any_sync(0xFFFFFFFFu, has_n);
-    int nsteps = ((rows + 3) & ~3) + kFastLanes - 1;  // rows rounded up: the last row block is flushed in-loop
+    int nsteps = ((rows + 3) & ~3) + L - 1;  // rows rounded up: the last row block is flushed in-loop
     if (!live) nsteps = 0;
 #pragma unroll
-    for (int off = 16; off >= 8; off >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xFFFFFFFFu, nsteps, off));
+    for (int off = 16; off >= L; off >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xFFFFFFFFu, nsteps, off));
     __syncthreads();  // lut + this warp's target codes
 
     uint32_t* dir = reinterpret_cast<uint32_t*>(scratch + grp.dir_off);
     uint32_t bestkey;
     int firstrow[2];
-    if (warp_has_n) FastDp<C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
-    else FastDp<C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
+    if (warp_has_n) FastDp<L, C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
+    else FastDp<L, C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
 
     // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
     // Every lane holds its first-in-reference-order maximum cell; lanes own increasing column ranges, so among
@@ -307,17 +312,17 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         const uint32_t pi = h ? grp.b : grp.a;
         const bool bad = h ? bad_b : bad_a;
         const int kh = half_s(bestkey, h);
-        const int mine = (kh >> 5) - k.bias;
+        const int mine = kh >> 5;
         int S = mine;
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(0xFFFFFFFFu, S, off));
+        for (int off = L / 2; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(0xFFFFFFFFu, S, off));
         const bool cand = live && (mine == S) && (S > 0);
         int key = cand ? (((firstrow[h] >> 3) << 8) | gl) : 0x7FFFFFFF;
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
+        for (int off = L / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
         const int wl = (S > 0) ? (key & 0xFF) : 0;  // winner lane of the group (S == 0: trackers stay at (0,0))
-        const int qend = __shfl_sync(0xFFFFFFFFu, col0 + (31 - (kh & 31)), wl, kFastLanes);
-        const int tend = __shfl_sync(0xFFFFFFFFu, firstrow[h], wl, kFastLanes);
+        const int qend = __shfl_sync(0xFFFFFFFFu, col0 + (31 - (kh & 31)), wl, L);
+        const int tend = __shfl_sync(0xFFFFFFFFu, firstrow[h], wl, L);
         if (!live || (h == 1 && grp.b == grp.a) || gl != h) continue;
         my_pair = (int)pi;
         my_end.score = S;
@@ -487,26 +492,37 @@ exact_redo_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ 
 // ---- host-side launchers ------------------------------------------------------------------------------
 namespace rsa {
 
-template <int C>
+template <int L, int C>
 inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
                             uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
     const int rows_pad = (max_rows + 15) & ~15;
-    const int groups_per_block = kFastWarpsPerBlock * kFastGroupsPerWarp;
+    constexpr int WPB = fast_warps_per_block(L);
+    const int groups_per_block = WPB * fast_groups_per_warp(L);
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)kFastWarpsPerBlock * 16 * ((C + 3) / 4) * 32 * 4;
+    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4;
     if (smem > 48 * 1024)  // long windows: opt in to more dynamic shared memory (per device, cheap to repeat)
-        cudaFuncSetAttribute(fast_dp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fast_dp_kernel<C><<<blocks, 32 * kFastWarpsPerBlock, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
+        cudaFuncSetAttribute(fast_dp_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fast_dp_kernel<L, C><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
                                                                      redo, redo_list, k, rows_pad, tba);
 }
 
 // returns 0, or -1 when C is outside the instantiated range
-inline int launch_fast_class(cudaStream_t st, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
+inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                              const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
                              uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
+    if (L == 16) {
+        switch (C) {
+#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
+            RSA_FAST_CASE16(17) RSA_FAST_CASE16(18) RSA_FAST_CASE16(19) RSA_FAST_CASE16(20) RSA_FAST_CASE16(21) RSA_FAST_CASE16(22)
+            RSA_FAST_CASE16(23) RSA_FAST_CASE16(24) RSA_FAST_CASE16(25) RSA_FAST_CASE16(26) RSA_FAST_CASE16(27) RSA_FAST_CASE16(28)
+            RSA_FAST_CASE16(29) RSA_FAST_CASE16(30) RSA_FAST_CASE16(31) RSA_FAST_CASE16(32)
+#undef RSA_FAST_CASE16
+            default: return -1;
+        }
+    }
     switch (C) {
-#define RSA_FAST_CASE(c) case c: launch_fast_one<c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
+#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
         RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6)
         RSA_FAST_CASE(7) RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12)
         RSA_FAST_CASE(13) RSA_FAST_CASE(14) RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18)

@@ -64,12 +64,13 @@ def test_planner_routes_by_shape():
     assert p["groups"] % 4 == 0 and p["groups"] >= 250
     p = ext.plan_debug(b.qoff, b.toff, exact_only=True)
     assert p["fast_pairs"] == 0 and p["exact_pairs"] == 500
-    # tiny and long queries go to the exact kernel; empty strings are failed records
+    # tiny queries go to the exact kernel, 257..512-base queries to the 16-lane packed kernel; empty strings
+    # are failed records
     q = [b"ACGT", b"A" * 300, b"", b"ACGTACGTAC"]
     t = [b"ACGTTT", b"A" * 400, b"ACGT", b""]
     bb = W.from_lists(q, t)
     p = ext.plan_debug(bb.qoff, bb.toff)
-    assert p["exact_pairs"] == 2 and p["failed"] == 2 and p["fast_pairs"] == 0
+    assert p["exact_pairs"] == 1 and p["failed"] == 2 and p["fast_pairs"] == 1
 
 
 def test_planner_chunks_by_scratch_budget():

@@ -214,10 +214,10 @@ def _random_related_pairs(rng, shapes):
 
 
 def test_every_query_length(engine, oracle_lib):
-    """Each |q| in 1..300 (every column count C and every wide/narrow lane split of the packed kernel, plus the
-    shapes it hands to the exact kernel), four windows each."""
+    """Each |q| in 1..500 (every column count C and every wide/narrow lane split of the 8- and 16-lane packed
+    kernels, plus the shapes handed to the exact kernel), four windows each."""
     rng = np.random.default_rng(180)
-    shapes = [(ql, int(rng.integers(max(1, ql - 20), ql + 120))) for ql in range(1, 301) for _ in range(4)]
+    shapes = [(ql, int(rng.integers(max(1, ql - 20), ql + 120))) for ql in range(1, 501) for _ in range(4)]
     b = _random_related_pairs(rng, shapes)
     res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
     bad = compare(engine, res, oracle_arrays(oracle_lib, b), b)
