@@ -5,7 +5,10 @@ NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall
 CSRC := rabbitsalign_b200/csrc
 LIB  := rabbitsalign_b200/librsa_ext.so
 
-all: $(LIB) oracle
+all: $(LIB) tools/dpx_microbench oracle
+
+tools/dpx_microbench: tools/dpx_microbench.cu $(CSRC)/fast_cell.cuh $(CSRC)/common.cuh
+	$(NVCC) -O3 -std=c++17 -lineinfo $(ARCH) -o $@ $<
 
 $(LIB): $(CSRC)/engine.cu $(wildcard $(CSRC)/*.cuh) include/rsa_ext.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/engine.cu

@@ -60,7 +60,9 @@ typedef struct {
  * ends 0-based inclusive, starts may be -1) plus the traceback's run-length bytes exactly as
  * GASAL2/src/kernels/get_tb.h:87-117 emits them: (count<<2)|op, count <= 63, op 0=M 1=X 2=D 3=I, in
  * END-TO-START order.  n_ops > RSA_EXT_RLE_INLINE: the full byte string is fetched with
- * rsa_ext_rle_overflow().  status: 0 ok, 1 window longer than max_target_len (not aligned). */
+ * rsa_ext_rle_overflow().  status: 0 ok; 1 window longer than max_target_len (not aligned; the caller never consumes
+ * those, src/aligner.cpp:18-24); 3 empty query or window (the reference reads an unwritten tile there).  All other
+ * records are bit-exact with the reference, including the ones its gasal_fail gate rejects. */
 typedef struct {
     int32_t score;
     int32_t query_start;
@@ -162,6 +164,12 @@ typedef struct {
 int rsa_ext_get_stats(const rsa_ext_t *h, rsa_ext_stats_t *out);
 
 int rsa_ext_version(void);
+
+/* Test hook, no CUDA call: plans the first chunk of a batch on the host and reports how it would be routed
+ * (out[0..7]: pairs, packed-kernel pairs, exact-kernel pairs, failed, groups, scratch bytes, column classes,
+ * in/out: timing repetitions -> mean ns per plan). */
+int rsa_ext_plan_debug(int64_t n, const int64_t *qoff, const int64_t *toff, int64_t scratch_cap, int exact_only,
+                       int64_t *out);
 
 /* Number of usable CUDA devices (0 without a driver/GPU): lets a host pipeline spread its workers over the
  * GPUs of one box (the reference is single-device, src/gasal2_ssw.cpp:34). */

@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "rsa_ext_create", "rsa_ext_destroy", "rsa_ext_last_error", "rsa_ext_submit", "rsa_ext_submit_ptrs",
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
-    "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo",
+    "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
 ]
 
 _lib = None
