@@ -9,7 +9,9 @@
 //   * blocking call; CIGAR text as the reference prints it (:184-243).
 // Differences: any batch size, storage is released at process exit, and with several GPUs visible the
 // workers are spread over them (thread_id % device count; RSA_EXT_DEVICES=n caps the count) -- the
-// reference uses device 0 only (:34).
+// reference uses device 0 only (:34).  CUDA initialisation and the primary context are started from a static
+// initializer on a helper thread, so they overlap the index load instead of stalling every worker's first batch
+// (measured 1-3 s inside a busy 16-worker process, tools/pipe_trace.sh); RSA_EXT_NO_WARMUP=1 turns that off.
 #include "gasal2_ssw.h"
 
 #include <cstdio>
@@ -17,6 +19,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "rsa_ext.h"
 
@@ -44,9 +47,32 @@ int device_count_cap() {
     return e ? atoi(e) : 0;
 }
 
-}  // namespace
+int usable_devices() {
+    int ndev = rsa_ext_device_count();
+    const int cap = device_count_cap();
+    return (cap > 0 && cap < ndev) ? cap : ndev;
+}
 
-extern "C" int rsa_ext_device_count(void);  // small helper exported by librsa_ext.so
+// Start the CUDA context(s) early; a failure here is not reported -- the first real call reports it.
+struct Warmup {
+    std::thread t;
+    Warmup() {
+        if (getenv("RSA_EXT_NO_WARMUP")) return;
+        t = std::thread([] {
+            const int ndev = usable_devices();
+            for (int d = 0; d < ndev; ++d) {
+                rsa_ext_config_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.device = d;
+                rsa_ext_t *h = nullptr;
+                if (rsa_ext_create(&cfg, &h) == RSA_EXT_OK) rsa_ext_destroy(h);
+            }
+        });
+    }
+    ~Warmup() { if (t.joinable()) t.join(); }
+} g_warmup;
+
+}  // namespace
 
 void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
                       std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
@@ -60,9 +86,7 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
 
     if (!w.h) {
         std::lock_guard<std::mutex> lock(g_create_mutex);
-        int ndev = rsa_ext_device_count();
-        const int cap = device_count_cap();
-        if (cap > 0 && cap < ndev) ndev = cap;
+        const int ndev = usable_devices();
         rsa_ext_config_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.device = ndev > 0 ? thread_id % ndev : 0;

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -36,6 +37,13 @@ using namespace rsa;
 namespace {
 
 thread_local std::string g_create_error;
+// Cold-path gate.  Context creation, stream/event creation, first-use module loading and cudaMalloc/cudaHostAlloc all
+// take process-wide driver locks; when the reference's 16 workers make their first call at the same moment the
+// waiters spin on those locks and the holder slows down ~10x (measured: 2.06 s instead of 0.2 s for the primary
+// context).  Handles therefore take this mutex (sleeping waiters) for rsa_ext_create and for their first submit.
+std::mutex g_cold_mutex;
+const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();  // library load (trace origin)
+double since_load_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count(); }
 
 constexpr int kSlots = 3;  // chunks in flight: one computing, one with its copies in flight, one being planned/retired
 constexpr int64_t kMaxChunkPairsDefault = 1 << 17;
@@ -86,12 +94,17 @@ struct ChunkPlan {
 struct Slot {
     PinBuf h_blob;
     unsigned long long* h_arena_used = nullptr;  // pinned; [0] arena bytes used, [1] pairs the redo pass could not place
-    DevBuf d_blob, d_q, d_t, d_ends, d_res, d_scratch, d_arena, d_aln;
+    DevBuf d_slab;                                            // one allocation; the views below are carved from it
+    DevBuf d_blob, d_q, d_t, d_ends, d_res, d_arena, d_aln;   // views into d_slab (ensure_slot)
+    DevBuf d_scratch;                                         // direction tiles, own allocation
     unsigned long long* d_arena_used = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_mid = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     ChunkPlan plan;
     bool busy = false;
 };
+
+// bytes a chunk needs from a slot (ensure_slot)
+struct SlotNeed { size_t blob, q, t, ends, res, arena, aln, scratch; };
 
 struct ResidentChunk {
     ChunkPlan plan;
@@ -116,6 +129,9 @@ struct rsa_ext {
 
     // pending batch
     bool pending = false;
+    bool resident_inflight = false;
+    SlotNeed r_need{};
+    bool warmed = false;  // first submit done (buffers allocated, kernels loaded): no cold-path gate any more
     int64_t n = 0;
     const char* qbuf = nullptr;
     const char* tbuf = nullptr;
@@ -169,6 +185,37 @@ int ensure_dev(rsa_ext* h, DevBuf& b, size_t need) {
     b.cap = 0;
     CU_TRY(h, cudaMalloc(&b.p, cap));
     b.cap = cap;
+    return RSA_EXT_OK;
+}
+
+// planned tiles + head-room for pairs the redo pass re-tiles (symbols outside ACGTN)
+inline size_t scratch_alloc_bytes(uint64_t planned) { return (size_t)align_up((size_t)planned, 256) + std::max<size_t>((size_t)16 << 20, (size_t)planned / 16); }
+
+// Size a slot's device buffers for one chunk.  Everything except the direction scratch is carved from ONE
+// allocation: cudaMalloc/cudaFree take a process-wide driver lock and stall every other worker's enqueue
+// (measured ~8 ms per round of eight cudaMallocs with 16 workers), so a slot allocates at most twice per growth.
+
+int ensure_slot(rsa_ext* h, Slot& s, const SlotNeed& n) {
+    DevBuf* view[7] = {&s.d_blob, &s.d_q, &s.d_t, &s.d_ends, &s.d_res, &s.d_arena, &s.d_aln};
+    const size_t need[7] = {n.blob, n.q, n.t, n.ends, n.res, n.arena, n.aln};
+    size_t off[7], total = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = total; total += align_up(need[i], 256); }
+    if (total > s.d_slab.cap) {
+        size_t cap = align_up(std::max({total, 2 * s.d_slab.cap, (size_t)4 << 20}), 1 << 20);
+        if (s.d_slab.p) CU_TRY(h, cudaFree(s.d_slab.p));
+        s.d_slab = DevBuf{};
+        CU_TRY(h, cudaMalloc(&s.d_slab.p, cap));
+        s.d_slab.cap = cap;
+    }
+    for (int i = 0; i < 7; ++i) { view[i]->p = s.d_slab.p + off[i]; view[i]->cap = need[i]; }
+    if (n.scratch > s.d_scratch.cap) {
+        size_t cap = align_up(std::max({n.scratch, 2 * s.d_scratch.cap, (size_t)16 << 20}), 1 << 20);
+        cap = std::min(cap, std::max(n.scratch, scratch_alloc_bytes(h->scratch_per_slot)));
+        if (s.d_scratch.p) CU_TRY(h, cudaFree(s.d_scratch.p));
+        s.d_scratch = DevBuf{};
+        CU_TRY(h, cudaMalloc(&s.d_scratch.p, cap));
+        s.d_scratch.cap = cap;
+    }
     return RSA_EXT_OK;
 }
 
@@ -407,8 +454,6 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     return RSA_EXT_OK;
 }
 
-// planned tiles + head-room for pairs the redo pass re-tiles (symbols outside ACGTN)
-inline size_t scratch_alloc_bytes(uint64_t planned) { return (size_t)align_up((size_t)planned, 256) + std::max<size_t>((size_t)16 << 20, (size_t)planned / 16); }
 
 // ---- launching -------------------------------------------------------------------------------------
 
@@ -513,19 +558,28 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
     if (rc) return rc;
     const ChunkPlan& p = s.plan;
-    if ((rc = ensure_dev(h, s.d_blob, p.blob_bytes))) return rc;
-    if ((rc = ensure_dev(h, s.d_q, (size_t)p.q_bytes + 16))) return rc;
-    if ((rc = ensure_dev(h, s.d_t, (size_t)p.t_bytes + 16))) return rc;
-    if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * p.n))) return rc;
-    if ((rc = ensure_dev(h, s.d_res, sizeof(rsa_ext_result_t) * p.n))) return rc;
-    if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(p.scratch_bytes)))) return rc;
-    if ((rc = ensure_dev(h, s.d_arena, (size_t)p.arena_bytes))) return rc;
+    const bool trace = getenv("RSA_EXT_TRACE") != nullptr;
+    auto t_last = t_plan0;
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rsa_ext %9.1f chunk %p n=%lld] %-22s %8.3f ms\n", since_load_ms(), (void*)h, (long long)p.n, what,
+                std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    lap("plan (+pinned staging)");
+    const SlotNeed need{p.blob_bytes, (size_t)p.q_bytes + 16, (size_t)p.t_bytes + 16, sizeof(DpEnd) * (size_t)p.n,
+                        sizeof(rsa_ext_result_t) * (size_t)p.n, (size_t)p.arena_bytes,
+                        h->alninfo ? sizeof(rsa_ext_alninfo_t) * (size_t)p.n : 0, scratch_alloc_bytes(p.scratch_bytes)};
+    if ((rc = ensure_slot(h, s, need))) return rc;
+    lap("device buffers");
 
     CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, s.h_blob.p, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.q_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_q.p, h->qbuf + h->qoff[p.lo], (size_t)p.q_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
     h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
+    lap("h2d enqueue");
 
     const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
     cudaStream_t s_dp = (!serial && (h->dp_toggle++ & 1)) ? h->s_comp2 : h->s_comp;
@@ -536,7 +590,6 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     cudaStream_t s_trace = serial ? s_dp : h->s_tb;
     if ((rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, p, nullptr))) return rc;
     if (h->alninfo) {
-        if ((rc = ensure_dev(h, s.d_aln, sizeof(rsa_ext_alninfo_t) * p.n))) return rc;
         finish_kernel<<<(unsigned)((p.n + kFinishThreads - 1) / kFinishThreads), kFinishThreads, 0, s_trace>>>(
             s.d_q.p, s.d_t.p, reinterpret_cast<const PairMeta*>(s.d_blob.p + p.off_meta),
             reinterpret_cast<const rsa_ext_result_t*>(s.d_res.p), (int)p.n, h->sc, h->end_bonus,
@@ -544,6 +597,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
         h->stats.kernel_launches++;
     }
     CU_TRY(h, cudaEventRecord(s.ev_comp, s_trace));
+    lap("kernel enqueue");
 
     CU_TRY(h, cudaStreamWaitEvent(h->s_d2h, s.ev_comp, 0));
     CU_TRY(h, cudaMemcpyAsync(h->results + p.lo, s.d_res.p, sizeof(rsa_ext_result_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -554,6 +608,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(h, cudaEventRecord(s.ev_d2h, h->s_d2h));
     h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_result_t) * p.n + 8;
+    lap("d2h enqueue");
 
     h->stats.pairs_fast += p.n_fast_pairs;
     h->stats.pairs_exact += p.n_exact[0] + p.n_exact[1] + p.n_exact[2];
@@ -606,6 +661,11 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
         }
         if (ql < 0 || toff[i + 1] < toff[i]) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
     }
+    if (h->resident_inflight) {  // an asynchronous resident run may still use the slots' scratch
+        CU_TRY(h, cudaStreamSynchronize(h->s_comp));
+        CU_TRY(h, cudaStreamSynchronize(h->s_tb));
+        h->resident_inflight = false;
+    }
     h->n = n; h->qbuf = qbuf; h->qoff = qoff; h->tbuf = tbuf; h->toff = toff; h->results = results;
     h->alninfo = h->alninfo_next;
     h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0; h->chunks_enqueued = 0;
@@ -613,11 +673,14 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
     h->retry.clear();
     h->stats = rsa_ext_stats_t{};
     h->pending = true;
+    std::unique_lock<std::mutex> cold(g_cold_mutex, std::defer_lock);
+    if (!h->warmed) cold.lock();
     while (h->next_pair < n && h->inflight < kSlots) {
         int rc = enqueue_chunk(h, h->slots[h->tail]);
         if (rc) { h->pending = false; return rc; }
         h->tail = (h->tail + 1) % kSlots;
     }
+    h->warmed = true;
     return RSA_EXT_OK;
 }
 
@@ -629,6 +692,7 @@ extern "C" int rsa_ext_version(void) { return 1; }
 
 // number of usable CUDA devices (0 when there is no driver/GPU)
 extern "C" int rsa_ext_device_count(void) {
+    std::lock_guard<std::mutex> cold(g_cold_mutex);
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
@@ -650,6 +714,7 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         return RSA_EXT_ERR_ARG;
     }
     if (cfg.scratch_bytes <= 0) cfg.scratch_bytes = kDefaultScratch;
+    std::lock_guard<std::mutex> cold(g_cold_mutex);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -671,7 +736,18 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         rsa_ext_destroy(h);
         return RSA_EXT_ERR_CUDA;
     };
+    const bool trace = getenv("RSA_EXT_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rsa_ext %9.1f create %p] %-28s %8.3f ms\n", since_load_ms(), (void*)h, what,
+                std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaFree(nullptr)) != cudaSuccess) return fail("context", e);
+    lap("context");
     if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
@@ -684,6 +760,7 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         if ((e = cudaStreamCreateWithPriority(&h->s_tb, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("stream", e);
     }
     if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    lap("6 streams");
     for (Slot& s : h->slots) {
         if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
@@ -692,11 +769,11 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         if ((e = cudaHostAlloc(&s.h_arena_used, 3 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
         if ((e = cudaMalloc(&s.d_arena_used, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     }
-    {
-        cudaDeviceProp prop;
-        if ((e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
-        h->n_sms = prop.multiProcessorCount;
-    }
+    lap("events + counters");
+    // (cudaGetDeviceProperties costs ~10 ms per call; one attribute is all the engine needs)
+    if ((e = cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg.device)) != cudaSuccess)
+        return fail("cudaDeviceGetAttribute", e);
+    lap("device attribute");
     *out = h;
     return RSA_EXT_OK;
 }
@@ -710,7 +787,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
     for (Slot& s : h->slots) {
-        for (DevBuf* b : {&s.d_blob, &s.d_q, &s.d_t, &s.d_ends, &s.d_res, &s.d_scratch, &s.d_arena, &s.d_aln})
+        for (DevBuf* b : {&s.d_slab, &s.d_scratch})
             if (b->p) cudaFree(b->p);
         if (s.h_blob.p) cudaFreeHost(s.h_blob.p);
         if (s.h_arena_used) cudaFreeHost(s.h_arena_used);
@@ -959,9 +1036,8 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
     if ((rc = ensure_dev(h, h->r_blobs, blob_total))) return rc;
     for (int k = 0; k < (h->res_chunks.size() > 1 ? 2 : 1); ++k) {  // resident chunks alternate between two slots' scratch
         Slot& s = h->slots[k];
-        if ((rc = ensure_dev(h, s.d_ends, sizeof(DpEnd) * max_pairs))) return rc;
-        if ((rc = ensure_dev(h, s.d_scratch, scratch_alloc_bytes(max_scratch)))) return rc;
-        if ((rc = ensure_dev(h, s.d_arena, max_arena))) return rc;
+        h->r_need = SlotNeed{0, 0, 0, sizeof(DpEnd) * (size_t)max_pairs, 0, (size_t)max_arena, 0, scratch_alloc_bytes(max_scratch)};
+        if ((rc = ensure_slot(h, s, h->r_need))) return rc;
     }
     CU_TRY(h, cudaMemcpy(h->r_q.p, qbuf + qoff[0], qbytes, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->r_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice));
@@ -987,9 +1063,13 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
 extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     if (!h) return RSA_EXT_ERR_ARG;
     if (h->res_chunks.empty()) { h->err = "nothing staged"; return RSA_EXT_ERR_STATE; }
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     h->stats.kernel_launches = 0;
     const int nslots = h->res_chunks.size() > 1 ? 2 : 1;
+    // a submit since rsa_ext_stage_resident may have re-carved the slots' buffers
+    for (int k = 0; k < nslots; ++k) { int rc = ensure_slot(h, h->slots[k], h->r_need); if (rc) return rc; }
+    h->resident_inflight = true;
     // whatever the caller recorded on the handle's stream (rsa_ext_stream) precedes the work on both DP streams
     CU_TRY(h, cudaEventRecord(h->ev_fork, h->s_comp));
     CU_TRY(h, cudaStreamWaitEvent(h->s_comp2, h->ev_fork, 0));

@@ -2,9 +2,12 @@
 (a) the B200 engine (integration/_build/rabbitsalign_b200) and (b) the reference's CPU SSW path
 (integration/_build/rabbitsalign_cpussw), same inputs, same thread count.  BASELINE.json metric (i).
 
-    python tools/e2e_reads_bench.py [--ref-len 20000000] [--reads 400000] [--threads N] [--paired]
+    python tools/e2e_reads_bench.py [--ref-len 20000000] [--reads 400000] [--threads N] [--paired] [--subsets a,b]
 
-Prints one JSON line.  The pipeline around the boundary (seeding, NAMs, SAM) is the reference's unmodified host
+Prints one JSON line.  With --subsets (read counts <= --reads, single-end) every binary also runs on the first a, b, ...
+reads of the same file and the line carries "mapping_s_per_mreads": the slope of the pipeline's own "Total time
+mapping" between the smallest and the largest run, i.e. the steady-state cost with process start-up (CUDA context,
+index load) taken out.  The pipeline around the boundary (seeding, NAMs, SAM) is the reference's unmodified host
 code, so this number is bounded by the host; it is reported, not optimised, in this round.
 """
 import argparse
@@ -36,6 +39,7 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--paired", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="unused (STREAM_BATCH_SIZE is a compile-time macro of the veneer)")
+    ap.add_argument("--subsets", default="", help="comma-separated read counts to also run (prefixes of the read file)")
     a = ap.parse_args()
     out = {"ref_len": a.ref_len, "reads": a.reads * (2 if a.paired else 1), "paired": a.paired, "threads": a.threads}
     with tempfile.TemporaryDirectory() as d:
@@ -44,21 +48,49 @@ def main():
                                "--contigs", str(a.contigs), "--reads", str(a.reads), "--seed", "77"] + (["--paired"] if a.paired else []))
         out["gen_s"] = round(time.time() - t0, 1)
         files = [os.path.join(d, "ref.fa"), os.path.join(d, "reads_1.fq")] + ([os.path.join(d, "reads_2.fq")] if a.paired else [])
+        def run(exe, fq_files, tag):
+            sam = os.path.join(d, tag + ".sam")
+            t0 = time.time()
+            r = subprocess.run([exe, "-t", str(a.threads), "-o", sam, files[0]] + fq_files, capture_output=True, text=True)
+            dt = time.time() - t0
+            if r.returncode != 0:
+                return {"error": r.stderr[-500:]}
+            mapping = [ln for ln in r.stderr.splitlines() if "Total time" in ln or "indexing" in ln.lower()]
+            res = {"wall_s": round(dt, 2), "sam_md5": md5_nopg(sam), "stderr_times": mapping[-8:]}
+            for ln in mapping:
+                if "Total time mapping" in ln:
+                    res["mapping_s"] = float(ln.split(":")[1].split()[0])
+            os.remove(sam)
+            return res
+
+        subsets = [int(x) for x in a.subsets.split(",") if x] if not a.paired else []
+        sub_files = {}
+        for k in subsets:
+            path = os.path.join(d, "sub_%d.fq" % k)
+            with open(files[1], "rb") as f, open(path, "wb") as g:
+                for _ in range(4 * k):
+                    g.write(f.readline())
+            sub_files[k] = path
         for name in ("rabbitsalign_cpussw", "rabbitsalign_b200"):
             exe = os.path.join(B, name)
             if not os.path.exists(exe):
                 out[name] = "not built"
                 continue
-            sam = os.path.join(d, name + ".sam")
-            t0 = time.time()
-            r = subprocess.run([exe, "-t", str(a.threads), "-o", sam] + files, capture_output=True, text=True)
-            dt = time.time() - t0
-            if r.returncode != 0:
-                out[name] = {"error": r.stderr[-500:]}
-                continue
-            mapping = [ln for ln in r.stderr.splitlines() if "Total time" in ln or "indexing" in ln.lower()]
-            out[name] = {"wall_s": round(dt, 2), "reads_per_s_wall": round(out["reads"] / dt), "sam_md5": md5_nopg(sam),
-                         "stderr_times": mapping[-8:]}
+            res = run(exe, files[1:], name)
+            if "error" not in res:
+                res["reads_per_s_wall"] = round(out["reads"] / res["wall_s"])
+            out[name] = res
+            pts = [(out["reads"], res.get("mapping_s"))]
+            for k in subsets:
+                rk = run(exe, [sub_files[k]], "%s_%d" % (name, k))
+                res["subset_%d" % k] = {kk: rk.get(kk) for kk in ("wall_s", "mapping_s", "error") if kk in rk}
+                pts.append((k, rk.get("mapping_s")))
+            pts = sorted(p for p in pts if p[1] is not None)
+            if len(pts) >= 2 and pts[-1][0] > pts[0][0]:
+                slope = (pts[-1][1] - pts[0][1]) / (pts[-1][0] - pts[0][0]) * 1e6
+                res["mapping_s_per_mreads"] = round(slope, 3)
+                res["startup_s"] = round(pts[0][1] - slope * pts[0][0] / 1e6, 2)
+                res["steady_reads_per_s"] = round(1e6 / slope) if slope > 0 else None
     print(json.dumps(out))
 
 
