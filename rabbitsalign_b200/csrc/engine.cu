@@ -20,8 +20,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -106,6 +108,26 @@ struct Slot {
 // bytes a chunk needs from a slot (ensure_slot)
 struct SlotNeed { size_t blob, q, t, ends, res, arena, aln, scratch; };
 
+// Plan-ahead ring (large batches): a helper thread plans chunk after chunk into these entries while the caller's
+// thread only enqueues and retires; an entry is reused once its chunk has retired.
+struct PlannedChunk {
+    ChunkPlan plan;
+    PinBuf blob;
+    int rc = 0;
+};
+constexpr int kPlanRing = kSlots + 2;
+constexpr int64_t kPlanAheadMinPairs = 32768;  // below this the caller's thread plans inline (no thread hop)
+struct PlanAhead {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    bool stop = false, active = false, cancel = false;
+    int64_t lo = 0;
+    long produced = 0, consumed = 0, released = 0;
+    double plan_ms = 0;
+    PlannedChunk ring[kPlanRing];
+};
+
 struct ResidentChunk {
     ChunkPlan plan;
     uint8_t* d_blob = nullptr;
@@ -144,6 +166,8 @@ struct rsa_ext {
     int64_t next_pair = 0;
     int head = 0, tail = 0, inflight = 0;
     int chunks_enqueued = 0;
+    PlanAhead* pa = nullptr;  // created by the first large submit
+    bool plan_ahead = false;  // the pending batch is planned by the helper thread
     std::unordered_map<int64_t, std::vector<uint8_t>> overflow;
     std::vector<int64_t> retry;  // pairs whose redo found no scratch (status 4): re-run exact-only at wait()
 
@@ -546,17 +570,87 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     return RSA_EXT_OK;
 }
 
-int enqueue_chunk(rsa_ext* h, Slot& s) {
+PlanInput pending_plan_input(const rsa_ext* h) {
     PlanInput in{h->n, h->qoff, h->toff, h->qbuf, h->tbuf, h->cfg.max_query_len, h->cfg.max_target_len,
                  h->scratch_per_slot, (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
-    // ramp: 16k, 32k, 64k, then full-size chunks, so the first kernels start while the host still plans
     in.match = h->sc.match;
-    in.max_pairs = h->chunks_enqueued < 3 ? ((int64_t)16384 << h->chunks_enqueued) : kMaxChunkPairs;
-    h->chunks_enqueued++;
+    return in;
+}
+
+// Chunk-size ramp of a batch: the first chunks are small so that the GPU starts while the host still plans.
+// Inline planning shares the caller's thread with enqueue/retire (16k, 32k, 64k); the plan-ahead thread runs
+// continuously, so its ramp only has to keep (plan + H2D) of chunk k+1 below the GPU time of chunk k.
+int64_t ramp_pairs(bool plan_ahead, long chunk_index) {
+    if (plan_ahead) {
+        static const int64_t r[] = {16384, 24576, 40960, 65536};
+        return chunk_index < 4 ? r[chunk_index] : kMaxChunkPairs;
+    }
+    return chunk_index < 3 ? ((int64_t)16384 << chunk_index) : kMaxChunkPairs;
+}
+
+void plan_ahead_main(rsa_ext* h) {
+    PlanAhead& pa = *h->pa;
+    cudaSetDevice(h->cfg.device);  // ensure_pin allocates pinned memory from this thread
+    std::unique_lock<std::mutex> lk(pa.m);
+    for (;;) {
+        pa.cv.wait(lk, [&] { return pa.stop || pa.active; });
+        if (pa.stop) return;
+        while (pa.active) {
+            if (pa.stop) return;
+            if (pa.cancel || pa.lo >= h->n) { pa.active = false; pa.cv.notify_all(); break; }
+            if (pa.produced - pa.released >= kPlanRing) { pa.cv.wait(lk); continue; }
+            PlannedChunk& e = pa.ring[pa.produced % kPlanRing];
+            PlanInput in = pending_plan_input(h);
+            in.max_pairs = ramp_pairs(true, pa.produced);
+            const int64_t lo = pa.lo;
+            lk.unlock();
+            const auto t0 = std::chrono::steady_clock::now();
+            const int rc = plan_chunk(h, in, lo, e.plan, nullptr, &e.blob);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            lk.lock();
+            e.rc = rc;
+            pa.plan_ms += ms;
+            pa.produced++;
+            if (rc) pa.active = false; else pa.lo = e.plan.hi;
+            pa.cv.notify_all();
+        }
+    }
+}
+
+// End the helper's work on the pending batch (normal completion or error) and wait until it is idle.
+void plan_ahead_finish(rsa_ext* h) {
+    if (!h->plan_ahead) return;
+    PlanAhead& pa = *h->pa;
+    std::unique_lock<std::mutex> lk(pa.m);
+    pa.cancel = true;
+    pa.cv.notify_all();
+    pa.cv.wait(lk, [&] { return !pa.active; });
+    h->stats.host_plan_ms += pa.plan_ms;
+    h->plan_ahead = false;
+}
+
+int enqueue_chunk(rsa_ext* h, Slot& s) {
     const auto t_plan0 = std::chrono::steady_clock::now();
-    int rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
-    h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
-    if (rc) return rc;
+    const uint8_t* h_blob = nullptr;
+    int rc;
+    if (h->plan_ahead) {
+        PlanAhead& pa = *h->pa;
+        std::unique_lock<std::mutex> lk(pa.m);
+        pa.cv.wait(lk, [&] { return pa.consumed < pa.produced; });
+        PlannedChunk& e = pa.ring[pa.consumed % kPlanRing];
+        pa.consumed++;
+        if (e.rc) return e.rc;
+        s.plan = e.plan;
+        h_blob = e.blob.p;  // stays untouched until this chunk retires (retire_chunk releases the entry)
+    } else {
+        PlanInput in = pending_plan_input(h);
+        in.max_pairs = ramp_pairs(false, h->chunks_enqueued);
+        rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
+        h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
+        if (rc) return rc;
+        h_blob = s.h_blob.p;
+    }
+    h->chunks_enqueued++;
     const ChunkPlan& p = s.plan;
     const bool trace = getenv("RSA_EXT_TRACE") != nullptr;
     auto t_last = t_plan0;
@@ -574,7 +668,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     if ((rc = ensure_slot(h, s, need))) return rc;
     lap("device buffers");
 
-    CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, s.h_blob.p, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, h_blob, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.q_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_q.p, h->qbuf + h->qoff[p.lo], (size_t)p.q_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
@@ -623,6 +717,8 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
 // After a chunk's D2H finished: pull the long-CIGAR arena (rare) and file the byte strings by pair index.
 int retire_chunk(rsa_ext* h, Slot& s) {
     CU_TRY(h, cudaEventSynchronize(s.ev_d2h));
+    if (getenv("RSA_EXT_TRACE"))
+        fprintf(stderr, "[rsa_ext %9.1f retire %p n=%lld]\n", since_load_ms(), (void*)h, (long long)s.plan.n);
     const unsigned long long used = *s.h_arena_used;
     if (used > 0) {
         std::vector<uint8_t> host(used);
@@ -643,6 +739,11 @@ int retire_chunk(rsa_ext* h, Slot& s) {
             if (h->results[i].status == 4) h->retry.push_back(i);
     s.busy = false;
     h->inflight--;
+    if (h->plan_ahead) {
+        std::lock_guard<std::mutex> lk(h->pa->m);
+        h->pa->released++;
+        h->pa->cv.notify_all();
+    }
     return RSA_EXT_OK;
 }
 
@@ -675,9 +776,27 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
     h->pending = true;
     std::unique_lock<std::mutex> cold(g_cold_mutex, std::defer_lock);
     if (!h->warmed) cold.lock();
+    if (n > kPlanAheadMinPairs) {
+        if (!h->pa) {
+            h->pa = new PlanAhead();
+            h->pa->th = std::thread(plan_ahead_main, h);
+        }
+        std::lock_guard<std::mutex> lk(h->pa->m);
+        h->pa->lo = 0; h->pa->produced = h->pa->consumed = h->pa->released = 0;
+        h->pa->plan_ms = 0;
+        h->pa->cancel = false;
+        h->pa->active = true;
+        h->plan_ahead = true;
+        h->pa->cv.notify_all();
+    }
     while (h->next_pair < n && h->inflight < kSlots) {
         int rc = enqueue_chunk(h, h->slots[h->tail]);
-        if (rc) { h->pending = false; return rc; }
+        if (rc) {
+            plan_ahead_finish(h);
+            if (h->inflight > 0) { cudaDeviceSynchronize(); for (Slot& sl : h->slots) sl.busy = false; h->inflight = 0; }
+            h->pending = false;
+            return rc;
+        }
         h->tail = (h->tail + 1) % kSlots;
     }
     h->warmed = true;
@@ -781,6 +900,18 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
 extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
+    if (h->pa) {
+        {
+            std::lock_guard<std::mutex> lk(h->pa->m);
+            h->pa->stop = true;
+            h->pa->cv.notify_all();
+        }
+        h->pa->th.join();
+        for (PlannedChunk& e : h->pa->ring)
+            if (e.blob.p) cudaFreeHost(e.blob.p);
+        delete h->pa;
+        h->pa = nullptr;
+    }
     if (h->s_comp) cudaStreamSynchronize(h->s_comp);
     if (h->s_comp2) cudaStreamSynchronize(h->s_comp2);
     if (h->s_tb) cudaStreamSynchronize(h->s_tb);
@@ -918,6 +1049,7 @@ extern "C" int rsa_ext_wait(rsa_ext_t* h) {
             h->tail = (h->tail + 1) % kSlots;
         }
     }
+    plan_ahead_finish(h);
     if (rc) {
         cudaDeviceSynchronize();
         for (Slot& s : h->slots) s.busy = false;
@@ -987,6 +1119,14 @@ extern "C" int rsa_ext_get_stats(const rsa_ext_t* hc, rsa_ext_stats_t* out) {
         }
         h->stats.dp_ms = dp;
         h->stats.tb_ms = tb;
+        if (getenv("RSA_EXT_TRACE")) {  // timeline of the last resident run, ms after the first chunk's DP start
+            for (size_t c = 0; c < h->res_chunks.size(); ++c) {
+                float t[4];
+                for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], h->r_events[0], h->r_events[4 * c + i]);
+                fprintf(stderr, "[rsa_ext timeline] chunk %2zu n=%6lld  dp %7.3f..%7.3f  tb %7.3f..%7.3f\n", c,
+                        (long long)h->res_chunks[c].plan.n, t[0], t[1], t[2], t[3]);
+            }
+        }
         unsigned long long c3[3] = {0, 0, 0};
         cudaMemcpy(c3, h->slots[0].d_arena_used, sizeof c3, cudaMemcpyDeviceToHost);
         h->stats.pairs_redo = (int64_t)c3[2];  // last chunk only
@@ -1034,7 +1174,9 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
     if ((rc = ensure_dev(h, h->r_t, tbytes + 16))) return rc;
     if ((rc = ensure_dev(h, h->r_res, sizeof(rsa_ext_result_t) * (size_t)n))) return rc;
     if ((rc = ensure_dev(h, h->r_blobs, blob_total))) return rc;
-    for (int k = 0; k < (h->res_chunks.size() > 1 ? 2 : 1); ++k) {  // resident chunks alternate between two slots' scratch
+    // resident chunks rotate through the slots' scratch: with three, DP(c) never waits for the traceback of the
+    // chunk that used its slot last (with two, DP(c) and DP(c+1) ran side by side and both waited: no overlap)
+    for (int k = 0; k < (int)std::min<size_t>(h->res_chunks.size(), kSlots); ++k) {
         Slot& s = h->slots[k];
         h->r_need = SlotNeed{0, 0, 0, sizeof(DpEnd) * (size_t)max_pairs, 0, (size_t)max_arena, 0, scratch_alloc_bytes(max_scratch)};
         if ((rc = ensure_slot(h, s, h->r_need))) return rc;
@@ -1066,7 +1208,7 @@ extern "C" int rsa_ext_run_resident(rsa_ext_t* h) {
     if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     h->stats.kernel_launches = 0;
-    const int nslots = h->res_chunks.size() > 1 ? 2 : 1;
+    const int nslots = (int)std::min<size_t>(h->res_chunks.size(), kSlots);
     // a submit since rsa_ext_stage_resident may have re-carved the slots' buffers
     for (int k = 0; k < nslots; ++k) { int rc = ensure_slot(h, h->slots[k], h->r_need); if (rc) return rc; }
     h->resident_inflight = true;

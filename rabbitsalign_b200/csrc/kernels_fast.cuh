@@ -232,7 +232,9 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int GPW = fast_groups_per_warp(L), WPB = fast_warps_per_block(L);
     const int gi = lane / L, gl = lane % L;
-    const int g_index = (blockIdx.x * WPB + warp) * GPW + gi;
+    // the planner orders a class by increasing window length; blocks are handed out in index order, so walk the
+    // class from its long end: the last, partially filled wave then holds the shortest tasks
+    const int g_index = (int)(gridDim.x * WPB * GPW) - 1 - ((blockIdx.x * WPB + warp) * GPW + gi);
     FastGroup grp;
     grp.a = 0xFFFFFFFFu; grp.b = 0xFFFFFFFFu; grp.dir_off = 0; grp.qlen = 0; grp.rows = 0;
     if (g_index < n_groups) grp = groups[g_index];

@@ -20,10 +20,28 @@ static int g_iters = 32768;
 static rsa::FastConsts g_consts;
 constexpr int CH = 8;
 
-enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL, N_OPS };
+enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL,
+          HFMA2, HMNMX2, FFMA, MIX_ALU_HFMA2, MIX_ALU3_HFMA2, MIX_ALU3_IMAD, N_OPS };
 static const char* kNames[N_OPS] = {"VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "IADD3", "LOP3", "PRMT",
-                                    "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (rsa::fast_cell, 2 cells per call)"};
-static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0};
+                                    "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (rsa::fast_cell, 2 cells per call)",
+                                    "HFMA2", "HMNMX2", "FFMA", "LOP3+HFMA2 1:1", "LOP3+HFMA2 3:1", "LOP3+IMAD 3:1"};
+static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0, CH, CH, CH, 2 * CH, 4 * CH, 4 * CH};
+
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int OP>
 __global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cycles, int ITERS) {
@@ -34,6 +52,7 @@ __global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cyc
 #pragma unroll
     for (int k = 0; k < CH; ++k) m[k] = a[k] ^ 0x5555u;
     __syncthreads();
+    const unsigned long long n0 = globaltimer_ns();
     const unsigned long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
@@ -50,15 +69,27 @@ __global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cyc
             else if (OP == SHF) a[k] = __funnelshift_r(a[k], b, 5);
             else if (OP == MIX_ALU_IMAD) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = m[k] * 3u + b; }
             else if (OP == MIX_DPX_IMAD) { a[k] = __vimax3_s16x2(a[k], b, c); m[k] = m[k] * 3u + b; }
+            else if (OP == HFMA2) a[k] = hfma2(a[k], b, c);
+            else if (OP == HMNMX2) a[k] = hmax2(a[k], b);
+            else if (OP == FFMA) a[k] = __float_as_uint(fmaf(__uint_as_float(a[k]), __uint_as_float(b), __uint_as_float(c)));
+            else if (OP == MIX_ALU_HFMA2) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = hfma2(m[k], b, c); }
+            else if (OP == MIX_ALU3_HFMA2) {
+                a[k] = (a[k] & b) | (c & ~a[k]); m[k] = hfma2(m[k], b, c);
+                a[k] = (a[k] & c) | (b & ~a[k]); a[k] = (a[k] & d) | (c & ~a[k]);
+            } else if (OP == MIX_ALU3_IMAD) {
+                a[k] = (a[k] & b) | (c & ~a[k]); m[k] = m[k] * 3u + b;
+                a[k] = (a[k] & c) | (b & ~a[k]); a[k] = (a[k] & d) | (c & ~a[k]);
+            }
         }
         b += d;  // loop-variant operand (1 extra instruction per iteration, amortised over CH)
     }
     const unsigned long long t1 = clock64();
+    const unsigned long long n1 = globaltimer_ns();
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < CH; ++k) s += a[k] + m[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
 // The packed cell recipe of the product kernel -- rsa::fast_cell() from csrc/fast_cell.cuh, the very same
@@ -72,6 +103,7 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
     for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = k.zero; qsel[c] = in[10 + c]; }
     uint32_t F = k.zero, Hl = k.zero, rowkey = 0, sink = 0;
     __syncthreads();
+    const unsigned long long n0 = globaltimer_ns();
     const unsigned long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
@@ -94,11 +126,12 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
         px += py;
     }
     const unsigned long long t1 = clock64();
+    const unsigned long long n1 = globaltimer_ns();
     uint32_t s = sink + rowkey + F;
 #pragma unroll
     for (int c = 0; c < CH; ++c) s += S[c] + E[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
 // ---- experimental recipe variants (same outputs as rsa::fast_cell; evaluated here before the kernel adopts one) ----
@@ -135,6 +168,7 @@ __global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const
     for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = zS; qsel[c] = in[10 + c]; }
     uint32_t F = zS, Hl = k.zero, rowkey = 0, sink = 0;
     __syncthreads();
+    const unsigned long long n0 = globaltimer_ns();
     const unsigned long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
@@ -157,11 +191,12 @@ __global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const
         px += py;
     }
     const unsigned long long t1 = clock64();
+    const unsigned long long n1 = globaltimer_ns();
     uint32_t s = sink + rowkey + F;
 #pragma unroll
     for (int c = 0; c < CH; ++c) s += S[c] + E[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
 template <int V>
@@ -197,11 +232,13 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
     }
     float ms = 0;
     CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    std::vector<unsigned long long> cyc(blocks);
-    CHECK(cudaMemcpy(cyc.data(), d_cyc, sizeof(unsigned long long) * blocks, cudaMemcpyDeviceToHost));
-    double mean = 0;
-    for (auto c : cyc) mean += (double)c;
+    std::vector<unsigned long long> cyc(2 * blocks);
+    CHECK(cudaMemcpy(cyc.data(), d_cyc, sizeof(unsigned long long) * 2 * blocks, cudaMemcpyDeviceToHost));
+    double mean = 0, mean_ns = 0;
+    for (int b = 0; b < blocks; ++b) { mean += (double)cyc[b]; mean_ns += (double)cyc[blocks + b]; }
     mean /= blocks;
+    mean_ns /= blocks;
+    const double sm_mhz = mean / mean_ns * 1e3;  // clock64 ticks per %globaltimer ns inside the kernel: the SM clock under this load
     const int ITERS = g_iters;
     const double warps_per_sm = (double)blocks_per_sm * threads / 32.0;
     if (OP == CELL) {
@@ -209,16 +246,15 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
         const double cells_per_clk_sm = 2.0 * cellpairs * 32.0 * warps_per_sm / mean;
         const double gcups = 2.0 * cellpairs * (double)blocks * threads / (ms * 1e-3) / 1e9;
         printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"cells_per_clk_per_sm\": %.2f, \"clk_per_cellpair_per_smsp_warp\": %.2f, "
-               "\"chip_gcups\": %.1f, \"ms\": %.3f, \"eff_mhz\": %.0f}\n",
-               kNames[OP], warps_per_sm, cells_per_clk_sm, mean / cellpairs / (warps_per_sm / 4.0), gcups, ms,
-               mean / (ms * 1e-3) / 1e6);
+               "\"chip_gcups\": %.1f, \"ms\": %.3f, \"sm_mhz_in_kernel\": %.0f}\n",
+               kNames[OP], warps_per_sm, cells_per_clk_sm, mean / cellpairs / (warps_per_sm / 4.0), gcups, ms, sm_mhz);
     } else {
         const double instr = (double)ITERS * kInstrPerIter[OP];  // per warp
         const double ipc_sm = instr * warps_per_sm / mean;
         const double chip = instr * (double)blocks * threads / 32.0 / (ms * 1e-3);
         printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"warp_instr_per_clk_per_sm\": %.3f, \"chip_warp_ginstr_per_s\": %.1f, "
-               "\"ms\": %.3f, \"eff_mhz\": %.0f}\n",
-               kNames[OP], warps_per_sm, ipc_sm, chip / 1e9, ms, mean / (ms * 1e-3) / 1e6);
+               "\"ms\": %.3f, \"sm_mhz_in_kernel\": %.0f}\n",
+               kNames[OP], warps_per_sm, ipc_sm, chip / 1e9, ms, sm_mhz);
     }
     (void)sm_khz;
 }
@@ -233,7 +269,7 @@ int main(int argc, char** argv) {
     uint32_t *d_out, *d_in;
     unsigned long long* d_cyc;
     CHECK(cudaMalloc(&d_out, sizeof(uint32_t) * n_sms * 8 * 1024));
-    CHECK(cudaMalloc(&d_cyc, sizeof(unsigned long long) * n_sms * 8));
+    CHECK(cudaMalloc(&d_cyc, sizeof(unsigned long long) * n_sms * 16));
     std::vector<uint32_t> in(64);
     in[0] = 0x00400040u; in[1] = 0u - 8u * 0x10001u; in[2] = 0u - 20u * 0x10001u; in[3] = 0xFFFFFFFFu;
     in[4] = 0x80008000u; in[5] = 0x40004000u; in[6] = 0x1FFF1FFFu; in[7] = 0x0FFF0FFFu; in[8] = 0x0A000000u; in[9] = 0x00000A00u;
@@ -260,6 +296,12 @@ int main(int argc, char** argv) {
             run<SHF>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<MIX_ALU_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<MIX_DPX_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<HFMA2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<HMNMX2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<FFMA>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU_HFMA2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU3_HFMA2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU3_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         }
         run<CELL>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         if (!quick) {
