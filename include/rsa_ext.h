@@ -13,6 +13,10 @@
  * negative status; rsa_ext_last_error() gives the text.  A handle is owned by one host thread at a
  * time (the reference keeps one GASAL stream + storage per worker `thread_id`,
  * src/gasal2_ssw.cpp:29,92-102); different handles are independent and may live on different GPUs.
+ * A handle that has seen a batch of more than 32768 pairs owns one helper thread (it plans the chunks of
+ * large batches ahead of the caller's thread; idle otherwise, joined by rsa_ext_destroy).  Handle creation
+ * and each handle's first submit are serialised process-wide (driver-lock contention).
+ * RSA_EXT_TRACE=1 in the environment prints host-side timing laps to stderr.
  *
  * There is NO CPU fallback inside this library: without a usable CUDA device rsa_ext_create fails.
  */
