@@ -239,3 +239,51 @@ def test_single_pair_batches(engine, oracle_lib):
     for q, t in [(b"ACGTACGTACGTACGT", b"TTACGTACGTACGTACGTTT"), (b"A", b"A"), (b"ACGTACGTAC" * 25, b"ACGTACGTAC" * 30)]:
         got = engine.solve_ssw_on_gpu([q], [t])[0].astuple()
         assert got == oracle_lib.align([q], [t])[0].astuple()
+
+
+def test_plan_ahead_equals_inline_slices(engine, oracle_lib):
+    """A batch above the plan-ahead threshold (helper thread plans the chunks) gives the records of the same pairs
+    sent in slices small enough to be planned inline; a sample is also checked against the oracle."""
+    b = W.extension_pairs(90_000, seed=170, fixed_query_len=False, indel_rate=0.01, n_rate=0.002)
+    whole = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    parts = []
+    step = 30_000  # <= 32768: inline planning
+    for lo in range(0, b.n, step):
+        part = b.slice(lo, min(b.n, lo + step))
+        parts.append(engine.align_packed(part.qbuf, part.qoff, part.tbuf, part.toff).copy())
+    sliced = np.concatenate(parts)
+    fields = ["score", "query_start", "query_end", "ref_start", "ref_end", "n_ops", "status"]
+    for f in fields:
+        assert (whole[f] == sliced[f]).all(), f
+    short = whole["n_ops"] <= 40
+    assert (whole["rle"][short] == sliced["rle"][short]).all()
+    sub = b.slice(0, 4000)
+    first = engine.align_packed(sub.qbuf, sub.qoff, sub.tbuf, sub.toff)
+    for f in fields:
+        assert (first[f] == whole[f][:4000]).all(), f
+    bad = compare(engine, first, oracle_arrays(oracle_lib, sub), sub)
+    assert not bad, "\n".join(bad)
+
+
+def test_large_then_small_then_large_on_one_handle(engine):
+    """The helper thread is reused across batches and idle for small ones."""
+    big = W.fixed_pairs_fast(70_000, qlen=150, tlen=220, sub_rate=0.02, seed=171)
+    small = W.extension_pairs(300, seed=172)
+    r1 = engine.align_packed(big.qbuf, big.qoff, big.tbuf, big.toff).copy()
+    rs = engine.align_packed(small.qbuf, small.qoff, small.tbuf, small.toff).copy()
+    r2 = engine.align_packed(big.qbuf, big.qoff, big.tbuf, big.toff).copy()
+    rs2 = engine.align_packed(small.qbuf, small.qoff, small.tbuf, small.toff).copy()
+    assert r1.tobytes() == r2.tobytes() and rs.tobytes() == rs2.tobytes()
+    assert (r1["status"] == 0).all() and (r1["score"] > 0).all()
+
+
+def test_query_too_long_inside_a_large_batch(engine):
+    from rabbitsalign_b200 import ExtensionError
+    b = W.fixed_pairs_fast(50_000, qlen=150, tlen=200, seed=173)
+    qs = [bytes(b.qbuf[b.qoff[i]:b.qoff[i + 1]]) for i in range(40_000)] + [b"A" * 501]
+    ts = [bytes(b.tbuf[b.toff[i]:b.toff[i + 1]]) for i in range(40_000)] + [b"A" * 600]
+    bb = W.from_lists(qs, ts)
+    with pytest.raises(ExtensionError) as ei:
+        engine.align_packed(bb.qbuf, bb.qoff, bb.tbuf, bb.toff)
+    assert ei.value.status == -3
+    assert engine.solve_ssw_on_gpu([b"ACGT"], [b"ACGT"])[0].score == 8
