@@ -105,6 +105,11 @@ int rsa_ext_poll(rsa_ext_t *h);
  * (given to submit) is filled. */
 int rsa_ext_wait(rsa_ext_t *h);
 
+/* Pre-allocate what batches of up to n pairs of (qlen x tlen) need (device buffers of the first chunk slot, pinned
+ * staging), so the first real batches allocate nothing.  Optional; the reference allocates its GASAL storage for
+ * STREAM_BATCH_SIZE x MAX lengths up front (gasal_init_streams, src/gasal2_ssw.cpp:92-102). */
+int rsa_ext_reserve(rsa_ext_t *h, int64_t n, int32_t qlen, int32_t tlen);
+
 /* Full RLE byte string of pair i of the last waited batch when n_ops > RSA_EXT_RLE_INLINE.
  * Returns the number of bytes written (<= cap) or a negative status. */
 int rsa_ext_rle_overflow(rsa_ext_t *h, int64_t i, uint8_t *out, int32_t cap);

@@ -8,6 +8,8 @@
 #   rabbitsalign_b200     integration/gasal2_ssw.cpp + librsa_ext.so     the product drop-in (needs a GPU)
 #   rabbitsalign_gasalref oracle/_ref/libgasal_ref512.so behind solve_ssw_on_gpu: the reference's own GASAL2
 #                         kernels compiled for the host = golden-SAM generator (CPU only, test infrastructure)
+#   rabbitsalign_b200_alninfo  the product drop-in plus the optional caller-loop edit (patch_caller.py): gasal_fail +
+#                         Aligner::align_gpu come from the device (finish_kernel); needs a GPU
 #   rabbitsalign_cpussw   solve_ssw_on_gpu returns failed records -> every extension takes the reference's
 #                         CPU SSW path (Aligner::align): the end-to-end CPU baseline (test/bench infrastructure)
 #
@@ -84,4 +86,24 @@ $CXX -o "$OUT/rabbitsalign_fx_b200" $FXOBJS $FXIO "$OUT/obj/veneer.o" -L"$ROOT/r
 $CXX -o "$OUT/rabbitsalign_fx_gasalref" $FXOBJS $FXIO "$OUT/obj/solve_gasalref.o" "$ROOT/oracle/_ref/libgasal_ref512.so" \
      -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
 $CXX -o "$OUT/rabbitsalign_fx_cpussw" $FXOBJS $FXIO "$OUT/obj/solve_cpussw.o" -lz -lpthread
+
+# ---- optional build: AlignmentInfo straight from the device.  The caller loops of src/pc.cpp get
+#      the two-call substitution of integration/patch_caller.py on a copy under _build/alninfo/; every unit that
+#      sees gasal_tmp_res is rebuilt with -DRSA_EXT_ALNINFO (the record carries the device's rsa_ext_alninfo_t).
+mkdir -p "$OUT/alninfo" "$OUT/obj_aln"
+python3 "$HERE/patch_caller.py" "$REF_ROOT/src/pc.cpp" "$OUT/alninfo/pc.cpp"
+ALNFLAGS="$FLAGS -DRSA_EXT_ALNINFO"
+pids=()
+( $CXX $ALNFLAGS -c "$OUT/alninfo/pc.cpp" -o "$OUT/obj_aln/pc.o" ) & pids+=($!)
+( $CXX $ALNFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$OUT/alninfo/pc.cpp" -o "$OUT/obj_aln/pc_fx.o" ) & pids+=($!)
+( $CXX $ALNFLAGS -c "$REF_ROOT/src/aligner.cpp" -o "$OUT/obj_aln/aligner.o" ) & pids+=($!)
+( $CXX $ALNFLAGS -c "$REF_ROOT/ext/ssw/ssw_cpp.cpp" -o "$OUT/obj_aln/ssw_cpp.o" ) & pids+=($!)
+( $CXX $ALNFLAGS -c "$HERE/gasal2_ssw.cpp" -o "$OUT/obj_aln/veneer.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+ALNOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc|aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_alninfo" $ALNOBJS "$OUT/obj_aln/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+ALNFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_aln/pc_fx.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_alninfo" $ALNFXOBJS $FXIO "$OUT/obj_aln/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
 ls -la "$OUT"/rabbitsalign_*

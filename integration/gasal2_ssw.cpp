@@ -18,8 +18,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <atomic>
+#include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <utility>
 
 #include "rsa_ext.h"
 
@@ -30,6 +34,9 @@ struct Worker {
     std::vector<const char *> qp, tp;
     std::vector<int32_t> ql, tl;
     std::vector<rsa_ext_result_t> res;
+#ifdef RSA_EXT_ALNINFO
+    std::vector<rsa_ext_alninfo_t> aln;
+#endif
     std::vector<uint8_t> rle;
     ~Worker() { if (h) rsa_ext_destroy(h); }
 };
@@ -47,29 +54,100 @@ int device_count_cap() {
     return e ? atoi(e) : 0;
 }
 
+#ifdef RSA_EXT_ALNINFO
+// End bonus the finish kernel uses.  Starts at strobealign's default; the first call site that runs tells us the
+// aligner's value (rsa_ext_veneer_end_bonus), after which records the device settled carry no CIGAR text.
+std::atomic<int> g_end_bonus{10};
+std::atomic<bool> g_end_bonus_confirmed{false};
+#endif
+
 int usable_devices() {
     int ndev = rsa_ext_device_count();
     const int cap = device_count_cap();
     return (cap > 0 && cap < ndev) ? cap : ndev;
 }
 
-// Start the CUDA context(s) early; a failure here is not reported -- the first real call reports it.
+// Start CUDA early and keep a pool of ready handles: the context, the streams and every buffer a 512-pair slice
+// needs are created by ONE helper thread while the host loads the index, not by 16 workers inside their first
+// batches (allocations issued while other workers are enqueueing stalled everyone for 0.05-0.9 s each).
+// The pool uses strobealign's default scores; a first call with other scores, or more workers than the pool holds,
+// creates its handle the ordinary way.  A failure here is not reported -- the first real call reports it.
+constexpr int kDefaultScores[4] = {2, 8, 12, 1};  // src/cmdline.hpp:46-50 / the prototype's default arguments
+constexpr int kPoolReadLen = 250, kPoolWindowLen = 500;  // shapes the pooled handles are pre-sized for
+
 struct Warmup {
     std::thread t;
+    std::mutex m;
+    std::condition_variable cv;
+    bool done = true;
+    std::vector<std::pair<int, rsa_ext_t *>> pool;  // (device, handle)
+
     Warmup() {
         if (getenv("RSA_EXT_NO_WARMUP")) return;
-        t = std::thread([] {
-            const int ndev = usable_devices();
-            for (int d = 0; d < ndev; ++d) {
+        done = false;
+        // RSA_EXT_WARMUP=sync: create the CUDA context(s) right here, before main() starts its threads (context
+        // creation inside a process that is already building an index on 16 threads was measured 2-4x slower)
+        const char *mode = getenv("RSA_EXT_WARMUP");
+        if (mode && !strcmp(mode, "sync")) {
+            const int nd = usable_devices();
+            for (int d = 0; d < nd; ++d) {
                 rsa_ext_config_t cfg;
                 memset(&cfg, 0, sizeof cfg);
                 cfg.device = d;
                 rsa_ext_t *h = nullptr;
                 if (rsa_ext_create(&cfg, &h) == RSA_EXT_OK) rsa_ext_destroy(h);
             }
+        }
+        t = std::thread([this] {
+            const int ndev = usable_devices();
+            const char *pe = getenv("RSA_EXT_POOL");
+            const int hw = (int)std::thread::hardware_concurrency();
+            const int want = pe ? atoi(pe) : std::min(std::max(hw, 1), 32);
+            for (int k = 0; k < want && ndev > 0; ++k) {
+                rsa_ext_config_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.device = k % ndev;
+                cfg.max_query_len = MAX_QUERY_LEN;
+                cfg.max_target_len = MAX_TARGET_LEN;
+                cfg.match = kDefaultScores[0]; cfg.mismatch = kDefaultScores[1];
+                cfg.gap_open = kDefaultScores[2]; cfg.gap_extend = kDefaultScores[3];
+                rsa_ext_t *h = nullptr;
+                if (rsa_ext_create(&cfg, &h) != RSA_EXT_OK) break;
+                rsa_ext_reserve(h, STREAM_BATCH_SIZE, kPoolReadLen, kPoolWindowLen);
+                if (k < ndev) {  // one tiny batch per device loads the common kernels
+                    const std::string q(150, 'A'), w(200, 'A');
+                    const char *qp = q.data(), *tp = w.data();
+                    const int32_t ql = (int32_t)q.size(), tl = (int32_t)w.size();
+                    rsa_ext_result_t r;
+                    if (rsa_ext_submit_ptrs(h, 1, &qp, &ql, &tp, &tl, &r) == RSA_EXT_OK) rsa_ext_wait(h);
+                }
+                std::lock_guard<std::mutex> lk(m);
+                pool.emplace_back(cfg.device, h);
+            }
+            std::lock_guard<std::mutex> lk(m);
+            done = true;
+            cv.notify_all();
         });
     }
-    ~Warmup() { if (t.joinable()) t.join(); }
+    // a ready handle on `device` with the default scores, or nullptr
+    rsa_ext_t *take(int device, int match, int mismatch, int gap_open, int gap_extend) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return done; });
+        if (match != kDefaultScores[0] || mismatch != kDefaultScores[1] || gap_open != kDefaultScores[2] ||
+            gap_extend != kDefaultScores[3])
+            return nullptr;
+        for (size_t i = 0; i < pool.size(); ++i)
+            if (pool[i].first == device) {
+                rsa_ext_t *h = pool[i].second;
+                pool.erase(pool.begin() + (long)i);
+                return h;
+            }
+        return nullptr;
+    }
+    ~Warmup() {
+        if (t.joinable()) t.join();
+        for (auto &e : pool) rsa_ext_destroy(e.second);
+    }
 } g_warmup;
 
 }  // namespace
@@ -96,7 +174,8 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
         cfg.mismatch = mismatch_score;
         cfg.gap_open = gap_open_score;
         cfg.gap_extend = gap_extend_score;
-        if (rsa_ext_create(&cfg, &w.h) != RSA_EXT_OK) die("rsa_ext_create", nullptr);
+        w.h = g_warmup.take(cfg.device, match_score, mismatch_score, gap_open_score, gap_extend_score);
+        if (!w.h && rsa_ext_create(&cfg, &w.h) != RSA_EXT_OK) die("rsa_ext_create", nullptr);
     }
 
     w.qp.resize(n); w.tp.resize(n); w.ql.resize(n); w.tl.resize(n); w.res.resize(n);
@@ -104,6 +183,12 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
         w.qp[i] = query_seqs[i].data(); w.ql[i] = (int32_t)query_seqs[i].size();
         w.tp[i] = target_seqs[i].data(); w.tl[i] = (int32_t)target_seqs[i].size();
     }
+#ifdef RSA_EXT_ALNINFO
+    const int end_bonus = g_end_bonus.load();
+    const bool text_free = g_end_bonus_confirmed.load();
+    w.aln.resize(n);
+    if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
+#endif
     int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
     if (rc == RSA_EXT_ERR_QUERY_LEN) {
         size_t mx = 0;
@@ -124,7 +209,12 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
             rle = w.rle.data();
         }
         std::string cigar;
-        if (r.n_ops > 0) {
+#ifdef RSA_EXT_ALNINFO
+        const bool need_text = !text_free || w.aln[i].status == 3;
+#else
+        const bool need_text = true;
+#endif
+        if (r.n_ops > 0 && need_text) {
             int len = rsa_ext_rle_to_text(rle, r.n_ops, text, (int32_t)sizeof text);
             if (len < 0) {
                 std::vector<char> big((size_t)r.n_ops * 8 + 16);
@@ -135,5 +225,17 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
             }
         }
         gasal_results[i] = {r.score, r.query_start, r.query_end, r.ref_start, r.ref_end, std::move(cigar)};
+#ifdef RSA_EXT_ALNINFO
+        gasal_results[i].aln = w.aln[i];
+        gasal_results[i].aln_end_bonus = end_bonus;
+#endif
     }
 }
+
+#ifdef RSA_EXT_ALNINFO
+void rsa_ext_veneer_end_bonus(int end_bonus) {
+    if (g_end_bonus_confirmed.load(std::memory_order_relaxed) && g_end_bonus.load(std::memory_order_relaxed) == end_bonus) return;
+    g_end_bonus.store(end_bonus);
+    g_end_bonus_confirmed.store(true);
+}
+#endif

@@ -28,6 +28,10 @@
 #define DEBUG
 #define MAX(a, b) (a > b ? a : b)
 
+#ifdef RSA_EXT_ALNINFO
+#include "rsa_ext.h"
+#endif
+
 struct gasal_tmp_res {
     int score;
     int query_start;
@@ -35,9 +39,52 @@ struct gasal_tmp_res {
     int ref_start;
     int ref_end;
     std::string cigar_str;
+#ifdef RSA_EXT_ALNINFO
+    // Optional build (INTEGRATION.md "take AlignmentInfo straight from the device"): what gasal_fail +
+    // Aligner::align_gpu would compute from this record, filled by the engine's finish kernel.
+    rsa_ext_alninfo_t aln;
+    int aln_end_bonus = -1;  // end bonus (-L) the device used; < 0: no device record, use the host path
+#endif
 };
 
 void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &todo_querys,
                       std::vector<std::string> &todo_refs, int match_score = 2, int mismatch_score = 8,
                       int gap_open_score = 12, int gap_extend_score = 1);
+
+#ifdef RSA_EXT_ALNINFO
+// The two call-site helpers of the optional build.  They replace, at the four caller loops of src/pc.cpp
+// (:735-744 and siblings), `gasal_fail(q, r, rec)` and `aligner.align_gpu(q, r, rec)`; integration/patch_caller.py
+// makes exactly that substitution on a build-time copy.  Anything the device did not settle (CIGAR longer than
+// RSA_EXT_CIGAR_INLINE ops, another end bonus than the aligner's) takes the reference's own host code.
+void rsa_ext_veneer_end_bonus(int end_bonus);  // tells the veneer the aligner's -L; from then on it skips CIGAR text
+                                               // for records the device settled
+
+template <class Rec>
+bool rsa_ext_gasal_fail(std::string &query, std::string &ref, Rec &rec) {
+    if (rec.aln_end_bonus >= 0) {
+        if (rec.aln.status == 0) return false;                         // accepted on the device
+        if (rec.aln.status == 1 || rec.aln.status == 2) return true;   // gasal_fail / window over MAX_TARGET_LEN
+    }
+    return gasal_fail(query, ref, rec);  // src/pc.cpp:466-478
+}
+
+template <class AlignerT, class Rec>
+auto rsa_ext_align_gpu(const AlignerT &aligner, const std::string &query, const std::string &ref, Rec &rec)
+    -> decltype(aligner.align_gpu(query, ref, rec)) {
+    const int want = aligner.parameters.end_bonus;
+    rsa_ext_veneer_end_bonus(want);
+    if (rec.aln_end_bonus == want && rec.aln.status == 0) {
+        decltype(aligner.align_gpu(query, ref, rec)) info;  // AlignmentInfo, src/aligner.hpp:20-30
+        info.cigar = decltype(info.cigar)(const_cast<uint32_t *>(rec.aln.cigar), (size_t)rec.aln.n_cigar);
+        info.edit_distance = (unsigned)rec.aln.edit_distance;
+        info.ref_start = (unsigned)rec.aln.ref_start;
+        info.ref_end = (unsigned)rec.aln.ref_end;
+        info.query_start = (unsigned)rec.aln.query_start;
+        info.query_end = (unsigned)rec.aln.query_end;
+        info.sw_score = rec.aln.sw_score;
+        return info;
+    }
+    return aligner.align_gpu(query, ref, rec);
+}
+#endif  // RSA_EXT_ALNINFO
 #endif  // STROBEALIGN_GASAL2_SSW_H

@@ -297,6 +297,19 @@ struct LenTables {
 };
 const LenTables& len_tables() { static const LenTables t; return t; }
 
+// Section offsets of the metadata blob of an n-pair chunk; returns its size.
+size_t blob_layout(ChunkPlan& plan, int64_t n) {
+    size_t off = 0;
+    plan.off_meta = off;   off = align_up(off + sizeof(PairMeta) * n, 16);
+    plan.off_info = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
+    plan.off_diroff = off; off = align_up(off + sizeof(uint64_t) * n, 16);
+    plan.off_list = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
+    plan.off_groups = off; off = align_up(off + sizeof(FastGroup) * (size_t)(n + 8 * 64), 16);
+    plan.off_redo = off;   off = align_up(off + sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4), 16);
+    plan.blob_bytes = off;
+    return off;
+}
+
 int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std::vector<uint8_t>* vec_blob,
                PinBuf* pin_blob) {
     const LenTables& LT = len_tables();
@@ -332,14 +345,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     plan.t_bytes = in.toff[hi] - t0;
 
     // 2) blob layout
-    size_t off = 0;
-    plan.off_meta = off;   off = align_up(off + sizeof(PairMeta) * n, 16);
-    plan.off_info = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
-    plan.off_diroff = off; off = align_up(off + sizeof(uint64_t) * n, 16);
-    plan.off_list = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
-    plan.off_groups = off; off = align_up(off + sizeof(FastGroup) * (size_t)(n + 8 * 64), 16);
-    plan.off_redo = off;   off = align_up(off + sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4), 16);
-    plan.blob_bytes = off;
+    const size_t off = blob_layout(plan, n);
     uint8_t* blob;
     if (vec_blob) { vec_blob->resize(off); blob = vec_blob->data(); }
     else {
@@ -972,6 +978,34 @@ extern "C" int rsa_ext_submit_ptrs(rsa_ext_t* h, int64_t n, const char* const* q
     }
     return submit_core(h, n, reinterpret_cast<const char*>(h->own_q.p), h->own_qoff.data(),
                        reinterpret_cast<const char*>(h->own_t.p), h->own_toff.data(), results);
+}
+
+// Allocate, now, what a batch of n pairs of (qlen x tlen) needs from slot 0 and the submit_ptrs staging, so that the
+// first real batches of this shape allocate nothing (a cudaMalloc issued while 16 workers are enqueueing has been
+// measured at 0.05-0.9 s, during which every other worker's enqueue stalls on the same driver lock).
+extern "C" int rsa_ext_reserve(rsa_ext_t* h, int64_t n, int32_t qlen, int32_t tlen) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    if (n <= 0 || qlen <= 0 || tlen <= 0 || qlen > h->cfg.max_query_len || tlen > h->cfg.max_target_len) {
+        h->err = "bad argument";
+        return RSA_EXT_ERR_ARG;
+    }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    std::lock_guard<std::mutex> cold(g_cold_mutex);
+    const LenTables& LT = len_tables();
+    uint64_t per_pair = (uint64_t)tlen * LT.exact_row_bytes_[qlen] + 16;  // same rule as the chunk budget (plan_chunk)
+    if (fast_shape_ok(qlen, tlen, h->sc.match)) per_pair = std::max<uint64_t>(per_pair, (uint64_t)((tlen + 3) & ~3) * LT.fast_row_bytes[qlen]);
+    ChunkPlan p;
+    const size_t blob = blob_layout(p, n);
+    const SlotNeed need{blob, (size_t)n * qlen + 16, (size_t)n * tlen + 16, sizeof(DpEnd) * (size_t)n,
+                        sizeof(rsa_ext_result_t) * (size_t)n, (size_t)n * (qlen + tlen + 1) + 64,
+                        sizeof(rsa_ext_alninfo_t) * (size_t)n, scratch_alloc_bytes((uint64_t)n * per_pair)};
+    int rc;
+    if ((rc = ensure_slot(h, h->slots[0], need))) return rc;
+    if ((rc = ensure_pin(h, h->slots[0].h_blob, blob))) return rc;
+    if ((rc = ensure_pin(h, h->own_q, (size_t)n * qlen + 16))) return rc;
+    if ((rc = ensure_pin(h, h->own_t, (size_t)n * tlen + 16))) return rc;
+    return RSA_EXT_OK;
 }
 
 extern "C" int rsa_ext_request_alninfo(rsa_ext_t* h, rsa_ext_alninfo_t* out, int32_t end_bonus) {

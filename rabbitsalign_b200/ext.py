@@ -63,6 +63,7 @@ ABI_SYMBOLS = [
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
+    "rsa_ext_reserve",
 ]
 
 _lib = None
@@ -112,6 +113,8 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_request_alninfo.restype = C.c_int
     lib.rsa_ext_plan_debug.argtypes = [i64, vp, vp, i64, C.c_int, vp]
     lib.rsa_ext_plan_debug.restype = C.c_int
+    lib.rsa_ext_reserve.argtypes = [vp, i64, i32, i32]
+    lib.rsa_ext_reserve.restype = C.c_int
     _lib = lib
     return lib
 
@@ -200,6 +203,10 @@ class ExtensionEngine:
         """Also produce `AlignmentInfo` records (ALNINFO_DTYPE) on the device for the following submits."""
         self._aln_keep = out
         self._check(self.lib.rsa_ext_request_alninfo(self.h, out.ctypes.data if out is not None else None, end_bonus))
+
+    def reserve(self, n: int, qlen: int, tlen: int):
+        """Pre-allocate for batches of up to n pairs of (qlen x tlen)."""
+        self._check(self.lib.rsa_ext_reserve(self.h, n, qlen, tlen))
 
     def poll(self) -> int:
         return self.lib.rsa_ext_poll(self.h)

@@ -2,7 +2,9 @@
 construction, gasal_fail gate, align_gpu, SAM writer -- compiled from /root/reference by
 integration/build.sh) linked against the product (integration/gasal2_ssw.cpp -> librsa_ext.so) must write
 the same SAM as the same pipeline linked against the reference's own GASAL2 kernels (golden md5s in
-tests/golden/sam_golden.json, generated in the dev container by tests/golden/make_sam_golden.py)."""
+tests/golden/sam_golden.json, generated in the dev container by tests/golden/make_sam_golden.py).
+The `alninfo` variants add the optional caller-loop edit (integration/patch_caller.py): gasal_fail and
+Aligner::align_gpu are taken from the device's finish kernel; the SAM must still be the same bytes."""
 import json
 import os
 import subprocess
@@ -17,10 +19,11 @@ pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_golden.json")))
 
 
+@pytest.mark.parametrize("variant", ["record", "alninfo"])
 @pytest.mark.parametrize("name", sorted(GOLD))
-def test_sam_is_byte_identical(name, tmp_path):
+def test_sam_is_byte_identical(name, variant, tmp_path):
     g = GOLD[name]
-    BIN = os.path.join(B, "rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200")
+    BIN = os.path.join(B, ("rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200") + ("_alninfo" if variant == "alninfo" else ""))
     if not os.path.exists(BIN):
         pytest.skip(f"{BIN} not built (needs /root/reference at build time)")
     d = str(tmp_path / name)

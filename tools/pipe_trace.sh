@@ -9,8 +9,11 @@ run() {  # tag, binary, env...
   s=$(date +%s%N)
   env "$@" $B/$exe -t $T -o $D/o.sam $D/ref.fa $D/reads_1.fq 2> gpurun_out/pipe_$tag.err
   e=$(date +%s%N)
-  echo "$tag wall $(( (e - s) / 1000000 )) ms; $(grep -a 'Total time mapping' gpurun_out/pipe_$tag.err); $(grep -a 'Total time indexing' gpurun_out/pipe_$tag.err)"
+  f=gpurun_out/pipe_$tag.err
+  echo "$tag wall $(( (e - s) / 1000000 )) ms; $(grep -a 'Total time mapping' $f); $(grep -a 'Total time indexing' $f); ctx $(grep -a -m1 'context' $f | awk '{print $2, $(NF-1)}'); first chunk $(grep -a -m1 ' chunk ' $f | awk '{print $2}'); last $(grep -a 'retire\|chunk' $f | tail -1 | awk '{print $2}'); calls $(grep -a -c 'retire' $f)"
 }
 for i in 1 2 3; do run b200_$i rabbitsalign_b200 RSA_EXT_TRACE=1; done
-run b200_nowarm rabbitsalign_b200 RSA_EXT_TRACE=1 RSA_EXT_NO_WARMUP=1
-for i in 1 2; do run cpu_$i rabbitsalign_cpussw X=1; done
+for i in 1 2 3; do run sync_$i rabbitsalign_b200 RSA_EXT_TRACE=1 RSA_EXT_WARMUP=sync; done
+for i in 1 2; do run aln_$i rabbitsalign_b200_alninfo RSA_EXT_TRACE=1; done
+for i in 1 2; do run alnsync_$i rabbitsalign_b200_alninfo RSA_EXT_TRACE=1 RSA_EXT_WARMUP=sync; done
+run cpu_1 rabbitsalign_cpussw X=1
