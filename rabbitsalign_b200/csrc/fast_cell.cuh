@@ -11,7 +11,7 @@ constexpr int kBias = 64;  // every stored half = value + kBias; E,F >= -(mismat
 
 struct FastConsts {
     uint32_t zero;     // (kBias, kBias)
-    uint32_t neg_x;    // ring constant: subtract mismatch from both halves
+    uint32_t neg_x16;  // per-half s16 (-mismatch) for the fused add+max of H
     uint32_t neg_xoe;  // subtract mismatch + gap_oe
     uint32_t neg_e;    // per-half s16 (-gap_ext) for VIADDMNMX
     uint32_t k_f, k_e, k_d, k_n;
@@ -30,12 +30,12 @@ __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
     FastConsts k;
     k.bias = kBias;
     k.zero = pair16(kBias);
-    k.neg_x = (uint32_t)(0u - (uint32_t)sc.mismatch * 0x00010001u);
+    k.neg_x16 = pair16(-sc.mismatch);
     k.neg_xoe = (uint32_t)(0u - (uint32_t)(sc.mismatch + sc.gap_oe) * 0x00010001u);
     k.neg_e = pair16(-sc.gap_ext);
     k.k_f = pair16(sc.gap_ext + 0x7FFF);
     k.k_e = pair16(sc.gap_ext + 0x3FFF);
-    k.k_d = pair16(0x1FFF);
+    k.k_d = pair16(0x1FFF + sc.mismatch);  // the flag is taken from h - s, and s carries +mismatch
     k.k_n = pair16(0x0FFF);
     k.x_pair = pair16(sc.mismatch);
     k.prof_match = (uint32_t)(sc.match + sc.mismatch);
@@ -71,18 +71,18 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 //      (15 F opened, 14 E opened, 13 H != diagonal, 12 max(F,E,0) != F; bits 11..0 are garbage);
 //      key = ((h - bias) << 5) | (31 - column) for the first-maximum tracking; `colconst` carries both the column
 //      term and the -bias*32 correction (ring constant), so the key of an all-zero cell is just its column term.
-// ALU pipe: VIMNMX3, VIMNMX, 2x VIADDMNMX, 3x IADD3, 4x LOP3(-class).  FMA pipe: the adds below written as IMADs.
+// ALU pipe: VIMNMX3, 3x VIADDMNMX (H takes its "- mismatch" inside the fused add+max, so diag+sub is never
+// materialised), 3x IADD3, 3x LOP3, one add.  FMA pipe: the adds below written as IMADs.
 __device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
                                           uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
-    const uint32_t tmp = s + k.neg_x;
     const uint32_t tg = s + k.neg_xoe;
     const uint32_t u = __vimax3_s16x2(F, e, k.zero);
-    h = __vmaxs2(tmp, u);
+    h = __viaddmax_s16x2(s, k.neg_x16, u);                        // max(diag + sub, F, E, 0)
     fn = __viaddmax_s16x2(F, k.neg_e, tg);
     en = __viaddmax_s16x2(e, k.neg_e, tg);
     const uint32_t fo = fn - F + k.k_f;                           // bit15: F opened
     const uint32_t eo = en - e + k.k_e;                           // bit14: E opened
-    const uint32_t nd = imad(tmp, k.minus1, imad(h, k.one, k.k_d));  // bit13: H != diagonal  (h - tmp + k_d, FMA pipe)
+    const uint32_t nd = imad(s, k.minus1, imad(h, k.one, k.k_d));    // bit13: H != diagonal  (h - (s - x) + 0x1FFF, FMA pipe)
     const uint32_t nf = u - F + k.k_n;                            // bit12: max(F,E,0) != F
     fl = bitsel(0x80008000u, fo, eo);
     fl = bitsel(0xC000C000u, fl, nd);
