@@ -196,3 +196,40 @@ def ssw_reference() -> Optional[SswReference]:
         p = os.path.join(_HERE, "_ref", f"libssw_ref_{v}.so")
         _cache["ssw"] = SswReference(p) if os.path.exists(p) else None
     return _cache["ssw"]
+
+
+class GasalGpuReference:
+    """The reference's own GPU path (GASAL2 + solve_ssw_on_gpu, compiled for sm_100a into _ref/libgasal_gpu.so):
+    the strongest checker there is -- the unmodified reference CUDA kernels on the same GPU -- and the GPU
+    comparator.  Needs a GPU; like the reference it exit()s the process on CUDA errors and on queries > 500."""
+
+    def __init__(self, path: str):
+        self.lib = C.CDLL(path)
+        self.lib.gasal_gpu_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.gasal_gpu_batch.restype = C.c_int
+        self.slice_size = int(self.lib.gasal_gpu_slice_size())
+
+    def batch(self, qbuf, qoff, tbuf, toff, thread_id: int = 0, cigar_stride: int = 0):
+        """-> (int32 array n x 5: score, query_start, query_end, ref_start, ref_end; list of CIGAR strings or None)"""
+        n = len(qoff) - 1
+        out5 = np.zeros((n, 5), dtype=np.int32)
+        cig = np.zeros(n * cigar_stride, dtype=np.uint8) if cigar_stride else None
+        qb = np.ascontiguousarray(qbuf, dtype=np.uint8)
+        tb = np.ascontiguousarray(tbuf, dtype=np.uint8)
+        qo = np.ascontiguousarray(qoff, dtype=np.int64)
+        to = np.ascontiguousarray(toff, dtype=np.int64)
+        self.lib.gasal_gpu_batch(thread_id, n, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data, to.ctypes.data,
+                                 out5.ctypes.data, cig.ctypes.data if cig is not None else None, cigar_stride)
+        texts = None
+        if cig is not None:
+            raw = cig.reshape(n, cigar_stride)
+            texts = [bytes(r).split(b"\0", 1)[0].decode() for r in raw]
+        return out5, texts
+
+
+def reference_gpu() -> Optional[GasalGpuReference]:
+    if "gasal_gpu" not in _cache:
+        p = os.path.join(_HERE, "_ref", "libgasal_gpu.so")
+        _cache["gasal_gpu"] = GasalGpuReference(p) if os.path.exists(p) else None
+    return _cache["gasal_gpu"]
