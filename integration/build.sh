@@ -10,6 +10,7 @@
 #                         kernels compiled for the host = golden-SAM generator (CPU only, test infrastructure)
 #   rabbitsalign_b200_alninfo  the product drop-in plus the optional caller-loop edit (patch_caller.py): gasal_fail +
 #                         Aligner::align_gpu come from the device (finish_kernel); needs a GPU
+#   rabbitsalign_gasalgpu the reference as shipped: its own solve_ssw_on_gpu + GASAL2 for sm_100a (comparator, needs a GPU)
 #   rabbitsalign_cpussw   solve_ssw_on_gpu returns failed records -> every extension takes the reference's
 #                         CPU SSW path (Aligner::align): the end-to-end CPU baseline (test/bench infrastructure)
 #
@@ -57,6 +58,12 @@ $CXX -o "$OUT/rabbitsalign_b200" $OBJS "$OUT/obj/veneer.o" -L"$ROOT/rabbitsalign
 $CXX $FLAGS -c "$HERE/solve_gasalref.cpp" -o "$OUT/obj/solve_gasalref.o"
 $CXX -o "$OUT/rabbitsalign_gasalref" $OBJS "$OUT/obj/solve_gasalref.o" "$ROOT/oracle/_ref/libgasal_ref512.so" \
      -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+# 2b) the reference AS SHIPPED, on this GPU: its own solve_ssw_on_gpu + GASAL2 compiled for sm_100a
+#     (oracle/_ref/libgasal_gpu.so, oracle/Makefile): the end-to-end GPU comparator (needs a GPU)
+if [ -f "$ROOT/oracle/_ref/libgasal_gpu.so" ]; then
+  $CXX -o "$OUT/rabbitsalign_gasalgpu" $OBJS "$ROOT/oracle/_ref/libgasal_gpu.so" \
+       -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+fi
 # 3) CPU-SSW path
 $CXX $FLAGS -c "$HERE/solve_cpussw.cpp" -o "$OUT/obj/solve_cpussw.o"
 $CXX -o "$OUT/rabbitsalign_cpussw" $OBJS "$OUT/obj/solve_cpussw.o" -lz -lpthread

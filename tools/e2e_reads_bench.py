@@ -71,7 +71,7 @@ def main():
                 for _ in range(4 * k):
                     g.write(f.readline())
             sub_files[k] = path
-        for name in ("rabbitsalign_cpussw", "rabbitsalign_b200", "rabbitsalign_b200_alninfo"):
+        for name in ("rabbitsalign_cpussw", "rabbitsalign_gasalgpu", "rabbitsalign_b200", "rabbitsalign_b200_alninfo"):
             exe = os.path.join(B, name)
             if not os.path.exists(exe):
                 out[name] = "not built"
