@@ -58,7 +58,13 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (arrival time, csv line)
+        self.t_begin = None
+
+    def mark_begin(self):
+        """Start of the timed region: only samples arriving after this count (nvidia-smi is started earlier, during
+        warm-up, because its own start-up can exceed a short timed region, especially with 8 ranks on a box)."""
+        self.t_begin = time.time()
 
     def start(self):
         try:
@@ -71,7 +77,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -83,7 +89,10 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if self.t_begin is None or t >= self.t_begin]
+        if not inside and self.lines:  # region shorter than the sampling period: the sample closest to it
+            inside = [self.lines[-1][1]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -241,6 +250,8 @@ def main():
     batch = make_batch(args.pairs, args.read_len, seed=sharding.rank_seed(43, rank))
     scratch_gb = int(os.environ.get("RSA_EXT_SCRATCH_GB", "0"))  # tuning knob (experiments)
     eng = ExtensionEngine(device=local_rank, scratch_bytes=scratch_gb << 30)
+    sampler = ClockSampler(local_rank)  # started now: nvidia-smi needs up to a second before its first sample
+    sampler.start()
 
     # pinned host copies (the C ABI copies straight from/to pinned memory)
     def pinned(a):
@@ -262,9 +273,8 @@ def main():
     for _ in range(max(3, args.warmup)):
         eng.run_resident()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)

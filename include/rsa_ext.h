@@ -66,7 +66,9 @@ typedef struct {
  * END-TO-START order.  n_ops > RSA_EXT_RLE_INLINE: the full byte string is fetched with
  * rsa_ext_rle_overflow().  status: 0 ok; 1 window longer than max_target_len (not aligned; the caller never consumes
  * those, src/aligner.cpp:18-24); 3 empty query or window (the reference reads an unwritten tile there).  All other
- * records are bit-exact with the reference, including the ones its gasal_fail gate rejects. */
+ * records are bit-exact with the reference, including the ones its gasal_fail gate rejects.  (4 and 5 never reach the
+ * caller: 4 = re-run internally by rsa_ext_wait; 5 = no kernel produced the pair, rsa_ext_wait returns
+ * RSA_EXT_ERR_CUDA instead of handing such records back.) */
 typedef struct {
     int32_t score;
     int32_t query_start;

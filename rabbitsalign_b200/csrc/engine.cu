@@ -116,6 +116,8 @@ struct PlannedChunk {
     int rc = 0;
 };
 constexpr int kPlanRing = kSlots + 2;
+constexpr int kSlotCounters = 4;  // per-slot device counters: arena bytes, pairs the redo pass could not place, pairs redone,
+                                  // pairs NO kernel produced (a lost launch: reported as an error)
 constexpr int64_t kPlanAheadMinPairs = 32768;  // below this the caller's thread plans inline (no thread hop)
 struct PlanAhead {
     std::thread th;
@@ -518,7 +520,7 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
                     const ChunkPlan& p, cudaEvent_t* ev) {
     CU_TRY(h, cudaMemsetAsync(d.ends, 0, sizeof(DpEnd) * p.n, st));
     CU_TRY(h, cudaMemsetAsync(const_cast<uint8_t*>(d.blob) + p.off_redo, 0, sizeof(RedoHeader), st));
-    CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, 3 * sizeof(unsigned long long), st));
+    CU_TRY(h, cudaMemsetAsync(d.arena_used, 0, kSlotCounters * sizeof(unsigned long long), st));
     if (ev) CU_TRY(h, cudaEventRecord(ev[0], st));
     const PairMeta* meta = reinterpret_cast<const PairMeta*>(d.blob + p.off_meta);
     const uint32_t* info = reinterpret_cast<const uint32_t*>(d.blob + p.off_info);
@@ -705,7 +707,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
         CU_TRY(h, cudaMemcpyAsync(h->alninfo + p.lo, s.d_aln.p, sizeof(rsa_ext_alninfo_t) * p.n, cudaMemcpyDeviceToHost, h->s_d2h));
         h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_alninfo_t) * p.n;
     }
-    CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(h, cudaMemcpyAsync(s.h_arena_used, s.d_arena_used, kSlotCounters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(h, cudaEventRecord(s.ev_d2h, h->s_d2h));
     h->stats.d2h_bytes += (int64_t)sizeof(rsa_ext_result_t) * p.n + 8;
     lap("d2h enqueue");
@@ -740,6 +742,13 @@ int retire_chunk(rsa_ext* h, Slot& s) {
         }
     }
     h->stats.pairs_redo += (int64_t)s.h_arena_used[2];
+    if (s.h_arena_used[3] > 0) {  // never silently hand back records no kernel computed
+        h->err = std::to_string(s.h_arena_used[3]) + " pairs of a chunk were not processed by any kernel (lost kernel launch)";
+        s.busy = false;
+        h->inflight--;
+        if (h->plan_ahead) { std::lock_guard<std::mutex> lk(h->pa->m); h->pa->released++; h->pa->cv.notify_all(); }
+        return RSA_EXT_ERR_CUDA;
+    }
     if (s.h_arena_used[1] > 0)
         for (int64_t i = s.plan.lo; i < s.plan.hi; ++i)
             if (h->results[i].status == 4) h->retry.push_back(i);
@@ -891,8 +900,8 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
-        if ((e = cudaHostAlloc(&s.h_arena_used, 3 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
-        if ((e = cudaMalloc(&s.d_arena_used, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+        if ((e = cudaHostAlloc(&s.h_arena_used, kSlotCounters * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
+        if ((e = cudaMalloc(&s.d_arena_used, kSlotCounters * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     }
     lap("events + counters");
     // (cudaGetDeviceProperties costs ~10 ms per call; one attribute is all the engine needs)
@@ -1278,6 +1287,14 @@ extern "C" int rsa_ext_fetch_resident(rsa_ext_t* h, rsa_ext_result_t* results) {
     CU_TRY(h, cudaStreamSynchronize(h->s_comp2));
     CU_TRY(h, cudaStreamSynchronize(h->s_tb));
     CU_TRY(h, cudaMemcpy(results, h->r_res.p, sizeof(rsa_ext_result_t) * (size_t)h->r_n, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < (int)std::min<size_t>(h->res_chunks.size(), kSlots); ++k) {  // counters of each slot's last chunk
+        unsigned long long c[kSlotCounters] = {};
+        CU_TRY(h, cudaMemcpy(c, h->slots[k].d_arena_used, sizeof c, cudaMemcpyDeviceToHost));
+        if (c[3] > 0) {
+            h->err = std::to_string(c[3]) + " pairs of a chunk were not processed by any kernel (lost kernel launch)";
+            return RSA_EXT_ERR_CUDA;
+        }
+    }
     return RSA_EXT_OK;
 }
 

@@ -26,6 +26,7 @@
 //     from those; otherwise the pair is flagged and the exact kernel recomputes the end cell (score-only).
 //   * symbols outside {A,C,G,T,N}: the pair is flagged and fully redone by the exact kernel.
 #pragma once
+#include <mutex>
 #include "common.cuh"
 #include "fast_cell.cuh"
 #include "fast_layout.cuh"
@@ -503,8 +504,23 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
     const int groups_per_block = WPB * fast_groups_per_warp(L);
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
     const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4;
-    if (smem > 48 * 1024)  // long windows: opt in to more dynamic shared memory (per device, cheap to repeat)
-        cudaFuncSetAttribute(fast_dp_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        // Long windows / wide lanes need the opt-in shared-memory limit.  The attribute belongs to the FUNCTION (per
+        // device), not to the launch: setting it to this launch's size raced with other workers launching the same
+        // instantiation with a larger size (their launch then failed and the chunk's pairs came back untouched).
+        // Raise it once per device to the device maximum instead; occupancy depends on the launch's own size only.
+        static std::mutex mu;
+        static bool done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev >= 0 && dev < 64 && !done[dev]) {
+            int optin = 0;
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            cudaFuncSetAttribute(fast_dp_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+            done[dev] = true;
+        }
+    }
     fast_dp_kernel<L, C><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
                                                                      redo, redo_list, k, rows_pad, tba);
 }

@@ -157,6 +157,10 @@ __global__ void __launch_bounds__(kTbThreads) tb_kernel(TbArgs a, int n, const D
         for (int k = 0; k < RSA_EXT_RLE_INLINE; ++k) r.rle[k] = 0;
         r.score = 0; r.query_start = -1; r.query_end = -1; r.ref_start = -1; r.ref_end = -1;
         r.n_ops = 0; r.status = (e.flags & DPF_NO_SCRATCH) ? (int16_t)4 : (int16_t)(a.info[pi] >> 16);
+        if (r.status == 0) {  // the host routed this pair to a kernel and no kernel wrote its DpEnd: a launch was lost
+            r.status = 5;
+            atomicAdd(a.arena_used + 3, 1ull);
+        }
         a.res[pi] = r;
         return;
     }

@@ -39,13 +39,19 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--paired", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="unused (STREAM_BATCH_SIZE is a compile-time macro of the veneer)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--sub", type=float, default=0.01)
+    ap.add_argument("--indel", type=float, default=0.003)
+    ap.add_argument("--max-indel", type=int, default=3)
     ap.add_argument("--subsets", default="", help="comma-separated read counts to also run (prefixes of the read file)")
     a = ap.parse_args()
-    out = {"ref_len": a.ref_len, "reads": a.reads * (2 if a.paired else 1), "paired": a.paired, "threads": a.threads}
+    out = {"ref_len": a.ref_len, "reads": a.reads * (2 if a.paired else 1), "paired": a.paired, "threads": a.threads,
+           "read_len": a.read_len, "sub": a.sub, "indel": a.indel, "max_indel": a.max_indel}
     with tempfile.TemporaryDirectory() as d:
         t0 = time.time()
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_reads.py"), d, "--ref-len", str(a.ref_len),
-                               "--contigs", str(a.contigs), "--reads", str(a.reads), "--seed", "77"] + (["--paired"] if a.paired else []))
+                               "--contigs", str(a.contigs), "--reads", str(a.reads), "--seed", "77", "--read-len", str(a.read_len),
+                               "--sub", str(a.sub), "--indel", str(a.indel), "--max-indel", str(a.max_indel)] + (["--paired"] if a.paired else []))
         out["gen_s"] = round(time.time() - t0, 1)
         files = [os.path.join(d, "ref.fa"), os.path.join(d, "reads_1.fq")] + ([os.path.join(d, "reads_2.fq")] if a.paired else [])
         def run(exe, fq_files, tag):
