@@ -287,3 +287,50 @@ def test_query_too_long_inside_a_large_batch(engine):
         engine.align_packed(bb.qbuf, bb.qoff, bb.tbuf, bb.toff)
     assert ei.value.status == -3
     assert engine.solve_ssw_on_gpu([b"ACGT"], [b"ACGT"])[0].score == 8
+
+
+def test_concurrent_workers_wide_classes_are_deterministic():
+    """16 handles on 16 threads, 512-pair slices of 250-bp variable-length indel-rich pairs (column classes whose
+    shared memory exceeds 48 KB, several classes per call): every record equals the single-handle baseline.
+    Regression test for the per-launch cudaFuncSetAttribute race (a lost launch handed back failed-looking records)."""
+    import threading
+    from rabbitsalign_b200 import ExtensionEngine
+    b = W.extension_pairs(48_000, seed=910, read_len=250, indel_rate=0.02, max_indel=4, sub_rate=0.02, fixed_query_len=False)
+    e0 = ExtensionEngine()
+    base = e0.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    e0.close()
+    assert (base["status"] == 0).all()
+    slices = [(lo, min(b.n, lo + 512)) for lo in range(0, b.n, 512)]
+    parts = [b.slice(lo, hi) for lo, hi in slices]
+    T = 16
+    engines = [ExtensionEngine() for _ in range(T)]
+    bad, errors, lock = [], [], threading.Lock()
+    fields = ["score", "query_start", "query_end", "ref_start", "ref_end", "n_ops", "status"]
+
+    def worker(w, order):
+        for k in order:
+            p = parts[k]
+            try:
+                r = engines[w].align_packed(p.qbuf, p.qoff, p.tbuf, p.toff)
+            except Exception as ex:  # noqa: BLE001
+                with lock:
+                    errors.append(str(ex))
+                return
+            lo, hi = slices[k]
+            diff = np.zeros(hi - lo, bool)
+            for f in fields:
+                diff |= r[f] != base[f][lo:hi]
+            if diff.any():
+                with lock:
+                    bad.extend((lo + np.nonzero(diff)[0]).tolist())
+
+    rng = np.random.default_rng(7)
+    for _ in range(3):
+        perm = rng.permutation(len(parts))
+        th = [threading.Thread(target=worker, args=(w, perm[w::T])) for w in range(T)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    for e in engines:
+        e.close()
+    assert not errors, errors[:3]
+    assert not bad, f"{len(bad)} records differ from the baseline, e.g. pairs {bad[:5]}"
