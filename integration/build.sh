@@ -93,6 +93,10 @@ $CXX -o "$OUT/rabbitsalign_fx_b200" $FXOBJS $FXIO "$OUT/obj/veneer.o" -L"$ROOT/r
 $CXX -o "$OUT/rabbitsalign_fx_gasalref" $FXOBJS $FXIO "$OUT/obj/solve_gasalref.o" "$ROOT/oracle/_ref/libgasal_ref512.so" \
      -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
 $CXX -o "$OUT/rabbitsalign_fx_cpussw" $FXOBJS $FXIO "$OUT/obj/solve_cpussw.o" -lz -lpthread
+if [ -f "$ROOT/oracle/_ref/libgasal_gpu.so" ]; then
+  $CXX -o "$OUT/rabbitsalign_fx_gasalgpu" $FXOBJS $FXIO "$ROOT/oracle/_ref/libgasal_gpu.so" \
+       -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+fi
 
 # ---- optional build: AlignmentInfo straight from the device.  The caller loops of src/pc.cpp get
 #      the two-call substitution of integration/patch_caller.py on a copy under _build/alninfo/; every unit that
