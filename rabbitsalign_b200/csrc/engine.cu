@@ -7,11 +7,13 @@
 //
 // Shape of the engine (B200-first, not GASAL2's):
 //   * a batch of any size is cut into chunks whose direction-bit scratch fits the handle's budget;
-//   * three chunk slots rotate over four streams (H2D, DP, traceback, D2H) so the copies of chunk k+1 overlap
-//     the kernels of chunk k; per chunk there is ONE metadata blob copy, two sequence copies
-//     in and one 64-byte-record copy out (the reference issues ~13 small copies per 512 pairs);
-//   * the host plans each chunk (length classes, equal-length pairing for the packed kernel, scratch
-//     offsets) while the GPU works on the previous one;
+//   * three chunk slots rotate over five streams (H2D, two DP streams used alternately, a high-priority traceback
+//     stream, D2H) so the copies of chunk k+1 overlap the kernels of chunk k and the traceback of chunk k runs beside
+//     the DP kernel of chunk k+1; per chunk there is ONE metadata blob copy, two sequence copies in and one
+//     64-byte-record copy out (the reference issues ~13 small copies per 512 pairs);
+//   * the host plans each chunk (length classes, equal-length pairing for the packed kernel, scratch offsets) while
+//     the GPU works on the previous ones -- for large batches on a per-handle helper thread that runs ahead of the
+//     caller's thread (PlanAhead), for small ones inline;
 //   * kernels: packed s16x2 DPX wavefront kernel (kernels_fast.cuh) for the bulk, exact int32 wavefront
 //     kernel (kernels_exact.cuh) for whatever the packed kernel declines, one traceback kernel
 //     (kernels_tb.cuh).  No CPU fallback exists here.
