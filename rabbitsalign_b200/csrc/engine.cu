@@ -893,7 +893,8 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         // retires, so the records of chunk k are not held back by the DP kernel of chunk k+1
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if ((e = cudaStreamCreateWithPriority(&h->s_tb, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("stream", e);
+        const char* pe = getenv("RSA_EXT_TB_PRIO");  // experiment knob: 0 = same priority as the DP streams
+        if ((e = cudaStreamCreateWithPriority(&h->s_tb, cudaStreamNonBlocking, (pe && atoi(pe) == 0) ? prio_lo : prio_hi)) != cudaSuccess) return fail("stream", e);
     }
     if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     lap("6 streams");
