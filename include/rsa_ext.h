@@ -107,6 +107,18 @@ int rsa_ext_poll(rsa_ext_t *h);
  * (given to submit) is filled. */
 int rsa_ext_wait(rsa_ext_t *h);
 
+/* ---- SURVEY 8(f) "next" row 1, first half: windows named by offset and length in a resident reference ------------
+ *
+ * The reference builds each window as a std::string (references.sequences[id].substr(...), src/pc.cpp:214-242) and
+ * GASAL copies it to the GPU.  rsa_ext_set_reference uploads the (concatenated) reference once -- at most 2^32-1
+ * bytes; `seq` must stay valid while windows are submitted (it is read again only when a pair is re-run exact-only).
+ * rsa_ext_submit_ref_windows then takes targets as win_off[i], win_len[i] into that buffer; queries as in
+ * rsa_ext_submit.  Results, rsa_ext_wait/poll and every status are exactly those of rsa_ext_submit on the same
+ * bytes (tests/test_gpu_parity.py::test_reference_windows_equal_explicit_windows). */
+int rsa_ext_set_reference(rsa_ext_t *h, const char *seq, int64_t len);
+int rsa_ext_submit_ref_windows(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff,
+                               const int64_t *win_off, const int32_t *win_len, rsa_ext_result_t *results);
+
 /* Pre-allocate what batches of up to n pairs of (qlen x tlen) need (device buffers of the first chunk slot, pinned
  * staging), so the first real batches allocate nothing.  Optional; the reference allocates its GASAL storage for
  * STREAM_BATCH_SIZE x MAX lengths up front (gasal_init_streams, src/gasal2_ssw.cpp:92-102). */

@@ -164,6 +164,11 @@ struct rsa_ext {
     const int64_t* qoff = nullptr;
     const int64_t* toff = nullptr;
     rsa_ext_result_t* results = nullptr;
+    const int64_t* win_off = nullptr;      // pending batch in window form (targets inside the resident reference)
+    const int32_t* win_len = nullptr;
+    DevBuf d_ref;                          // resident reference (rsa_ext_set_reference)
+    const char* ref_host = nullptr;
+    int64_t ref_len = 0;
     rsa_ext_alninfo_t* alninfo = nullptr;  // optional second output of the pending batch
     rsa_ext_alninfo_t* alninfo_next = nullptr;
     int end_bonus = 10;
@@ -275,6 +280,12 @@ struct PlanInput {
     bool exact_only;
     int64_t max_pairs = kMaxChunkPairsDefault;  // cap for this chunk (the first chunks of a batch ramp up)
     int match = 2;
+    // window form (rsa_ext_submit_ref_windows): target i = [win_off[i], win_off[i] + win_len[i]) of the resident
+    // reference; `toff`/`tbuf` are unused then and no window bytes travel
+    const int64_t* win_off = nullptr;
+    const int32_t* win_len = nullptr;
+    int64_t t_start(int64_t i) const { return win_off ? win_off[i] : toff[i]; }
+    int64_t t_len(int64_t i) const { return win_off ? (int64_t)win_len[i] : toff[i + 1] - toff[i]; }
 };
 
 // A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
@@ -321,10 +332,10 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     //    Scratch is budgeted with the larger of the two layouts' needs so any routing fits.
     int64_t hi = lo;
     uint64_t scratch = 0;
-    const int64_t q0 = in.qoff[lo], t0 = in.toff[lo];
+    const int64_t q0 = in.qoff[lo], t0 = in.win_off ? 0 : in.toff[lo];
     const int64_t hi_cap = std::min<int64_t>(in.n, lo + std::min<int64_t>(kMaxChunkPairs, in.max_pairs));
     while (hi < hi_cap) {
-        const int64_t ql = in.qoff[hi + 1] - in.qoff[hi], tl = in.toff[hi + 1] - in.toff[hi];
+        const int64_t ql = in.qoff[hi + 1] - in.qoff[hi], tl = in.t_len(hi);
         if (ql < 0 || tl < 0) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
         if (ql > in.max_qlen) {
             h->err = "read size is too big, " + std::to_string(ql) + " > " + std::to_string(in.max_qlen);
@@ -337,7 +348,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
                 need = std::max<uint64_t>(need, (uint64_t)((tl + 3) & ~3) * LT.fast_row_bytes[ql]);
         }
         if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
-                        in.toff[hi + 1] - t0 > kMaxChunkSeqBytes))
+                        (!in.win_off && in.toff[hi + 1] - t0 > kMaxChunkSeqBytes)))
             break;
         scratch += need;
         ++hi;
@@ -346,7 +357,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     plan = ChunkPlan();
     plan.lo = lo; plan.hi = hi; plan.n = n;
     plan.q_bytes = in.qoff[hi] - q0;
-    plan.t_bytes = in.toff[hi] - t0;
+    plan.t_bytes = in.win_off ? 0 : in.toff[hi] - t0;
 
     // 2) blob layout
     const size_t off = blob_layout(plan, n);
@@ -375,8 +386,8 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
     int64_t cells = 0;
     uint32_t qmin = 0xFFFFFFFFu, qmax = 0;
     for (int64_t i = 0; i < n; ++i) {
-        const int64_t qo = in.qoff[lo + i], to = in.toff[lo + i];
-        const int64_t ql = in.qoff[lo + i + 1] - qo, tl = in.toff[lo + i + 1] - to;
+        const int64_t qo = in.qoff[lo + i], to = in.t_start(lo + i);
+        const int64_t ql = in.qoff[lo + i + 1] - qo, tl = in.t_len(lo + i);
         meta[i].qoff = (uint32_t)(qo - q0);
         meta[i].toff = (uint32_t)(to - t0);
         meta[i].qlen = (uint16_t)ql;
@@ -584,6 +595,8 @@ PlanInput pending_plan_input(const rsa_ext* h) {
     PlanInput in{h->n, h->qoff, h->toff, h->qbuf, h->tbuf, h->cfg.max_query_len, h->cfg.max_target_len,
                  h->scratch_per_slot, (h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok};
     in.match = h->sc.match;
+    in.win_off = h->win_off;
+    in.win_len = h->win_len;
     return in;
 }
 
@@ -680,7 +693,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
 
     CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, h_blob, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.q_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_q.p, h->qbuf + h->qoff[p.lo], (size_t)p.q_bytes, cudaMemcpyHostToDevice, h->s_h2d));
-    if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));  // (0 in window form)
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
     h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
     lap("h2d enqueue");
@@ -688,14 +701,15 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
     cudaStream_t s_dp = (!serial && (h->dp_toggle++ & 1)) ? h->s_comp2 : h->s_comp;
     CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_h2d, 0));
-    ChunkDev d{s.d_blob.p, s.d_q.p, s.d_t.p, reinterpret_cast<DpEnd*>(s.d_ends.p),
+    const uint8_t* d_targets = h->win_off ? h->d_ref.p : s.d_t.p;  // window form: meta.toff indexes the resident reference
+    ChunkDev d{s.d_blob.p, s.d_q.p, d_targets, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
     cudaStream_t s_trace = serial ? s_dp : h->s_tb;
     if ((rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, p, nullptr))) return rc;
     if (h->alninfo) {
         finish_kernel<<<(unsigned)((p.n + kFinishThreads - 1) / kFinishThreads), kFinishThreads, 0, s_trace>>>(
-            s.d_q.p, s.d_t.p, reinterpret_cast<const PairMeta*>(s.d_blob.p + p.off_meta),
+            s.d_q.p, d_targets, reinterpret_cast<const PairMeta*>(s.d_blob.p + p.off_meta),
             reinterpret_cast<const rsa_ext_result_t*>(s.d_res.p), (int)p.n, h->sc, h->end_bonus,
             reinterpret_cast<rsa_ext_alninfo_t*>(s.d_aln.p));
         h->stats.kernel_launches++;
@@ -764,11 +778,22 @@ int retire_chunk(rsa_ext* h, Slot& s) {
     return RSA_EXT_OK;
 }
 
-int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
-                rsa_ext_result_t* results) {
+// Targets either as a concatenated buffer with prefix offsets (tbuf/toff) or, window form, as (win_off, win_len)
+// into the resident reference.
+int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
+                   const int64_t* win_off, const int32_t* win_len, rsa_ext_result_t* results) {
     if (!h) return RSA_EXT_ERR_ARG;
     if (h->pending) { h->err = "a batch is already pending"; return RSA_EXT_ERR_STATE; }
-    if (n <= 0 || !qbuf || !qoff || !tbuf || !toff || !results) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    const bool windows = win_off != nullptr;
+    if (n <= 0 || !qbuf || !qoff || !results || (windows ? !win_len : (!tbuf || !toff))) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    if (windows) {
+        if (!h->d_ref.p) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
+        for (int64_t i = 0; i < n; ++i)
+            if (win_len[i] < 0 || win_off[i] < 0 || win_off[i] + win_len[i] > h->ref_len) {
+                h->err = "window " + std::to_string(i) + " lies outside the resident reference";
+                return RSA_EXT_ERR_ARG;
+            }
+    }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     // the reference validates the whole slice before touching the GPU (gasal2_ssw.cpp:74-89)
     for (int64_t i = 0; i < n; ++i) {
@@ -777,7 +802,7 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
             h->err = "gasal2 : read size is too big, " + std::to_string(ql) + " > " + std::to_string(h->cfg.max_query_len);
             return RSA_EXT_ERR_QUERY_LEN;
         }
-        if (ql < 0 || toff[i + 1] < toff[i]) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
+        if (ql < 0 || (!windows && toff[i + 1] < toff[i])) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
     }
     if (h->resident_inflight) {  // an asynchronous resident run may still use the slots' scratch
         CU_TRY(h, cudaStreamSynchronize(h->s_comp));
@@ -785,6 +810,7 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
         h->resident_inflight = false;
     }
     h->n = n; h->qbuf = qbuf; h->qoff = qoff; h->tbuf = tbuf; h->toff = toff; h->results = results;
+    h->win_off = win_off; h->win_len = win_len;
     h->alninfo = h->alninfo_next;
     h->next_pair = 0; h->head = 0; h->tail = 0; h->inflight = 0; h->chunks_enqueued = 0;
     h->overflow.clear();
@@ -818,6 +844,11 @@ int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, co
     }
     h->warmed = true;
     return RSA_EXT_OK;
+}
+
+int submit_core(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
+                rsa_ext_result_t* results) {
+    return submit_core_ex(h, n, qbuf, qoff, tbuf, toff, nullptr, nullptr, results);
 }
 
 }  // namespace
@@ -946,7 +977,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
         if (s.ev_mid) cudaEventDestroy(s.ev_mid);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
-    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
+    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs, &h->d_ref})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
     if (h->own_q.p) cudaFreeHost(h->own_q.p);
@@ -990,6 +1021,30 @@ extern "C" int rsa_ext_submit_ptrs(rsa_ext_t* h, int64_t n, const char* const* q
     }
     return submit_core(h, n, reinterpret_cast<const char*>(h->own_q.p), h->own_qoff.data(),
                        reinterpret_cast<const char*>(h->own_t.p), h->own_toff.data(), results);
+}
+
+// ---- SURVEY 8(f) rank 1, first half: windows by (offset, length) into a reference that lives in HBM -------------
+//
+// The reference builds every window as a std::string (references.sequences[ref_id].substr(...), src/pc.cpp:214-242)
+// and the veneer copies those bytes to the GPU again.  With the reference sequence resident, a batch names its windows
+// by offset and length: no window bytes are built, gathered or copied (250 of the 450 bytes per pair of a 150 bp batch).
+extern "C" int rsa_ext_set_reference(rsa_ext_t* h, const char* seq, int64_t len) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    if (!seq || len <= 0 || len > (int64_t)0xFFFFFFFFll) { h->err = "reference must be 1..2^32-1 bytes"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    std::lock_guard<std::mutex> cold(g_cold_mutex);
+    int rc = ensure_dev(h, h->d_ref, (size_t)len + 16);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpy(h->d_ref.p, seq, (size_t)len, cudaMemcpyHostToDevice));
+    h->ref_host = seq;  // kept for the rare exact-only re-submission (status 4); the caller keeps it alive
+    h->ref_len = len;
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_submit_ref_windows(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
+                                          const int64_t* win_off, const int32_t* win_len, rsa_ext_result_t* results) {
+    return submit_core_ex(h, n, qbuf, qoff, nullptr, nullptr, win_off, win_len, results);
 }
 
 // Allocate, now, what a batch of n pairs of (qlen x tlen) needs from slot 0 and the submit_ptrs staging, so that the
@@ -1046,7 +1101,8 @@ static int run_retry(rsa_ext* h) {
     std::vector<int32_t> ql(m), tl(m);
     for (int64_t k = 0; k < m; ++k) {
         qp[k] = h->qbuf + h->qoff[idx[k]]; ql[k] = (int32_t)(h->qoff[idx[k] + 1] - h->qoff[idx[k]]);
-        tp[k] = h->tbuf + h->toff[idx[k]]; tl[k] = (int32_t)(h->toff[idx[k] + 1] - h->toff[idx[k]]);
+        if (h->win_off) { tp[k] = h->ref_host + h->win_off[idx[k]]; tl[k] = h->win_len[idx[k]]; }
+        else { tp[k] = h->tbuf + h->toff[idx[k]]; tl[k] = (int32_t)(h->toff[idx[k] + 1] - h->toff[idx[k]]); }
     }
     std::vector<rsa_ext_result_t> tmp(m);
     rsa_ext_result_t* results = h->results;

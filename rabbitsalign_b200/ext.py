@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
-    "rsa_ext_reserve",
+    "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows",
 ]
 
 _lib = None
@@ -115,6 +115,10 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_plan_debug.restype = C.c_int
     lib.rsa_ext_reserve.argtypes = [vp, i64, i32, i32]
     lib.rsa_ext_reserve.restype = C.c_int
+    lib.rsa_ext_set_reference.argtypes = [vp, vp, i64]
+    lib.rsa_ext_set_reference.restype = C.c_int
+    lib.rsa_ext_submit_ref_windows.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.rsa_ext_submit_ref_windows.restype = C.c_int
     _lib = lib
     return lib
 
@@ -203,6 +207,24 @@ class ExtensionEngine:
         """Also produce `AlignmentInfo` records (ALNINFO_DTYPE) on the device for the following submits."""
         self._aln_keep = out
         self._check(self.lib.rsa_ext_request_alninfo(self.h, out.ctypes.data if out is not None else None, end_bonus))
+
+    def set_reference(self, seq: np.ndarray):
+        """Upload the (concatenated) reference once; windows are then named by offset and length."""
+        assert seq.dtype == np.uint8
+        self._ref_keep = np.ascontiguousarray(seq)
+        self._check(self.lib.rsa_ext_set_reference(self.h, self._ref_keep.ctypes.data, len(self._ref_keep)))
+
+    def align_ref_windows(self, qbuf, qoff, win_off, win_len) -> np.ndarray:
+        """Blocking: queries against windows [win_off[i], win_off[i]+win_len[i]) of the resident reference."""
+        n = len(qoff) - 1
+        results = np.zeros(n, dtype=RESULT_DTYPE)
+        wo = np.ascontiguousarray(win_off, dtype=np.int64)
+        wl = np.ascontiguousarray(win_len, dtype=np.int32)
+        self._keep = (qbuf, qoff, wo, wl, results)
+        self._check(self.lib.rsa_ext_submit_ref_windows(self.h, n, qbuf.ctypes.data, qoff.ctypes.data, wo.ctypes.data,
+                                                        wl.ctypes.data, results.ctypes.data))
+        self.wait()
+        return results
 
     def reserve(self, n: int, qlen: int, tlen: int):
         """Pre-allocate for batches of up to n pairs of (qlen x tlen)."""

@@ -334,3 +334,44 @@ def test_concurrent_workers_wide_classes_are_deterministic():
         e.close()
     assert not errors, errors[:3]
     assert not bad, f"{len(bad)} records differ from the baseline, e.g. pairs {bad[:5]}"
+
+
+def test_reference_windows_equal_explicit_windows(engine, oracle_lib):
+    """Windows named by (offset, length) in a resident reference give the records of the same windows sent as bytes
+    (no window strings are built or copied); a sample is checked against the oracle too.
+    60 000 pairs: the plan-ahead path; IUPAC symbols in the reference exercise the redo pass through the window form."""
+    rng = np.random.default_rng(77)
+    ref = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=3_000_000)
+    ref[rng.integers(0, len(ref), size=300)] = ord("N")
+    ref[rng.integers(0, len(ref), size=100)] = ord("R")
+    n = 60_000
+    win_len = rng.integers(150, 420, size=n).astype(np.int32)
+    win_off = rng.integers(0, len(ref) - 500, size=n).astype(np.int64)
+    qs, ts = [], []
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    for i in range(n):
+        w = ref[win_off[i]:win_off[i] + win_len[i]]
+        lo = int(rng.integers(0, max(1, len(w) - 150)))
+        q = w[lo:lo + 150].copy()
+        mut = rng.random(len(q)) < 0.02
+        q[mut] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(mut.sum()))
+        if i % 7 == 0 and len(q) > 40:  # a deletion in the read
+            q = np.concatenate([q[:30], q[33:]])
+        qs.append(q.tobytes())
+        ts.append(w.tobytes())
+    b = W.from_lists(qs, ts)
+    explicit = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    engine.set_reference(ref)
+    byref = engine.align_ref_windows(b.qbuf, b.qoff, win_off, win_len)
+    for f in ["score", "query_start", "query_end", "ref_start", "ref_end", "n_ops", "status"]:
+        assert (explicit[f] == byref[f]).all(), f
+    short = explicit["n_ops"] <= 40
+    assert (explicit["rle"][short] == byref["rle"][short]).all()
+    sub = b.slice(0, 3000)
+    bad = compare(engine, byref[:3000], oracle_arrays(oracle_lib, sub), sub)
+    assert not bad, "\n".join(bad)
+    # a window outside the reference is an argument error, and the handle stays usable
+    from rabbitsalign_b200 import ExtensionError
+    with pytest.raises(ExtensionError):
+        engine.align_ref_windows(b.qbuf[:b.qoff[1]], b.qoff[:2], np.array([len(ref) - 10]), np.array([100]))
+    assert engine.solve_ssw_on_gpu([b"ACGT"], [b"ACGT"])[0].score == 8
