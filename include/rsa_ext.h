@@ -63,8 +63,8 @@ typedef struct {
 /* One result per pair: the integer fields of `struct gasal_tmp_res` (src/gasal2_ssw.h:31-38; starts and
  * ends 0-based inclusive, starts may be -1) plus the traceback's run-length bytes exactly as
  * GASAL2/src/kernels/get_tb.h:87-117 emits them: (count<<2)|op, count <= 63, op 0=M 1=X 2=D 3=I, in
- * END-TO-START order.  n_ops > RSA_EXT_RLE_INLINE: the full byte string is fetched with
- * rsa_ext_rle_overflow().  status: 0 ok; 1 window longer than max_target_len (not aligned; the caller never consumes
+ * END-TO-START order.  n_ops > RSA_EXT_RLE_INLINE: rle[] holds the first RSA_EXT_RLE_INLINE bytes and the full byte
+ * string is fetched with rsa_ext_rle_overflow() (records are byte-deterministic: no internal offsets inside).  status: 0 ok; 1 window longer than max_target_len (not aligned; the caller never consumes
  * those, src/aligner.cpp:18-24); 3 empty query or window (the reference reads an unwritten tile there).  All other
  * records are bit-exact with the reference, including the ones its gasal_fail gate rejects.  (4 and 5 never reach the
  * caller: 4 = re-run internally by rsa_ext_wait; 5 = no kernel produced the pair, rsa_ext_wait returns
@@ -100,7 +100,10 @@ int rsa_ext_submit(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qof
 int rsa_ext_submit_ptrs(rsa_ext_t *h, int64_t n, const char *const *q, const int32_t *qlen,
                         const char *const *t, const int32_t *tlen, rsa_ext_result_t *results);
 
-/* gasal_is_aln_async_done (GASAL2/src/gasal_align.cu:310-326): 0 = finished, 1 = still running. */
+/* gasal_is_aln_async_done (GASAL2/src/gasal_align.cu:310-326): 0 = finished, 1 = still running.  Usable in the
+ * reference's `while (poll) usleep(100)` loop (src/gasal2_ssw.cpp:179): poll itself retires finished chunks and
+ * enqueues the next ones of a multi-chunk batch, without blocking.  After it returned 0, rsa_ext_wait no longer waits
+ * for the GPU; it must still be called (it finalises the batch and reports any error). */
 int rsa_ext_poll(rsa_ext_t *h);
 
 /* The poll/usleep loop and result unpacking of src/gasal2_ssw.cpp:179-249: blocks until `results`

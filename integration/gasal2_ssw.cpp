@@ -57,8 +57,10 @@ int device_count_cap() {
 #ifdef RSA_EXT_ALNINFO
 // End bonus the finish kernel uses.  Starts at strobealign's default; the first call site that runs tells us the
 // aligner's value (rsa_ext_veneer_end_bonus), after which records the device settled carry no CIGAR text.
-std::atomic<int> g_end_bonus{10};
-std::atomic<bool> g_end_bonus_confirmed{false};
+// Bonus and "confirmed" flag live in ONE atomic word (bit 30 = confirmed), so a worker can never pair a stale bonus
+// with confirmed == true.
+constexpr int kBonusConfirmed = 1 << 30;
+std::atomic<int> g_end_bonus_state{10};
 #endif
 
 int usable_devices() {
@@ -155,8 +157,13 @@ struct Warmup {
 void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
                       std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
                       int gap_extend_score) {
-    assert(thread_id >= 0 && thread_id < THREAD_NUM_MAX);
-    assert(query_seqs.size() == target_seqs.size());
+    // the reference only assert()s these (src/gasal2_ssw.cpp:27-28), which vanishes under NDEBUG and then indexes its
+    // per-thread statics out of bounds; fail loudly instead
+    if (thread_id < 0 || thread_id >= THREAD_NUM_MAX || query_seqs.size() != target_seqs.size()) {
+        fprintf(stderr, "[RSA_EXT ERROR:] solve_ssw_on_gpu: thread_id %d outside [0, %d) or %zu queries vs %zu windows\n",
+                thread_id, THREAD_NUM_MAX, query_seqs.size(), target_seqs.size());
+        exit(EXIT_FAILURE);
+    }
     Worker &w = g_workers[thread_id];
     const size_t n = query_seqs.size();
     gasal_results.resize(n);
@@ -184,8 +191,9 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
         w.tp[i] = target_seqs[i].data(); w.tl[i] = (int32_t)target_seqs[i].size();
     }
 #ifdef RSA_EXT_ALNINFO
-    const int end_bonus = g_end_bonus.load();
-    const bool text_free = g_end_bonus_confirmed.load();
+    const int bonus_state = g_end_bonus_state.load(std::memory_order_acquire);
+    const int end_bonus = bonus_state & (kBonusConfirmed - 1);
+    const bool text_free = (bonus_state & kBonusConfirmed) != 0;  // end_bonus is the aligner's own value
     w.aln.resize(n);
     if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
 #endif
@@ -234,8 +242,8 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
 
 #ifdef RSA_EXT_ALNINFO
 void rsa_ext_veneer_end_bonus(int end_bonus) {
-    if (g_end_bonus_confirmed.load(std::memory_order_relaxed) && g_end_bonus.load(std::memory_order_relaxed) == end_bonus) return;
-    g_end_bonus.store(end_bonus);
-    g_end_bonus_confirmed.store(true);
+    const int want = (end_bonus & (kBonusConfirmed - 1)) | kBonusConfirmed;
+    if (g_end_bonus_state.load(std::memory_order_relaxed) == want) return;
+    g_end_bonus_state.store(want, std::memory_order_release);
 }
 #endif

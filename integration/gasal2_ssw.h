@@ -84,6 +84,13 @@ auto rsa_ext_align_gpu(const AlignerT &aligner, const std::string &query, const 
         info.sw_score = rec.aln.sw_score;
         return info;
     }
+    // host path for this record (long CIGAR, or a record computed before the veneer learned the aligner's -L).  The
+    // veneer only omits the CIGAR text of records the device settled with the aligner's own bonus, so the text is here.
+    if (rec.cigar_str.empty() && rec.score > 0 && rec.aln_end_bonus >= 0 && rec.aln.status == 0) {
+        std::cerr << "[RSA_EXT ERROR:] device record without CIGAR text reached the host path (end bonus "
+                  << rec.aln_end_bonus << " vs " << want << ")" << std::endl;
+        exit(EXIT_FAILURE);
+    }
     return aligner.align_gpu(query, ref, rec);
 }
 #endif  // RSA_EXT_ALNINFO

@@ -19,20 +19,36 @@ from rabbitsalign_b200 import workload as W  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def dump(name, batch, ref, scoring=None):
+def dump(name, batch, ref, scoring=None, engine=None):
+    """engine: ExtensionEngine limits the GPU replay needs (max_query_len / max_target_len beyond the defaults)."""
     scoring = scoring or {}
     qs, ts = batch.queries(), batch.targets()
     res = ref.align(qs, ts, **scoring)
     pairs = [{"q": q.decode("latin1"), "t": t.decode("latin1"), "res": list(r.astuple())} for q, t, r in zip(qs, ts, res)]
-    json.dump({"scoring": scoring, "source": os.path.basename(ref.path) + " (reference GASAL2 kernels, host build)",
-               "pairs": pairs}, open(os.path.join(OUT, f"pairs_{name}.json"), "w"))
+    doc = {"scoring": scoring, "source": os.path.basename(ref.path) + " (reference GASAL2 kernels, host build)", "pairs": pairs}
+    if engine:
+        doc["engine"] = engine
+    json.dump(doc, open(os.path.join(OUT, f"pairs_{name}.json"), "w"))
     print(name, len(pairs))
+
+
+def round2(r, r512):
+    """Corners added in round 2 (tests/test_gpu_round2.py uses the same generators at larger sizes)."""
+    for alpha in (b"AC", b"AAAC", b"A", b"ACGTN"):
+        dump("r2_ties16_" + alpha.decode(), W.tie_dense_pairs(30, 257, 496, alpha, seed=310 + len(alpha)), r)
+    dump("r2_ties8_AC", W.tie_dense_pairs(60, 100, 256, b"AC", seed=320, tmax=400), r)
+    dump("r2_saturation", W.saturation_pairs(), r512, engine={"max_query_len": 512})
+    # windows of 2001..2049 bases are beyond MAX_TARGET_LEN for the reference's caller, but its kernels handle them
+    dump("r2_window_edges", W.window_edge_pairs(), r, engine={"max_target_len": 2100})
 
 
 if __name__ == "__main__":
     r = oracle.reference()
     r512 = oracle.reference(512)
     assert r is not None and r512 is not None, "build oracle/_ref first (make -C oracle)"
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":
+        round2(r, r512)
+        sys.exit(0)
     dump("probes", W.from_lists([b"ACGTNCGTAC", b"ACGTACGTAC", b"AAAA", b"NNNN", b"ACGT", b"ACGTACGTACGT", b"acgtacgt"],
                                 [b"ACGTACGTAC", b"ACGTACGTAC", b"CCCC", b"ACGT", b"TTACGTTT", b"GGACGTACGTACGTCC", b"ACGTACGT"]), r)
     dump("adversarial_acgtn", W.adversarial_pairs(400, seed=201), r)
@@ -43,3 +59,4 @@ if __name__ == "__main__":
     dump("ext250_indel", W.extension_pairs(80, seed=206, read_len=250, indel_rate=0.05, max_indel=4, fixed_query_len=False), r)
     dump("long_q500_t2000", W.adversarial_pairs(12, seed=207, max_q=500, max_t=2000), r512)
     dump("scoring_1_4_6_2", W.adversarial_pairs(300, seed=208), r, dict(match=1, mismatch=4, gap_open=6, gap_extend=2))
+    round2(r, r512)

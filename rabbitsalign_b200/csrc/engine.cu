@@ -155,6 +155,7 @@ struct rsa_ext {
 
     // pending batch
     bool pending = false;
+    int deferred_rc = 0;  // error met inside rsa_ext_poll, reported by the following rsa_ext_wait
     bool resident_inflight = false;
     SlotNeed r_need{};
     bool warmed = false;  // first submit done (buffers allocated, kernels loaded): no cold-path gate any more
@@ -541,11 +542,11 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     RedoHeader* redo = reinterpret_cast<RedoHeader*>(const_cast<uint8_t*>(d.blob) + p.off_redo);
     uint32_t* redo_list = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(d.blob) + p.off_redo + sizeof(RedoHeader));
     TbArgs tba{d.q, d.t, meta, info, diroff, d.scratch, d.res, h->sc, d.arena, d.arena_used, d.arena_cap};
-    // packed kernel, one launch per column class (traces its own pairs back)
+    // packed kernel, one launch per column class
     for (const auto& fc : p.fast) {
         int rc = launch_fast_class(st, fc.L, fc.C, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
-                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen, tba);
+                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen);
         if (rc != 0) { h->err = "no packed-kernel instance for L=" + std::to_string(fc.L) + " C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
@@ -745,13 +746,17 @@ int retire_chunk(rsa_ext* h, Slot& s) {
         fprintf(stderr, "[rsa_ext %9.1f retire %p n=%lld]\n", since_load_ms(), (void*)h, (long long)s.plan.n);
     const unsigned long long used = *s.h_arena_used;
     if (used > 0) {
+        // rare: some CIGARs of this chunk are longer than the record's inline bytes.  Their arena offsets were parked
+        // in ends[pi].qend/tend by the traceback (kernels_tb.cuh), so the records themselves stay byte-deterministic.
         std::vector<uint8_t> host(used);
+        std::vector<DpEnd> ends((size_t)s.plan.n);
         CU_TRY(h, cudaMemcpy(host.data(), s.d_arena.p, used, cudaMemcpyDeviceToHost));
+        CU_TRY(h, cudaMemcpy(ends.data(), s.d_ends.p, sizeof(DpEnd) * (size_t)s.plan.n, cudaMemcpyDeviceToHost));
         for (int64_t i = s.plan.lo; i < s.plan.hi; ++i) {
             const rsa_ext_result_t& r = h->results[i];
             if (r.n_ops > RSA_EXT_RLE_INLINE && r.status == 0) {
-                unsigned long long off;
-                memcpy(&off, &r.rle[RSA_EXT_RLE_INLINE - 8], 8);
+                const DpEnd& e = ends[(size_t)(i - s.plan.lo)];
+                const unsigned long long off = (unsigned long long)(uint32_t)e.qend | ((unsigned long long)(uint32_t)e.tend << 32);
                 if (off + (unsigned long long)r.n_ops <= used)
                     h->overflow[i] = std::vector<uint8_t>(host.begin() + off, host.begin() + off + r.n_ops);
             }
@@ -816,6 +821,7 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     h->overflow.clear();
     h->retry.clear();
     h->stats = rsa_ext_stats_t{};
+    h->deferred_rc = RSA_EXT_OK;
     h->pending = true;
     std::unique_lock<std::mutex> cold(g_cold_mutex, std::defer_lock);
     if (!h->warmed) cold.lock();
@@ -1037,6 +1043,9 @@ extern "C" int rsa_ext_set_reference(rsa_ext_t* h, const char* seq, int64_t len)
     int rc = ensure_dev(h, h->d_ref, (size_t)len + 16);
     if (rc) return rc;
     CU_TRY(h, cudaMemcpy(h->d_ref.p, seq, (size_t)len, cudaMemcpyHostToDevice));
+    // a pageable cudaMemcpy may return once the bytes are staged; the engine's streams are non-blocking, so nothing
+    // would order their kernels behind the final DMA
+    CU_TRY(h, cudaDeviceSynchronize());
     h->ref_host = seq;  // kept for the rare exact-only re-submission (status 4); the caller keeps it alive
     h->ref_len = len;
     return RSA_EXT_OK;
@@ -1083,12 +1092,39 @@ extern "C" int rsa_ext_request_alninfo(rsa_ext_t* h, rsa_ext_alninfo_t* out, int
     return RSA_EXT_OK;
 }
 
+// Retire the head chunk and enqueue the next one.  block == false: only when the head chunk's copies have landed.
+// Returns 1 = progress, 0 = nothing ready (non-blocking only) or nothing in flight, < 0 = error.
+static int advance(rsa_ext* h, bool block) {
+    if (h->inflight == 0) return 0;
+    Slot& s = h->slots[h->head];
+    if (!block) {
+        const cudaError_t q = cudaEventQuery(s.ev_d2h);
+        if (q == cudaErrorNotReady) { (void)cudaGetLastError(); return 0; }
+    }
+    int rc = retire_chunk(h, s);
+    if (rc) return rc;
+    h->head = (h->head + 1) % kSlots;
+    if (h->next_pair < h->n) {
+        if ((rc = enqueue_chunk(h, h->slots[h->tail]))) return rc;
+        h->tail = (h->tail + 1) % kSlots;
+    }
+    return 1;
+}
+
+// Like gasal_is_aln_async_done in the reference's `while (poll) usleep` loop (src/gasal2_ssw.cpp:179), poll must make
+// progress by itself: a batch of more chunks than slots only advances when finished chunks are retired and the next
+// ones enqueued, so poll does exactly that (without blocking).  0 = every chunk has landed (rsa_ext_wait will not
+// block on the GPU any more; it still has to be called: it finalises the batch and reports errors), 1 = still running.
 extern "C" int rsa_ext_poll(rsa_ext_t* h) {
     if (!h || !h->pending) return 0;
-    if (h->next_pair < h->n) return 1;
-    for (int k = 0; k < kSlots; ++k)
-        if (h->slots[k].busy && cudaEventQuery(h->slots[k].ev_d2h) == cudaErrorNotReady) return 1;
-    return 0;
+    if (h->deferred_rc) return 0;  // rsa_ext_wait reports it
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return 0;
+    for (;;) {
+        const int r = advance(h, false);
+        if (r < 0) { h->deferred_rc = r; return 0; }
+        if (r == 0) break;
+    }
+    return (h->inflight > 0 || h->next_pair < h->n) ? 1 : 0;
 }
 
 // Pairs the redo pass could not re-tile (status 4; only possible when a chunk holds more symbols outside
@@ -1097,12 +1133,21 @@ extern "C" int rsa_ext_poll(rsa_ext_t* h) {
 static int run_retry(rsa_ext* h) {
     const std::vector<int64_t> idx = h->retry;
     const int64_t m = (int64_t)idx.size();
-    std::vector<const char*> qp(m), tp(m);
-    std::vector<int32_t> ql(m), tl(m);
+    // own staging: the pending batch's buffers may be the handle's submit_ptrs staging (own_q/own_t), which a nested
+    // submit_ptrs would overwrite while reading from it
+    std::vector<int64_t> qo((size_t)m + 1), to((size_t)m + 1);
+    qo[0] = to[0] = 0;
     for (int64_t k = 0; k < m; ++k) {
-        qp[k] = h->qbuf + h->qoff[idx[k]]; ql[k] = (int32_t)(h->qoff[idx[k] + 1] - h->qoff[idx[k]]);
-        if (h->win_off) { tp[k] = h->ref_host + h->win_off[idx[k]]; tl[k] = h->win_len[idx[k]]; }
-        else { tp[k] = h->tbuf + h->toff[idx[k]]; tl[k] = (int32_t)(h->toff[idx[k] + 1] - h->toff[idx[k]]); }
+        const int64_t i = idx[k];
+        qo[k + 1] = qo[k] + (h->qoff[i + 1] - h->qoff[i]);
+        to[k + 1] = to[k] + (h->win_off ? (int64_t)h->win_len[i] : h->toff[i + 1] - h->toff[i]);
+    }
+    std::vector<char> qs((size_t)qo[m] + 16), ts((size_t)to[m] + 16);
+    for (int64_t k = 0; k < m; ++k) {
+        const int64_t i = idx[k];
+        memcpy(qs.data() + qo[k], h->qbuf + h->qoff[i], (size_t)(qo[k + 1] - qo[k]));
+        const char* tsrc = h->win_off ? h->ref_host + h->win_off[i] : h->tbuf + h->toff[i];
+        memcpy(ts.data() + to[k], tsrc, (size_t)(to[k + 1] - to[k]));
     }
     std::vector<rsa_ext_result_t> tmp(m);
     rsa_ext_result_t* results = h->results;
@@ -1114,7 +1159,7 @@ static int run_retry(rsa_ext* h) {
     const rsa_ext_stats_t stats = h->stats;
     const int32_t flags = h->cfg.flags;
     h->cfg.flags |= RSA_EXT_FLAG_EXACT_ONLY;
-    int rc = rsa_ext_submit_ptrs(h, m, qp.data(), ql.data(), tp.data(), tl.data(), tmp.data());
+    int rc = submit_core(h, m, qs.data(), qo.data(), ts.data(), to.data(), tmp.data());
     if (rc == RSA_EXT_OK) rc = rsa_ext_wait(h);
     h->cfg.flags = flags;
     h->alninfo_next = aln_req;
@@ -1141,15 +1186,11 @@ extern "C" int rsa_ext_wait(rsa_ext_t* h) {
     if (!h) return RSA_EXT_ERR_ARG;
     if (!h->pending) { h->err = "nothing submitted"; return RSA_EXT_ERR_STATE; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
-    int rc = RSA_EXT_OK;
-    while (h->inflight > 0) {
-        Slot& s = h->slots[h->head];
-        if ((rc = retire_chunk(h, s))) break;
-        h->head = (h->head + 1) % kSlots;
-        if (h->next_pair < h->n) {
-            if ((rc = enqueue_chunk(h, h->slots[h->tail]))) break;
-            h->tail = (h->tail + 1) % kSlots;
-        }
+    int rc = h->deferred_rc;  // an error rsa_ext_poll ran into
+    h->deferred_rc = RSA_EXT_OK;
+    while (rc == RSA_EXT_OK && h->inflight > 0) {
+        const int r = advance(h, true);
+        if (r < 0) rc = r;
     }
     plan_ahead_finish(h);
     if (rc) {
@@ -1296,6 +1337,7 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
         h->stats.cells += h->res_chunks[c].plan.cells;
     }
     h->stats.h2d_bytes = (int64_t)(qbytes + tbytes + blob_total);
+    CU_TRY(h, cudaDeviceSynchronize());  // pageable uploads above vs the non-blocking streams (see rsa_ext_set_reference)
     while (h->r_events.size() < 4 * h->res_chunks.size()) {
         cudaEvent_t ev;
         CU_TRY(h, cudaEventCreate(&ev));

@@ -44,13 +44,7 @@ constexpr int kFastMaxTlen = 2047;
 __host__ __device__ constexpr int fast_groups_per_warp(int L) { return 32 / L; }
 __host__ __device__ constexpr int fast_warps_per_block(int L) { return L == 8 ? 4 : 2; }
 __host__ __device__ constexpr int fast_ring_slots(int L) { return L == 8 ? 16 : 32; }  // >= L - 1 + 4, power of two
-// Trace pairs back inside the DP kernel (lanes 0/1 of each group) instead of in tb_kernel.  Measured on B200:
-// 1.36 vs 1.50 TCUPS per step -- the 8 walking lanes keep the warp's registers for ~150 dependent HBM round trips
-// (the block's tiles are long out of L2), which costs the ALU-bound DP more latency hiding than the separate
-// kernel costs in time.  Kept for experiments.
-#ifndef RSA_FUSED_TRACEBACK
-#define RSA_FUSED_TRACEBACK 0
-#endif
+// (Tracing pairs back inside this kernel was tried in round 1 and dropped: 1.36 vs 1.50 TCUPS per step)
 
 struct FastGroup {
     uint32_t a, b;      // pair indices in the chunk (b == a: lone pair; a == 0xFFFFFFFF: empty slot)
@@ -226,7 +220,7 @@ __global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <=
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
-               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad, TbArgs tba) {
+               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad) {
     extern __shared__ uint8_t fast_smem[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 words
     if (threadIdx.x < 8) lut[threadIdx.x] = profile_word(threadIdx.x, k);
@@ -305,8 +299,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
     // Every lane holds its first-in-reference-order maximum cell; lanes own increasing column ranges, so among
     // the lanes reaching the pair's maximum the winner is the smallest (8-row block, lane).  Lane 0 of the group
-    // then owns pair a and lane 1 pair b: they publish the DpEnd and trace the pair back right away, while the
-    // group's direction tile is still in L2 (the stand-alone traceback kernel would fetch it from HBM).
+    // then owns pair a and lane 1 pair b: they publish the DpEnd for the traceback kernel.
     DpEnd my_end;
     my_end.score = 0; my_end.qend = 0; my_end.tend = 0; my_end.flags = 0;
     int my_pair = -1;
@@ -331,17 +324,14 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         my_end.score = S;
         my_end.qend = S > 0 ? qend : 0;
         my_end.tend = S > 0 ? tend : 0;
-        my_end.flags = bad ? DPF_NEED_EXACT : (DPF_DONE | DPF_LAYOUT_FAST | (RSA_FUSED_TRACEBACK ? DPF_TRACED : 0u));
+        my_end.flags = bad ? DPF_NEED_EXACT : (DPF_DONE | DPF_LAYOUT_FAST);
     }
-    __syncwarp();  // the group's direction words (stored by all 8 lanes) are visible to lanes 0 and 1 now
     if (my_pair >= 0) {
         ends[my_pair] = my_end;
         if (my_end.flags & DPF_NEED_EXACT) {
             // symbols outside {A,C,G,T,N}: full exact redo (own direction tile), traced by tb_kernel afterwards
             const unsigned int slot = atomicAdd(&redo->count, 1u);
             redo_list[slot] = (uint32_t)my_pair;
-        } else if (RSA_FUSED_TRACEBACK) {
-            tb_one_pair(tba, my_pair, my_end);
         }
     }
 }
@@ -498,7 +488,7 @@ namespace rsa {
 template <int L, int C>
 inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                            uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
+                            uint32_t* redo_list, const FastConsts& k, int max_rows) {
     const int rows_pad = (max_rows + 15) & ~15;
     constexpr int WPB = fast_warps_per_block(L);
     const int groups_per_block = WPB * fast_groups_per_warp(L);
@@ -522,16 +512,16 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
         }
     }
     fast_dp_kernel<L, C><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
-                                                                     redo, redo_list, k, rows_pad, tba);
+                                                                     redo, redo_list, k, rows_pad);
 }
 
 // returns 0, or -1 when C is outside the instantiated range
 inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                              const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                             uint32_t* redo_list, const FastConsts& k, int max_rows, const TbArgs& tba) {
+                             uint32_t* redo_list, const FastConsts& k, int max_rows) {
     if (L == 16) {
         switch (C) {
-#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
+#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
             RSA_FAST_CASE16(17) RSA_FAST_CASE16(18) RSA_FAST_CASE16(19) RSA_FAST_CASE16(20) RSA_FAST_CASE16(21) RSA_FAST_CASE16(22)
             RSA_FAST_CASE16(23) RSA_FAST_CASE16(24) RSA_FAST_CASE16(25) RSA_FAST_CASE16(26) RSA_FAST_CASE16(27) RSA_FAST_CASE16(28)
             RSA_FAST_CASE16(29) RSA_FAST_CASE16(30) RSA_FAST_CASE16(31) RSA_FAST_CASE16(32)
@@ -540,7 +530,7 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
         }
     }
     switch (C) {
-#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tba); return 0;
+#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
         RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6)
         RSA_FAST_CASE(7) RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12)
         RSA_FAST_CASE(13) RSA_FAST_CASE(14) RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18)

@@ -103,7 +103,11 @@ struct TbArgs {
 // Trace one pair back and write its 64-byte record.  Shared (not inlined) by the stand-alone traceback
 // kernel and by the packed DP kernel, which traces its own pairs right after computing them while their
 // direction tiles are still in L2.
-__device__ __noinline__ void tb_one_pair(const TbArgs& a, int pi, DpEnd e) {
+//
+// Long CIGARs (n_ops > RSA_EXT_RLE_INLINE): the record keeps the FIRST inline bytes (so records are byte-deterministic)
+// and the full string goes to the chunk's arena; its arena offset (scheduling dependent, internal) is parked in
+// ends[pi].qend/tend, which nothing reads after the traceback (the host fetches `ends` only when an arena was used).
+__device__ __noinline__ void tb_one_pair(const TbArgs& a, int pi, DpEnd e, DpEnd* __restrict__ ends) {
     rsa_ext_result_t r;
 #pragma unroll
     for (int k = 0; k < RSA_EXT_RLE_INLINE; ++k) r.rle[k] = 0;
@@ -122,12 +126,12 @@ __device__ __noinline__ void tb_one_pair(const TbArgs& a, int pi, DpEnd e) {
     int n_ops = tb_walk(c, e.score, e.tend, e.qend, a.sc, r.rle, RSA_EXT_RLE_INLINE, nullptr, &si, &sj);
     r.status = 0;
     if (n_ops > RSA_EXT_RLE_INLINE) {
-        // rare: long CIGAR.  Reserve n_ops bytes in the chunk's arena and walk again writing all of them;
-        // the arena offset rides in the last 8 inline bytes.
+        // rare: long CIGAR.  Reserve n_ops bytes in the chunk's arena and walk again writing all of them.
         const unsigned long long off = atomicAdd(a.arena_used, (unsigned long long)n_ops);
         if (off + (unsigned long long)n_ops <= a.arena_cap) {
             tb_walk(c, e.score, e.tend, e.qend, a.sc, r.rle, 0, a.arena + off, &si, &sj);
-            memcpy(&r.rle[RSA_EXT_RLE_INLINE - 8], &off, 8);
+            ends[pi].qend = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
+            ends[pi].tend = (int32_t)(uint32_t)(off >> 32);
         } else {
             r.status = 2;  // cannot happen: the arena is sized for the worst case of the chunk
         }
@@ -145,7 +149,7 @@ constexpr int kTbThreads = 128;
 
 // Stand-alone traceback: every pair of the chunk that is not traced yet (exact-kernel pairs, redone pairs)
 // and the failed records of pairs no kernel ran on.
-__global__ void __launch_bounds__(kTbThreads) tb_kernel(TbArgs a, int n, const DpEnd* __restrict__ ends) {
+__global__ void __launch_bounds__(kTbThreads) tb_kernel(TbArgs a, int n, DpEnd* __restrict__ ends) {
     const int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= n) return;
     const DpEnd e = ends[pi];
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(kTbThreads) tb_kernel(TbArgs a, int n, const D
         a.res[pi] = r;
         return;
     }
-    tb_one_pair(a, pi, e);
+    tb_one_pair(a, pi, e, ends);
 }
 
 // Traceback of the packed kernel's pairs in GROUP order: threads 2g and 2g+1 trace pairs a and b of group g.
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kTbThreads) tb_groups_kernel(TbArgs a, const F
     const int pi = (int)((t & 1) ? grp.b : grp.a);
     const DpEnd e = ends[pi];
     if ((e.flags & (DPF_DONE | DPF_LAYOUT_FAST | DPF_TRACED)) != (DPF_DONE | DPF_LAYOUT_FAST)) return;
-    tb_one_pair(a, pi, e);
+    tb_one_pair(a, pi, e, ends);
     ends[pi].flags = e.flags | DPF_TRACED;
 }
 

@@ -226,6 +226,22 @@ class ExtensionEngine:
         self.wait()
         return results
 
+    def align_ptrs(self, queries: Sequence[bytes], targets: Sequence[bytes]) -> np.ndarray:
+        """Blocking rsa_ext_submit_ptrs: n separate strings, the shape of std::vector<std::string> (the veneer's path)."""
+        n = len(queries)
+        results = np.zeros(n, dtype=RESULT_DTYPE)
+        qb = [C.create_string_buffer(bytes(q), max(1, len(q))) for q in queries]
+        tb = [C.create_string_buffer(bytes(t), max(1, len(t))) for t in targets]
+        qp = (C.c_void_p * n)(*[C.addressof(x) for x in qb])
+        tp = (C.c_void_p * n)(*[C.addressof(x) for x in tb])
+        ql = np.array([len(q) for q in queries], dtype=np.int32)
+        tl = np.array([len(t) for t in targets], dtype=np.int32)
+        self._keep = (qb, tb, qp, tp, ql, tl, results)
+        self._check(self.lib.rsa_ext_submit_ptrs(self.h, n, C.cast(qp, C.c_void_p), ql.ctypes.data,
+                                                 C.cast(tp, C.c_void_p), tl.ctypes.data, results.ctypes.data))
+        self.wait()
+        return results
+
     def reserve(self, n: int, qlen: int, tlen: int):
         """Pre-allocate for batches of up to n pairs of (qlen x tlen)."""
         self._check(self.lib.rsa_ext_reserve(self.h, n, qlen, tlen))

@@ -224,3 +224,72 @@ def extension_pairs_fast(n: int, read_len: int = 150, sub_rate: float = 0.01, in
     toff = np.zeros(n + 1, np.int64)
     toff[1:] = np.cumsum(tl)
     return PairBatch(np.concatenate(qparts), qoff, np.concatenate(tparts).astype(np.uint8), toff)
+
+
+# ---- round-2 parity corners (shared by tests/test_gpu_round2.py and oracle/make_golden.py) ---------------------------
+
+def tie_dense_pairs(n: int, qmin: int, qmax: int, alphabet: bytes, seed: int, tmax: int = 700) -> PairBatch:
+    """Related pairs over a tiny alphabet: equal maxima and co-optimal paths everywhere (first-maximum rule,
+    H-source priority, gap-extension ties).  qmin/qmax select the lane geometry (257..500: 16-lane groups)."""
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(alphabet, dtype=np.uint8)
+    qs, ts = [], []
+    for _ in range(n):
+        ql = int(rng.integers(qmin, qmax + 1))
+        tl = int(rng.integers(max(1, ql - 40), min(tmax, ql + 200)))
+        t = alpha[rng.integers(0, len(alpha), size=tl)]
+        a = int(rng.integers(0, max(1, tl - ql)))
+        q = t[a:a + ql].copy()
+        if len(q) < ql:
+            q = np.concatenate([q, alpha[rng.integers(0, len(alpha), size=ql - len(q))]])
+        m = rng.random(ql) < 0.05
+        q[m] = alpha[rng.integers(0, len(alpha), size=int(m.sum()))]
+        if rng.random() < 0.5 and ql > 12:
+            p = int(rng.integers(5, ql - 5))
+            q = np.concatenate([q[:p], q[p + 2:], alpha[rng.integers(0, len(alpha), size=2)]])
+        qs.append(q.astype(np.uint8).tobytes())
+        ts.append(t.astype(np.uint8).tobytes())
+    return from_lists(qs, ts)
+
+
+def saturation_pairs(seed: int = 220, qlens=(496, 500, 511, 512)) -> PairBatch:
+    """Perfect / near-perfect matches of long queries: scores 2*|q| - small, i.e. 992..1024 at the default scoring --
+    the top of the packed kernel's key range (score << 5 | column in a positive s16: score <= 1023) and the hand-off to
+    the exact kernel at 1024.  Six variants per length: perfect, one mismatch, one deletion, homopolymer, AC repeat,
+    leading N."""
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for ql in qlens:
+        for variant in range(6):
+            t = _ACGT[rng.integers(0, 4, size=ql + 60)]
+            q = t[30:30 + ql].copy()
+            if variant == 1:
+                q[ql // 2] = _ACGT[(_CODE[q[ql // 2]] + 1) % 4]
+            if variant == 2:
+                q = np.concatenate([q[:100], q[101:], _ACGT[rng.integers(0, 4, size=1)]])
+            if variant == 3:
+                t = np.full(ql + 60, ord("A"), np.uint8)
+                q = t[:ql].copy()
+            if variant == 4:
+                t = np.tile(np.frombuffer(b"AC", dtype=np.uint8), (ql + 60) // 2)
+                q = t[:ql].copy()
+            if variant == 5:
+                q[0] = ord("N")
+            qs.append(q.astype(np.uint8).tobytes())
+            ts.append(t.astype(np.uint8).tobytes())
+    return from_lists(qs, ts)
+
+
+def window_edge_pairs(seed: int = 221, tlens=(2046, 2047, 2048, 2049), qlens=(150, 300)) -> PairBatch:
+    """Windows at the packed kernel's row limit (2047) and just beyond; the alignment ends in the last rows."""
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for tl in tlens:
+        for ql in qlens:
+            t = _ACGT[rng.integers(0, 4, size=tl)]
+            a = tl - ql - 3
+            q = t[a:a + ql].copy()
+            q[ql // 3] = ord("A") if q[ql // 3] != ord("A") else ord("C")
+            qs.append(q.tobytes())
+            ts.append(t.tobytes())
+    return from_lists(qs, ts)

@@ -146,7 +146,7 @@ def test_golden_vectors_from_reference_kernels(name, exact_only):
     import os
     from rabbitsalign_b200 import ExtensionEngine
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name)))
-    e = ExtensionEngine(exact_only=exact_only, **g.get("scoring", {}))
+    e = ExtensionEngine(exact_only=exact_only, **g.get("scoring", {}), **g.get("engine", {}))
     got = e.solve_ssw_on_gpu([p["q"].encode("latin1") for p in g["pairs"]], [p["t"].encode("latin1") for p in g["pairs"]])
     e.close()
     bad = [(p["q"], p["t"], list(r.astuple()), p["res"]) for p, r in zip(g["pairs"], got) if list(r.astuple()) != p["res"]]

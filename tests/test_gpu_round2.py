@@ -1,0 +1,165 @@
+"""GPU suite, round 2: regression tests for the advisor's findings (poll-driven multi-chunk batches, the status-4
+re-run entered through submit_ptrs / window form, byte-deterministic records with long CIGARs) and the parity corners
+the round-1 review listed (16-lane path with tie-dense inputs, near-saturation scores and the packed->exact hand-off at
+match*|q| = 1023/1024, |t| = 2047/2048, 5 % indel 250-bp pairs against the reference's own GPU path)."""
+import time
+
+import numpy as np
+import pytest
+
+import oracle
+from rabbitsalign_b200 import ExtensionEngine, workload as W
+from parity_util import compare, oracle_arrays
+
+pytestmark = pytest.mark.gpu
+FIELDS = ["score", "query_start", "query_end", "ref_start", "ref_end", "n_ops", "status"]
+
+
+def test_poll_drives_a_multichunk_batch(oracle_lib):
+    """the reference drives its batch with `while (poll) usleep` (src/gasal2_ssw.cpp:179).  With a
+    tiny scratch budget the batch needs many more chunks than the engine has slots; poll alone must finish it."""
+    b = W.extension_pairs(6000, seed=201, fixed_query_len=False)
+    e = ExtensionEngine(scratch_bytes=24 << 20)
+    base = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    res = e.submit(b.qbuf, b.qoff, b.tbuf, b.toff)
+    t0 = time.time()
+    polls = 0
+    while e.poll():
+        polls += 1
+        time.sleep(0.0001)
+        assert time.time() - t0 < 60, "poll never reached 0 (livelock)"
+    e.wait()
+    assert polls > 0
+    assert res.tobytes() == base.tobytes()
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+
+
+def _iupac_batch(n, seed):
+    b = W.extension_pairs(n, seed=seed)
+    q = b.qbuf.copy()
+    q[b.qoff[:-1] + 75] = ord("R")  # every pair needs the exact redo pass
+    return W.PairBatch(q, b.qoff, b.tbuf, b.toff)
+
+
+def test_retry_entered_through_submit_ptrs(oracle_lib):
+    """the status-4 re-run used to go through rsa_ext_submit_ptrs again and copied from the handle's
+    own pinned staging into itself.  Enter through submit_ptrs (what the veneer does) and check every record."""
+    b = _iupac_batch(3000, 202)
+    e = ExtensionEngine()
+    res = e.align_ptrs(b.queries(), b.targets())
+    st = e.stats()
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+    assert st["pairs_redo"] >= 3000
+
+
+def test_retry_entered_through_reference_windows(oracle_lib):
+    rng = np.random.default_rng(203)
+    ref = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1_000_000)
+    n = 3000
+    win_len = rng.integers(230, 260, size=n).astype(np.int32)
+    win_off = rng.integers(0, len(ref) - 300, size=n).astype(np.int64)
+    qs, ts = [], []
+    for i in range(n):
+        w = ref[win_off[i]:win_off[i] + win_len[i]]
+        q = w[40:190].copy()
+        q[75] = ord("R")
+        qs.append(q.tobytes())
+        ts.append(w.tobytes())
+    b = W.from_lists(qs, ts)
+    e = ExtensionEngine()
+    e.set_reference(ref)
+    res = e.align_ref_windows(b.qbuf, b.qoff, win_off, win_len)
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+
+
+def test_long_cigar_records_are_byte_deterministic(oracle_lib):
+    """records with more than 40 RLE bytes used to carry a scheduling-dependent arena offset."""
+    b = W.extension_pairs(4000, seed=204, read_len=400, indel_rate=0.06, max_indel=2, sub_rate=0.04, fixed_query_len=False)
+    e = ExtensionEngine()
+    r1 = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    assert (r1["n_ops"] > 40).sum() > 50, "the case must contain long CIGARs"
+    r2 = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    assert r1.tobytes() == r2.tobytes()
+    e.stage_resident(b.qbuf, b.qoff, b.tbuf, b.toff)
+    e.run_resident()
+    r3 = e.fetch_resident(b.n)
+    assert r1.tobytes() == r3.tobytes()
+    # the inline bytes are the first 40 bytes of the full string
+    e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    for i in np.nonzero(r1["n_ops"] > 40)[0][:50]:
+        assert (e.full_rle(r1, int(i))[:40] == r1["rle"][i]).all()
+    bad = compare(e, r1, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+
+
+# ---- parity corners -----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("alphabet", [b"AC", b"AAAC", b"A", b"ACGTN"], ids=["AC", "AAAC", "A", "ACGTN"])
+def test_sixteen_lane_path_tie_dense(engine, oracle_lib, alphabet):
+    """|q| 257..500 (16-lane groups) over alphabets where equal maxima and co-optimal paths are everywhere."""
+    b = W.tie_dense_pairs(160, 257, 500, alphabet, seed=210 + len(alphabet))
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    bad = compare(engine, res, oracle_arrays(oracle_lib, b), b)
+    assert not bad, "\n".join(bad)
+    assert engine.stats()["pairs_fast"] == b.n
+
+
+def test_near_saturation_scores_and_exact_handoff(oracle_lib):
+    """Perfect and near-perfect matches at |q| in {496, 500, 511, 512}: scores 992..1022 stay on the packed kernel (the
+    maximum-tracking key (score << 5 | column) is a positive s16 up to 1023), 2 * 512 = 1024 goes to the exact kernel."""
+    b = W.saturation_pairs()
+    e = ExtensionEngine(max_query_len=512)
+    res = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    st = e.stats()
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+    assert res["score"].max() == 1024 and (res["score"] >= 1000).sum() >= 8
+    assert st["pairs_exact"] == 6 and st["pairs_fast"] == 18  # |q| = 512 is handed to the exact kernel statically
+
+
+def test_window_length_2047_and_2048(oracle_lib):
+    """|t| = 2047 is the packed kernel's last row count, 2048 the exact kernel's first."""
+    b = W.window_edge_pairs()
+    e = ExtensionEngine(max_target_len=2100)
+    res = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    st = e.stats()
+    bad = compare(e, res, oracle_arrays(oracle_lib, b), b)
+    e.close()
+    assert not bad, "\n".join(bad)
+    assert st["pairs_fast"] == 4 and st["pairs_exact"] == 4
+
+
+def test_250bp_5pct_indel_50k_pairs_against_reference_gpu(engine):
+    """BASELINE configs[3]: 250-bp reads at a 5 % indel-event rate, 50 000 pairs, every field and the CIGAR text against
+    the reference's own CUDA path (GASAL2 + src/gasal2_ssw.cpp for sm_100a) on the same GPU."""
+    ref_gpu = oracle.reference_gpu()
+    if ref_gpu is None:
+        pytest.skip("oracle/_ref/libgasal_gpu.so not built (needs /root/reference at build time)")
+    b = W.extension_pairs(50_000, seed=230, read_len=250, indel_rate=0.05, max_indel=4, fixed_query_len=False)
+    ql = np.diff(b.qoff)
+    tl = np.diff(b.toff)
+    assert (ql <= 496).all() and (tl <= 2000).all()
+    res = engine.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff)
+    n_bad, first = 0, []
+    for lo in range(0, b.n, 512):  # the reference takes STREAM_BATCH_SIZE = 512 pairs per call
+        p = b.slice(lo, min(b.n, lo + 512))
+        out5, texts = ref_gpu.batch(p.qbuf, p.qoff, p.tbuf, p.toff, thread_id=2, cigar_stride=2048)
+        for k in range(p.n):
+            i = lo + k
+            got = (int(res["score"][i]), int(res["query_start"][i]), int(res["query_end"][i]), int(res["ref_start"][i]),
+                   int(res["ref_end"][i]), engine.cigar(res, i))
+            exp = tuple(int(x) for x in out5[k]) + (texts[k],)
+            if got != exp:
+                n_bad += 1
+                if len(first) < 5:
+                    first.append(f"pair {i}: product {got} reference-gpu {exp}")
+    assert n_bad == 0, f"{n_bad} of {b.n} differ\n" + "\n".join(first)
+    assert np.mean(res["n_ops"]) > 15  # long CIGARs, as the config intends
