@@ -119,6 +119,10 @@ int rsa_ext_wait(rsa_ext_t *h);
  * rsa_ext_submit.  Results, rsa_ext_wait/poll and every status are exactly those of rsa_ext_submit on the same
  * bytes (tests/test_gpu_parity.py::test_reference_windows_equal_explicit_windows). */
 int rsa_ext_set_reference(rsa_ext_t *h, const char *seq, int64_t len);
+/* Let `h` use the reference `donor` uploaded (same device; the copy in HBM is shared and freed with its last user):
+ * the pipeline's workers each own a handle but need the reference once per GPU (north_star: "index and reference
+ * replicated per GPU"). */
+int rsa_ext_share_reference(rsa_ext_t *h, const rsa_ext_t *donor);
 int rsa_ext_submit_ref_windows(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff,
                                const int64_t *win_off, const int32_t *win_len, rsa_ext_result_t *results);
 

@@ -117,4 +117,37 @@ $CXX -o "$OUT/rabbitsalign_b200_alninfo" $ALNOBJS "$OUT/obj_aln/veneer.o" -L"$RO
 ALNFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_aln/pc_fx.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
 $CXX -o "$OUT/rabbitsalign_fx_b200_alninfo" $ALNFXOBJS $FXIO "$OUT/obj_aln/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
      -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# ---- zero-edit whole-chunk build (VERDICT r1 task 1a): the same unmodified sources, -DSTREAM_BATCH_SIZE=1048576, so a
+#      chunk's todo list goes down in one solve_ssw_on_gpu call instead of 512-pair slices (the engine takes any n).
+mkdir -p "$OUT/obj_big"
+BIGFLAGS="$FLAGS -DSTREAM_BATCH_SIZE=1048576"
+pids=()
+( $CXX $BIGFLAGS -c "$REF_ROOT/src/pc.cpp" -o "$OUT/obj_big/pc.o" ) & pids+=($!)
+( $CXX $BIGFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$REF_ROOT/src/pc.cpp" -o "$OUT/obj_big/pc_fx.o" ) & pids+=($!)
+( $CXX $BIGFLAGS -c "$HERE/gasal2_ssw.cpp" -o "$OUT/obj_big/veneer.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+BIGOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_big/pc.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_big" $BIGOBJS "$OUT/obj_big/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+BIGFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_big/pc_fx.o";; main) echo "$OUT/obj_fx/main.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_big" $BIGFXOBJS $FXIO "$OUT/obj_big/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+
+# ---- window build (caller half): patch_caller.py --windows on a copy of src/pc.cpp:
+#      windows travel as (contig, start, length), one call per chunk, genome resident in HBM, AlignmentInfo from the device.
+mkdir -p "$OUT/windows" "$OUT/obj_win"
+python3 "$HERE/patch_caller.py" --windows "$REF_ROOT/src/pc.cpp" "$OUT/windows/pc.cpp"
+WINFLAGS="$FLAGS -DRSA_EXT_WINDOWS"
+pids=()
+( $CXX $WINFLAGS -c "$OUT/windows/pc.cpp" -o "$OUT/obj_win/pc.o" ) & pids+=($!)
+( $CXX $WINFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$OUT/windows/pc.cpp" -o "$OUT/obj_win/pc_fx.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$HERE/gasal2_ssw.cpp" -o "$OUT/obj_win/veneer.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+# (aligner.o / ssw_cpp.o of the alninfo build: the record layout is the same)
+WINOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_win/pc.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_win" $WINOBJS "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+WINFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_win/pc_fx.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_win" $WINFXOBJS $FXIO "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
 ls -la "$OUT"/rabbitsalign_*

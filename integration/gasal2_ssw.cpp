@@ -31,6 +31,11 @@ namespace {
 
 struct Worker {
     rsa_ext_t *h = nullptr;
+    int device = 0;
+    bool has_reference = false;                 // window build: the handle sees the genome resident on its GPU
+    std::vector<char> qcat;                     // window build: the batch's queries back to back
+    std::vector<int64_t> qoff, woff;
+    std::vector<int32_t> wlen;
     std::vector<const char *> qp, tp;
     std::vector<int32_t> ql, tl;
     std::vector<rsa_ext_result_t> res;
@@ -76,6 +81,7 @@ int usable_devices() {
 // creates its handle the ordinary way.  A failure here is not reported -- the first real call reports it.
 constexpr int kDefaultScores[4] = {2, 8, 12, 1};  // src/cmdline.hpp:46-50 / the prototype's default arguments
 constexpr int kPoolReadLen = 250, kPoolWindowLen = 500;  // shapes the pooled handles are pre-sized for
+constexpr int kPoolPairs = STREAM_BATCH_SIZE < 8192 ? STREAM_BATCH_SIZE : 8192;  // (whole-chunk builds raise the macro)
 
 struct Warmup {
     std::thread t;
@@ -115,7 +121,7 @@ struct Warmup {
                 cfg.gap_open = kDefaultScores[2]; cfg.gap_extend = kDefaultScores[3];
                 rsa_ext_t *h = nullptr;
                 if (rsa_ext_create(&cfg, &h) != RSA_EXT_OK) break;
-                rsa_ext_reserve(h, STREAM_BATCH_SIZE, kPoolReadLen, kPoolWindowLen);
+                rsa_ext_reserve(h, kPoolPairs, kPoolReadLen, kPoolWindowLen);
                 if (k < ndev) {  // one tiny batch per device loads the common kernels
                     const std::string q(150, 'A'), w(200, 'A');
                     const char *qp = q.data(), *tp = w.data();
@@ -154,21 +160,19 @@ struct Warmup {
 
 }  // namespace
 
-void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
-                      std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
-                      int gap_extend_score) {
+namespace {
+
+// The worker's handle: created on its first call with that call's scores (src/gasal2_ssw.cpp:29-57,92-102).
+Worker &acquire_worker(int thread_id, size_t n_queries, size_t n_targets, int match_score, int mismatch_score,
+                       int gap_open_score, int gap_extend_score) {
     // the reference only assert()s these (src/gasal2_ssw.cpp:27-28), which vanishes under NDEBUG and then indexes its
     // per-thread statics out of bounds; fail loudly instead
-    if (thread_id < 0 || thread_id >= THREAD_NUM_MAX || query_seqs.size() != target_seqs.size()) {
+    if (thread_id < 0 || thread_id >= THREAD_NUM_MAX || n_queries != n_targets) {
         fprintf(stderr, "[RSA_EXT ERROR:] solve_ssw_on_gpu: thread_id %d outside [0, %d) or %zu queries vs %zu windows\n",
-                thread_id, THREAD_NUM_MAX, query_seqs.size(), target_seqs.size());
+                thread_id, THREAD_NUM_MAX, n_queries, n_targets);
         exit(EXIT_FAILURE);
     }
     Worker &w = g_workers[thread_id];
-    const size_t n = query_seqs.size();
-    gasal_results.resize(n);
-    if (n == 0) return;
-
     if (!w.h) {
         std::lock_guard<std::mutex> lock(g_create_mutex);
         const int ndev = usable_devices();
@@ -181,32 +185,23 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
         cfg.mismatch = mismatch_score;
         cfg.gap_open = gap_open_score;
         cfg.gap_extend = gap_extend_score;
+        w.device = cfg.device;
         w.h = g_warmup.take(cfg.device, match_score, mismatch_score, gap_open_score, gap_extend_score);
         if (!w.h && rsa_ext_create(&cfg, &w.h) != RSA_EXT_OK) die("rsa_ext_create", nullptr);
     }
+    return w;
+}
 
-    w.qp.resize(n); w.tp.resize(n); w.ql.resize(n); w.tl.resize(n); w.res.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-        w.qp[i] = query_seqs[i].data(); w.ql[i] = (int32_t)query_seqs[i].size();
-        w.tp[i] = target_seqs[i].data(); w.tl[i] = (int32_t)target_seqs[i].size();
-    }
-#ifdef RSA_EXT_ALNINFO
-    const int bonus_state = g_end_bonus_state.load(std::memory_order_acquire);
-    const int end_bonus = bonus_state & (kBonusConfirmed - 1);
-    const bool text_free = (bonus_state & kBonusConfirmed) != 0;  // end_bonus is the aligner's own value
-    w.aln.resize(n);
-    if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
-#endif
-    int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
-    if (rc == RSA_EXT_ERR_QUERY_LEN) {
-        size_t mx = 0;
-        for (size_t i = 0; i < n; ++i) mx = MAX(mx, query_seqs[i].length());
-        std::cerr << "gasal2 : read size is too big, " << mx << " > " << MAX_QUERY_LEN << std::endl;
-        exit(0);
-    }
-    if (rc != RSA_EXT_OK) die("rsa_ext_submit_ptrs", w.h);
-    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+[[noreturn]] void die_query_too_long(const std::vector<std::string> &query_seqs) {
+    size_t mx = 0;
+    for (const std::string &q : query_seqs) mx = MAX(mx, q.length());
+    std::cerr << "gasal2 : read size is too big, " << mx << " > " << MAX_QUERY_LEN << std::endl;  // gasal2_ssw.cpp:84-87
+    exit(0);
+}
 
+// records -> gasal_tmp_res (CIGAR text as src/gasal2_ssw.cpp:184-243 prints it)
+void unpack_results(Worker &w, size_t n, std::vector<gasal_tmp_res> &gasal_results, bool text_free, int end_bonus) {
+    (void)text_free; (void)end_bonus;
     char text[4096];
     for (size_t i = 0; i < n; ++i) {
         const rsa_ext_result_t &r = w.res[i];
@@ -239,6 +234,110 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
 #endif
     }
 }
+
+}  // namespace
+
+void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
+                      std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
+                      int gap_extend_score) {
+    Worker &w = acquire_worker(thread_id, query_seqs.size(), target_seqs.size(), match_score, mismatch_score,
+                               gap_open_score, gap_extend_score);
+    const size_t n = query_seqs.size();
+    gasal_results.resize(n);
+    if (n == 0) return;
+
+    w.qp.resize(n); w.tp.resize(n); w.ql.resize(n); w.tl.resize(n); w.res.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        w.qp[i] = query_seqs[i].data(); w.ql[i] = (int32_t)query_seqs[i].size();
+        w.tp[i] = target_seqs[i].data(); w.tl[i] = (int32_t)target_seqs[i].size();
+    }
+    int end_bonus = 0;
+    bool text_free = false;
+#ifdef RSA_EXT_ALNINFO
+    const int bonus_state = g_end_bonus_state.load(std::memory_order_acquire);
+    end_bonus = bonus_state & (kBonusConfirmed - 1);
+    text_free = (bonus_state & kBonusConfirmed) != 0;  // end_bonus is the aligner's own value
+    w.aln.resize(n);
+    if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
+#endif
+    int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
+    if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
+    if (rc != RSA_EXT_OK) die("rsa_ext_submit_ptrs", w.h);
+    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    unpack_results(w, n, gasal_results, text_free, end_bonus);
+}
+
+#ifdef RSA_EXT_WINDOWS
+namespace {
+// The reference genome as ONE buffer (contigs back to back) + where each contig starts: built once per process from
+// references.sequences, uploaded once per GPU by the first worker that lands there and shared by the others.
+struct ResidentGenome {
+    std::mutex m;
+    const std::vector<std::string> *source = nullptr;
+    std::string concat;
+    std::vector<int64_t> contig_off;
+    rsa_ext_t *owner[64] = {};  // per device: the handle that uploaded (donor for rsa_ext_share_reference)
+} g_genome;
+
+void attach_reference(Worker &w, const std::vector<std::string> &sequences) {
+    std::lock_guard<std::mutex> lk(g_genome.m);
+    if (!g_genome.source) {
+        size_t total = 0;
+        for (const std::string &s : sequences) total += s.size();
+        g_genome.concat.reserve(total);
+        g_genome.contig_off.reserve(sequences.size() + 1);
+        for (const std::string &s : sequences) { g_genome.contig_off.push_back((int64_t)g_genome.concat.size()); g_genome.concat += s; }
+        g_genome.contig_off.push_back((int64_t)g_genome.concat.size());
+        g_genome.source = &sequences;
+    } else if (g_genome.source != &sequences) {
+        fprintf(stderr, "[RSA_EXT ERROR:] solve_ssw_on_gpu_windows: one reference per process\n");
+        exit(EXIT_FAILURE);
+    }
+    const int d = w.device;
+    if (d < 0 || d >= 64) die("device ordinal", nullptr);
+    if (!g_genome.owner[d]) {
+        if (rsa_ext_set_reference(w.h, g_genome.concat.data(), (int64_t)g_genome.concat.size()) != RSA_EXT_OK) die("rsa_ext_set_reference", w.h);
+        g_genome.owner[d] = w.h;
+    } else if (rsa_ext_share_reference(w.h, g_genome.owner[d]) != RSA_EXT_OK) {
+        die("rsa_ext_share_reference", w.h);
+    }
+    w.has_reference = true;
+}
+}  // namespace
+
+void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
+                              std::vector<RsaWindow> &windows, const std::vector<std::string> &sequences, int match_score,
+                              int mismatch_score, int gap_open_score, int gap_extend_score) {
+    Worker &w = acquire_worker(thread_id, query_seqs.size(), windows.size(), match_score, mismatch_score, gap_open_score,
+                               gap_extend_score);
+    const size_t n = query_seqs.size();
+    gasal_results.resize(n);
+    if (n == 0) return;
+    if (!w.has_reference) attach_reference(w, sequences);
+
+    // queries back to back (the engine copies them to the GPU from here); windows as (offset, length) in the genome
+    w.qoff.resize(n + 1); w.woff.resize(n); w.wlen.resize(n); w.res.resize(n);
+    size_t qbytes = 0;
+    for (size_t i = 0; i < n; ++i) { w.qoff[i] = (int64_t)qbytes; qbytes += query_seqs[i].size(); }
+    w.qoff[n] = (int64_t)qbytes;
+    w.qcat.resize(qbytes + 16);
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(w.qcat.data() + w.qoff[i], query_seqs[i].data(), query_seqs[i].size());
+        w.woff[i] = g_genome.contig_off[windows[i].ref_id] + (int64_t)windows[i].start;
+        w.wlen[i] = (int32_t)windows[i].len;
+    }
+    const int bonus_state = g_end_bonus_state.load(std::memory_order_acquire);
+    const int end_bonus = bonus_state & (kBonusConfirmed - 1);
+    const bool text_free = (bonus_state & kBonusConfirmed) != 0;
+    w.aln.resize(n);
+    if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
+    int rc = rsa_ext_submit_ref_windows(w.h, (int64_t)n, w.qcat.data(), w.qoff.data(), w.woff.data(), w.wlen.data(), w.res.data());
+    if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
+    if (rc != RSA_EXT_OK) die("rsa_ext_submit_ref_windows", w.h);
+    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    unpack_results(w, n, gasal_results, text_free, end_bonus);
+}
+#endif  // RSA_EXT_WINDOWS
 
 #ifdef RSA_EXT_ALNINFO
 void rsa_ext_veneer_end_bonus(int end_bonus) {

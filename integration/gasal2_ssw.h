@@ -28,6 +28,9 @@
 #define DEBUG
 #define MAX(a, b) (a > b ? a : b)
 
+#ifdef RSA_EXT_WINDOWS
+#define RSA_EXT_ALNINFO  // the window build takes AlignmentInfo from the device as well
+#endif
 #ifdef RSA_EXT_ALNINFO
 #include "rsa_ext.h"
 #endif
@@ -51,6 +54,36 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
                       std::vector<std::string> &todo_refs, int match_score = 2, int mismatch_score = 8,
                       int gap_open_score = 12, int gap_extend_score = 1);
 
+#ifdef RSA_EXT_WINDOWS
+// SURVEY 8(f) rank 1, caller half: a reference window named by (contig, start, length) instead of a std::string built
+// with substr (src/pc.cpp:214-242, 333-368).  The todo list of a chunk becomes std::vector<RsaWindow>; the whole list
+// goes down in ONE call (no 512-pair slice copies, src/pc.cpp:644-672) and the engine reads the windows from the
+// reference resident in HBM (rsa_ext_set_reference / rsa_ext_submit_ref_windows).  The string is only materialised
+// for the rare record the host has to finish itself (gasal_fail -> Aligner::align, long CIGARs).
+struct RsaWindow {
+    const std::string *contig;  // references.sequences[ref_id]
+    uint32_t ref_id;
+    uint32_t start;
+    uint32_t len;
+    RsaWindow(const std::vector<std::string> &sequences, size_t ref_id_, size_t start_, size_t want)
+        : contig(&sequences[ref_id_]), ref_id((uint32_t)ref_id_) {
+        // std::string::substr semantics: the length is clipped to the end of the contig
+        const size_t sz = contig->size();
+        start = (uint32_t)(start_ < sz ? start_ : sz);
+        len = (uint32_t)(want < sz - start ? want : sz - start);
+    }
+    size_t size() const { return len; }
+    size_t length() const { return len; }
+    std::string str() const { return contig->substr(start, len); }
+    operator std::string() const { return str(); }
+};
+
+// One call per chunk: `sequences` is references.sequences (uploaded once per GPU, shared by all workers).
+void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &todo_querys,
+                              std::vector<RsaWindow> &todo_refs, const std::vector<std::string> &sequences,
+                              int match_score = 2, int mismatch_score = 8, int gap_open_score = 12, int gap_extend_score = 1);
+#endif
+
 #ifdef RSA_EXT_ALNINFO
 // The two call-site helpers of the optional build.  They replace, at the four caller loops of src/pc.cpp
 // (:735-744 and siblings), `gasal_fail(q, r, rec)` and `aligner.align_gpu(q, r, rec)`; integration/patch_caller.py
@@ -59,22 +92,23 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
 void rsa_ext_veneer_end_bonus(int end_bonus);  // tells the veneer the aligner's -L; from then on it skips CIGAR text
                                                // for records the device settled
 
-template <class Rec>
-bool rsa_ext_gasal_fail(std::string &query, std::string &ref, Rec &rec) {
+template <class RefT, class Rec>
+bool rsa_ext_gasal_fail(std::string &query, RefT &ref_in, Rec &rec) {
     if (rec.aln_end_bonus >= 0) {
         if (rec.aln.status == 0) return false;                         // accepted on the device
         if (rec.aln.status == 1 || rec.aln.status == 2) return true;   // gasal_fail / window over MAX_TARGET_LEN
     }
+    std::string ref = ref_in;            // (a copy only on this rare path; RsaWindow materialises its string here)
     return gasal_fail(query, ref, rec);  // src/pc.cpp:466-478
 }
 
-template <class AlignerT, class Rec>
-auto rsa_ext_align_gpu(const AlignerT &aligner, const std::string &query, const std::string &ref, Rec &rec)
-    -> decltype(aligner.align_gpu(query, ref, rec)) {
+template <class AlignerT, class RefT, class Rec>
+auto rsa_ext_align_gpu(const AlignerT &aligner, const std::string &query, const RefT &ref_in, Rec &rec)
+    -> decltype(aligner.align_gpu(query, std::string(), rec)) {
     const int want = aligner.parameters.end_bonus;
     rsa_ext_veneer_end_bonus(want);
     if (rec.aln_end_bonus == want && rec.aln.status == 0) {
-        decltype(aligner.align_gpu(query, ref, rec)) info;  // AlignmentInfo, src/aligner.hpp:20-30
+        decltype(aligner.align_gpu(query, std::string(), rec)) info;  // AlignmentInfo, src/aligner.hpp:20-30
         info.cigar = decltype(info.cigar)(const_cast<uint32_t *>(rec.aln.cigar), (size_t)rec.aln.n_cigar);
         info.edit_distance = (unsigned)rec.aln.edit_distance;
         info.ref_start = (unsigned)rec.aln.ref_start;
@@ -91,6 +125,7 @@ auto rsa_ext_align_gpu(const AlignerT &aligner, const std::string &query, const 
                   << rec.aln_end_bonus << " vs " << want << ")" << std::endl;
         exit(EXIT_FAILURE);
     }
+    const std::string ref = ref_in;
     return aligner.align_gpu(query, ref, rec);
 }
 #endif  // RSA_EXT_ALNINFO

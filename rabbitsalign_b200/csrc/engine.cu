@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -132,6 +133,18 @@ struct PlanAhead {
     PlannedChunk ring[kPlanRing];
 };
 
+// Reference sequence resident in HBM (rsa_ext_set_reference); handles of one device may share one copy
+// (rsa_ext_share_reference), e.g. the 16 workers of the pipeline.
+struct RefBuf {
+    int device = 0;
+    uint8_t* d = nullptr;
+    const char* host = nullptr;  // kept for the rare exact-only re-submission (status 4); the caller keeps it alive
+    int64_t len = 0;
+    ~RefBuf() {
+        if (d) { cudaSetDevice(device); cudaFree(d); }
+    }
+};
+
 struct ResidentChunk {
     ChunkPlan plan;
     uint8_t* d_blob = nullptr;
@@ -167,9 +180,7 @@ struct rsa_ext {
     rsa_ext_result_t* results = nullptr;
     const int64_t* win_off = nullptr;      // pending batch in window form (targets inside the resident reference)
     const int32_t* win_len = nullptr;
-    DevBuf d_ref;                          // resident reference (rsa_ext_set_reference)
-    const char* ref_host = nullptr;
-    int64_t ref_len = 0;
+    std::shared_ptr<RefBuf> ref;           // resident reference (rsa_ext_set_reference / rsa_ext_share_reference)
     rsa_ext_alninfo_t* alninfo = nullptr;  // optional second output of the pending batch
     rsa_ext_alninfo_t* alninfo_next = nullptr;
     int end_bonus = 10;
@@ -702,7 +713,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
     cudaStream_t s_dp = (!serial && (h->dp_toggle++ & 1)) ? h->s_comp2 : h->s_comp;
     CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_h2d, 0));
-    const uint8_t* d_targets = h->win_off ? h->d_ref.p : s.d_t.p;  // window form: meta.toff indexes the resident reference
+    const uint8_t* d_targets = h->win_off ? h->ref->d : s.d_t.p;  // window form: meta.toff indexes the resident reference
     ChunkDev d{s.d_blob.p, s.d_q.p, d_targets, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
@@ -792,9 +803,9 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     const bool windows = win_off != nullptr;
     if (n <= 0 || !qbuf || !qoff || !results || (windows ? !win_len : (!tbuf || !toff))) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
     if (windows) {
-        if (!h->d_ref.p) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
+        if (!h->ref) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
         for (int64_t i = 0; i < n; ++i)
-            if (win_len[i] < 0 || win_off[i] < 0 || win_off[i] + win_len[i] > h->ref_len) {
+            if (win_len[i] < 0 || win_off[i] < 0 || win_off[i] + win_len[i] > h->ref->len) {
                 h->err = "window " + std::to_string(i) + " lies outside the resident reference";
                 return RSA_EXT_ERR_ARG;
             }
@@ -983,7 +994,8 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
         if (s.ev_mid) cudaEventDestroy(s.ev_mid);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
-    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs, &h->d_ref})
+    h->ref.reset();
+    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
     if (h->own_q.p) cudaFreeHost(h->own_q.p);
@@ -1040,14 +1052,26 @@ extern "C" int rsa_ext_set_reference(rsa_ext_t* h, const char* seq, int64_t len)
     if (!seq || len <= 0 || len > (int64_t)0xFFFFFFFFll) { h->err = "reference must be 1..2^32-1 bytes"; return RSA_EXT_ERR_ARG; }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     std::lock_guard<std::mutex> cold(g_cold_mutex);
-    int rc = ensure_dev(h, h->d_ref, (size_t)len + 16);
-    if (rc) return rc;
-    CU_TRY(h, cudaMemcpy(h->d_ref.p, seq, (size_t)len, cudaMemcpyHostToDevice));
+    h->ref.reset();
+    auto rb = std::make_shared<RefBuf>();
+    rb->device = h->cfg.device;
+    CU_TRY(h, cudaMalloc(&rb->d, (size_t)len + 16));
+    CU_TRY(h, cudaMemcpy(rb->d, seq, (size_t)len, cudaMemcpyHostToDevice));
     // a pageable cudaMemcpy may return once the bytes are staged; the engine's streams are non-blocking, so nothing
     // would order their kernels behind the final DMA
     CU_TRY(h, cudaDeviceSynchronize());
-    h->ref_host = seq;  // kept for the rare exact-only re-submission (status 4); the caller keeps it alive
-    h->ref_len = len;
+    rb->host = seq;
+    rb->len = len;
+    h->ref = rb;
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_share_reference(rsa_ext_t* h, const rsa_ext_t* donor) {
+    if (!h || !donor) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    if (!donor->ref) { h->err = "the donor handle has no resident reference"; return RSA_EXT_ERR_STATE; }
+    if (donor->ref->device != h->cfg.device) { h->err = "the donor handle lives on another device"; return RSA_EXT_ERR_ARG; }
+    h->ref = donor->ref;
     return RSA_EXT_OK;
 }
 
@@ -1146,7 +1170,7 @@ static int run_retry(rsa_ext* h) {
     for (int64_t k = 0; k < m; ++k) {
         const int64_t i = idx[k];
         memcpy(qs.data() + qo[k], h->qbuf + h->qoff[i], (size_t)(qo[k + 1] - qo[k]));
-        const char* tsrc = h->win_off ? h->ref_host + h->win_off[i] : h->tbuf + h->toff[i];
+        const char* tsrc = h->win_off ? h->ref->host + h->win_off[i] : h->tbuf + h->toff[i];
         memcpy(ts.data() + to[k], tsrc, (size_t)(to[k + 1] - to[k]));
     }
     std::vector<rsa_ext_result_t> tmp(m);

@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
-    "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows",
+    "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows", "rsa_ext_share_reference",
 ]
 
 _lib = None
@@ -117,6 +117,8 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_reserve.restype = C.c_int
     lib.rsa_ext_set_reference.argtypes = [vp, vp, i64]
     lib.rsa_ext_set_reference.restype = C.c_int
+    lib.rsa_ext_share_reference.argtypes = [vp, vp]
+    lib.rsa_ext_share_reference.restype = C.c_int
     lib.rsa_ext_submit_ref_windows.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.rsa_ext_submit_ref_windows.restype = C.c_int
     _lib = lib
@@ -213,6 +215,11 @@ class ExtensionEngine:
         assert seq.dtype == np.uint8
         self._ref_keep = np.ascontiguousarray(seq)
         self._check(self.lib.rsa_ext_set_reference(self.h, self._ref_keep.ctypes.data, len(self._ref_keep)))
+
+    def share_reference(self, donor: "ExtensionEngine"):
+        """Use the resident reference another engine on the same device uploaded (one copy in HBM)."""
+        self._ref_keep = donor._ref_keep
+        self._check(self.lib.rsa_ext_share_reference(self.h, donor.h))
 
     def align_ref_windows(self, qbuf, qoff, win_off, win_len) -> np.ndarray:
         """Blocking: queries against windows [win_off[i], win_off[i]+win_len[i]) of the resident reference."""

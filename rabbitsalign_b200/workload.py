@@ -226,7 +226,7 @@ def extension_pairs_fast(n: int, read_len: int = 150, sub_rate: float = 0.01, in
     return PairBatch(np.concatenate(qparts), qoff, np.concatenate(tparts).astype(np.uint8), toff)
 
 
-# ---- round-2 parity corners (shared by tests/test_gpu_round2.py and oracle/make_golden.py) ---------------------------
+# ---- round-2 parity corners (shared by the GPU tests and the golden-vector generator) -------------------------------
 
 def tie_dense_pairs(n: int, qmin: int, qmax: int, alphabet: bytes, seed: int, tmax: int = 700) -> PairBatch:
     """Related pairs over a tiny alphabet: equal maxima and co-optimal paths everywhere (first-maximum rule,

@@ -19,11 +19,32 @@ pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_golden.json")))
 
 
-@pytest.mark.parametrize("variant", ["record", "alninfo", "reference-gpu"])
+SUFFIX = {"record": "", "alninfo": "_alninfo", "big": "_big", "windows": "_win", "two-gpus": "_win"}
+
+
+def _gpu_count():
+    from rabbitsalign_b200 import ext
+    return ext.load_library().rsa_ext_device_count()
+
+
+@pytest.mark.parametrize("variant", ["record", "alninfo", "big", "windows", "two-gpus", "reference-gpu"])
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_sam_is_byte_identical(name, variant, tmp_path):
+    """record: unmodified caller, 512-pair slices.  alninfo: AlignmentInfo from the device.  big: unmodified caller
+    compiled with -DSTREAM_BATCH_SIZE=1048576 (one call per chunk).  windows: the caller edit of SURVEY 8f rank 1
+    (windows as offsets into the genome resident in HBM, one call per chunk).  two-gpus: the windows build with its
+    workers spread over two GPUs (genome replicated per GPU); skipped on a one-GPU box."""
     g = GOLD[name]
-    BIN = os.path.join(B, ("rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200") + ("_alninfo" if variant == "alninfo" else ""))
+    BIN = os.path.join(B, ("rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200") + SUFFIX.get(variant, ""))
+    env = dict(os.environ)
+    if variant == "two-gpus":
+        if _gpu_count() < 2:
+            pytest.skip("needs two GPUs")
+        if g["threads"] < 2:
+            pytest.skip("one worker cannot span two GPUs")
+        env["RSA_EXT_DEVICES"] = "2"
+    else:
+        env["RSA_EXT_DEVICES"] = "1"
     if variant == "reference-gpu":
         # the reference as shipped (its own GASAL2 GPU path, sm_100a build): the golden md5s came from its kernels
         # compiled for the HOST; this confirms them against the real GPU run
@@ -39,7 +60,7 @@ def test_sam_is_byte_identical(name, variant, tmp_path):
         assert md5_file(os.path.join(d, f)) == g["inputs"][f], f"synthetic input {f} differs from the golden run"
     out = os.path.join(d, "b200.sam")
     args = [os.path.join(d, "ref.fa"), os.path.join(d, "reads_1.fq")] + ([os.path.join(d, "reads_2.fq")] if g["paired"] else [])
-    r = subprocess.run([BIN, "-t", str(g["threads"]), "-o", out] + args, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([BIN, "-t", str(g["threads"]), "-o", out] + args, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     n = sum(1 for ln in open(out, "rb") if not ln.startswith(b"@"))
     assert n == g["records"]

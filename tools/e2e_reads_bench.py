@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--sub", type=float, default=0.01)
     ap.add_argument("--indel", type=float, default=0.003)
     ap.add_argument("--max-indel", type=int, default=3)
+    ap.add_argument("--binaries", default="", help="comma-separated binaries under integration/_build (default: all)")
+    ap.add_argument("--repeat", type=int, default=1, help="runs per binary; the best wall time is reported, all are listed")
     ap.add_argument("--subsets", default="", help="comma-separated read counts to also run (prefixes of the read file)")
     a = ap.parse_args()
     out = {"ref_len": a.ref_len, "reads": a.reads * (2 if a.paired else 1), "paired": a.paired, "threads": a.threads,
@@ -77,14 +79,28 @@ def main():
                 for _ in range(4 * k):
                     g.write(f.readline())
             sub_files[k] = path
-        for name in ("rabbitsalign_cpussw", "rabbitsalign_gasalgpu", "rabbitsalign_b200", "rabbitsalign_b200_alninfo"):
+        names = a.binaries.split(",") if a.binaries else ["rabbitsalign_cpussw", "rabbitsalign_gasalgpu", "rabbitsalign_b200",
+                                                          "rabbitsalign_b200_alninfo", "rabbitsalign_b200_big", "rabbitsalign_b200_win"]
+        for name in names:
             exe = os.path.join(B, name)
             if not os.path.exists(exe):
                 out[name] = "not built"
                 continue
             res = run(exe, files[1:], name)
+            walls = [res.get("wall_s")]
+            for _ in range(a.repeat - 1):
+                r2 = run(exe, files[1:], name)
+                walls.append(r2.get("wall_s"))
+                if "error" not in r2 and ("error" in res or r2["wall_s"] < res["wall_s"]):
+                    r2_md5_same = r2.get("sam_md5") == res.get("sam_md5")
+                    res = r2
+                    res["sam_md5_stable"] = r2_md5_same
+            if a.repeat > 1:
+                res["wall_s_runs"] = walls
             if "error" not in res:
                 res["reads_per_s_wall"] = round(out["reads"] / res["wall_s"])
+                if res.get("mapping_s"):
+                    res["reads_per_s_mapping"] = round(out["reads"] / res["mapping_s"])
             out[name] = res
             pts = [(out["reads"], res.get("mapping_s"))]
             for k in subsets:
