@@ -12,10 +12,9 @@ mate-rescue windows).  Metric: extension GCUPS, cells = sum |q|*|t| (SURVEY.md 8
              compute stream, max over ranks.
   e2e        the same batch through the C ABI from pinned HOST buffers (rsa_ext_submit + rsa_ext_wait):
              H2D of the ASCII + plan, kernels, D2H of the records, every step, wall clock.
-  roofline   see DESIGN.md: the DP kernel is bound by the integer/DPX issue rate, so `roofline_issue` carries
-             the meaningful fraction (ceiling measured live by tools/dpx_microbench); `roofline` (contract
-             format, bound "hbm") reports the algorithmic HBM traffic of the DP kernel against the measured
-             copy bandwidth.
+  roofline   the DP kernel is bound by the integer/DPX issue rate, so that is the roof reported: DP-phase
+             GCUPS against the ALU-pipe issue rate measured live by tools/dpx_microbench x 64 cells / 12 instructions per
+             packed cell pair; the kernel's own bare-recipe ceiling, the HBM view and the staging rates ride along.
   cpu_baseline / --impl reference
              the reference's own CPU extension path (Aligner::align = SSW, compiled from /root/reference
              into oracle/_ref) on the host cores, bounded sample of the same workload.
@@ -41,6 +40,16 @@ def workload_desc(pairs, read_len):
     return (f"BASELINE configs[1]-shaped extension batch: {pairs} (query,window) pairs per GPU per step, "
             f"{read_len} bp reads, windows read+flanks(0..50) (95%) / mate-rescue windows (5%), 1% substitutions, "
             f"0.2%/bp indel events; cells = sum |q|*|t|")
+
+
+def config_dict(pairs, read_len):
+    """Identical in both arms (the driver compares the dicts); everything arm-specific lives outside `config`."""
+    return {"workload": workload_desc(pairs, read_len), "pairs_per_gpu_per_step": pairs, "read_len": read_len,
+            "scoring": "match 2, mismatch 8, gap open 12, gap extend 1 (strobealign defaults)",
+            "l2": "inputs + direction tiles of one step (> 20 GB) exceed the 126 MB L2; no flush needed",
+            "note": "BASELINE configs[4] (extension microbench) is 10 M pairs of this shape; a step is 1 048 576 of them so "
+                    "that warm-up, the CPU baseline and the extra legs fit a default run (GCUPS is size-normalised; "
+                    "--pairs 10485760 runs the full size)"}
 
 
 def make_batch(pairs, read_len, seed):
@@ -158,21 +167,89 @@ def issue_ceiling():
     except Exception:  # noqa: BLE001
         return None
     best = None
-    dpx = None
+    alu = {}
     for ln in out.splitlines():
         try:
             r = json.loads(ln)
         except ValueError:
             continue
         if r.get("test", "").startswith("SW cell recipe"):
-            if best is None or r["cells_per_clk_per_sm"] > best["cells_per_clk_per_sm"]:
+            if best is None or r["chip_gcups"] > best["chip_gcups"]:
                 best = r
-        if r.get("test") == "VIMNMX3.S16x2":
-            dpx = max(dpx or 0.0, r["warp_instr_per_clk_per_sm"])
-    if best is None:
+        # CUDA-event-timed issue rates of the ALU-pipe DPX instructions (whole chip, warp-instructions per second)
+        if r.get("test") in ("VIMNMX3.S16x2", "VIADDMNMX.S16x2", "LOP3") and "chip_warp_ginstr_per_s" in r:
+            alu[r["test"]] = max(alu.get(r["test"], 0.0), r["chip_warp_ginstr_per_s"])
+    if best is None or "VIADDMNMX.S16x2" not in alu:
         return None
-    best["dpx_warp_instr_per_clk_per_sm"] = dpx
-    return best
+    return {"recipe_chip_gcups": best["chip_gcups"], "alu_warp_ginstr_per_s": alu["VIADDMNMX.S16x2"], "alu_rates": alu}
+
+
+def leg_250bp_indel(device, scratch_gb):
+    """BASELINE configs[3]: 250-bp reads at a 5 % indel-event rate (wide windows, ~30-run CIGARs).  8192 distinct pairs
+    (scalar generator) tiled 16x to 131 072 pairs; resident (CUDA events) and end to end (submit/wait, wall)."""
+    import torch
+    from rabbitsalign_b200 import ExtensionEngine, workload as W
+    from rabbitsalign_b200.ext import RESULT_DTYPE
+    u = W.extension_pairs(8192, seed=44, read_len=250, indel_rate=0.05, max_indel=4, fixed_query_len=False)
+    reps = 16
+    qbuf = np.tile(u.qbuf, reps)
+    tbuf = np.tile(u.tbuf, reps)
+    qoff = np.concatenate([u.qoff[:-1] + k * int(u.qoff[-1]) for k in range(reps)] + [np.array([reps * int(u.qoff[-1])])]).astype(np.int64)
+    toff = np.concatenate([u.toff[:-1] + k * int(u.toff[-1]) for k in range(reps)] + [np.array([reps * int(u.toff[-1])])]).astype(np.int64)
+    cells = float(u.cells) * reps
+    n = u.n * reps
+    eng = ExtensionEngine(device=device, scratch_bytes=scratch_gb << 30)
+    eng.stage_resident(qbuf, qoff, tbuf, toff)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", device))
+    for _ in range(3):
+        eng.run_resident()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        eng.run_resident()
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    res = eng.fetch_resident(n)
+    results = np.zeros(n, dtype=RESULT_DTYPE)
+    eng.submit(qbuf, qoff, tbuf, toff, results); eng.wait()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.submit(qbuf, qoff, tbuf, toff, results); eng.wait()
+    dt = (time.perf_counter() - t0) / 3
+    out = {"pairs": n, "distinct_pairs": u.n, "mean_cigar_runs": float(np.mean(res["n_ops"])),
+           "mean_window": float(np.mean(np.diff(u.toff))), "resident_gcups": cells / (ms * 1e-3) / 1e9,
+           "e2e_gcups_pageable_host": cells / dt / 1e9, "records_equal": bool(results.tobytes() == res.tobytes())}
+    eng.close()
+    return out
+
+
+def pipeline_block(threads):
+    """BASELINE metric (i), end-to-end reads/s: the reference's host pipeline (integration/_build, compiled from the
+    reference by integration/build.sh) with the reference's own GPU path vs this engine, same synthetic FASTQ/FASTA,
+    same threads.  A small job (600 k single-end reads, 20 Mb): process start-up weighs in, so the pipeline's own
+    "Total time mapping" is reported next to the wall clock.  Larger runs: profiles/r2_e2e_*.json."""
+    exe = os.path.join(ROOT, "tools", "e2e_reads_bench.py")
+    bins = ["rabbitsalign_gasalgpu", "rabbitsalign_b200_big", "rabbitsalign_b200_win"]
+    if not all(os.path.exists(os.path.join(ROOT, "integration", "_build", b)) for b in bins[:2]):
+        return None
+    try:
+        r = subprocess.run([sys.executable, exe, "--ref-len", "20000000", "--reads", "600000", "--threads", str(threads),
+                            "--binaries", ",".join(bins)], capture_output=True, text=True, timeout=240)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:  # noqa: BLE001
+        return {"error": str(ex)[:200]}
+    out = {"reads": d["reads"], "ref_len": d["ref_len"], "threads": d["threads"]}
+    for b in bins:
+        if isinstance(d.get(b), dict):
+            out[b] = {k: d[b].get(k) for k in ("wall_s", "mapping_s", "reads_per_s_wall", "reads_per_s_mapping", "sam_md5")}
+    try:
+        out["sam_identical"] = len({out[b]["sam_md5"] for b in bins if b in out}) == 1
+        out["mapping_speedup_vs_reference_gpu_build"] = out[bins[0]]["mapping_s"] / out[bins[1]]["mapping_s"]
+    except Exception:  # noqa: BLE001
+        pass
+    return out
 
 
 def main():
@@ -185,6 +262,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="pairs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the 250-bp leg and the pipeline block")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,9 +282,12 @@ def main():
             "impl": "reference", "metric": METRIC, "value": g, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16/u8 SSE2", "data": "synthetic",
-            "config": {"workload": workload_desc(args.pairs, args.read_len),
-                       "note": "reference CPU path (Aligner::align: SSW striped SW + banded traceback + end bonus) "
-                               "on all host cores; no GPU involved, so the value does not grow with --gpus"},
+            "config": config_dict(args.pairs, args.read_len),
+            "detail": {"note": "reference CPU path (Aligner::align: SSW striped SW + banded traceback + end bonus) on all "
+                               "host cores; no GPU involved, so the value does not grow with --gpus",
+                       "build": "oracle/_ref/libssw_ref_v3.so: the reference's ext/ssw + src/aligner.cpp compiled "
+                                "-O3 -march=x86-64-v3 (the reference's build.sh:49 uses -march=native on its build host; "
+                                "the library is built in the dev container and must run on the GPU box)"},
             "cpu_baseline": {"value": g, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{sample} pairs of the step's batch per step"},
             "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -270,7 +351,8 @@ def main():
     # ---- device-resident leg: `value` ------------------------------------------------------------------
     eng.stage_resident(qbuf, qoff, tbuf, toff)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
-    for _ in range(max(3, args.warmup)):
+    warmup = max(3, args.warmup)  # the timing rules ask for at least three warm-up steps
+    for _ in range(warmup):
         eng.run_resident()
     torch.cuda.synchronize()
     barrier()
@@ -389,23 +471,58 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", tj)))["dram_bytes_per_cell"] * batch.cells / n_dp_launches
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": "fast_dp_kernel<C> (packed s16x2 DP + direction nibbles)",
-                "achieved": hbm_achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": (hbm_achieved / peaks["hbm_gbs"]) if hbm_achieved else None, "traffic": traffic,
-                "algorithmic_bytes_per_launch": dp_bytes / n_dp_launches, "launches_per_step": n_dp_launches,
-                "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                "note": "issue-bound by design (SURVEY 8d): see roofline_issue for the binding ceiling"}
+    # The binding roof of the DP kernel is the integer/DPX issue rate, so that is what `roofline` reports:
+    #   achieved = DP-phase GCUPS (CUDA events around the DP kernels, serialised engine: nothing overlaps them);
+    #   peak     = measured ALU-pipe issue rate (tools/dpx_microbench: VIADDMNMX.S16x2 warp-instructions per second over
+    #              the whole chip, CUDA events, this run) x 64 cells per warp-instruction (32 lanes x s16x2)
+    #              / 12 instructions per packed cell pair.  The 12 is SURVEY 8d's floor: 15 integer ops per cell with
+    #              traceback (1 compare/select, 1 diag add, 3 max for H incl. the 0 floor, 1 shared tmp-GapOE, 2 x (add+max)
+    #              for E'/F', 4 direction predicates, 1 running max); DPX fuses add+max and the 3-way max+relu, leaving
+    #              ~12 instructions for two packed cells.  Recipe-independent: nothing of this kernel enters the peak.
+    #   traffic  = DRAM bytes per DP launch from the ncu --set full capture (bytes per cell x cells of an average launch).
+    kInstrFloor = 12
     ceil = issue_ceiling()
     dp_gcups = batch.cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
-    roofline_issue = None
+    hbm = {"achieved": hbm_achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+           "frac": (hbm_achieved / peaks["hbm_gbs"]) if hbm_achieved else None,
+           "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+           "note": "algorithmic bytes of the DP phase (ASCII in + 4-bit direction tiles + 16-byte end records) per second; "
+                   "far from the HBM roof by design"}
+    # window-staging phase (north_star): the staging is fused into the DP kernel (ASCII -> codes/profiles in shared memory
+    # and registers), so its bytes move at the DP kernel's pace; the dominant stream is the direction tiles going out
+    staging = {"ascii_in_gbs": float(np.sum(ql + tl)) / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
+               "direction_tiles_out_gbs": float(np.sum(ql * tl) / 2) / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
+               "note": "fused into fast_dp_kernel: no separate staging kernel exists; rates = bytes / DP-phase time"}
+    roofline = None
     if ceil and dp_gcups:
-        roofline_issue = {
-            "bound": "int/DPX issue", "achieved": dp_gcups, "peak": ceil["chip_gcups"], "unit": "GCUPS",
-            "frac": dp_gcups / ceil["chip_gcups"],
-            "peak_source": "tools/dpx_microbench, same process tree, bare packed cell recipe on all SMs",
-            "ceiling_cells_per_clk_per_sm": ceil["cells_per_clk_per_sm"],
-            "dpx_warp_instr_per_clk_per_sm": ceil.get("dpx_warp_instr_per_clk_per_sm"),
-            "dp_ms": dp_ms, "tb_ms": tb_ms}
+        peak = ceil["alu_warp_ginstr_per_s"] * 64.0 / kInstrFloor
+        roofline = {"bound": "int/DPX issue", "kernel": "fast_dp_kernel<L,C> (packed s16x2 DP + direction nibbles)",
+                    "achieved": dp_gcups, "peak": peak, "unit": "GCUPS", "frac": dp_gcups / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": dp_bytes / n_dp_launches, "launches_per_step": n_dp_launches,
+                    "peak_source": "tools/dpx_microbench in this run: VIADDMNMX.S16x2 issue rate (CUDA events, whole chip) "
+                                   f"x 64 cells / {kInstrFloor} instructions per packed cell pair (SURVEY 8d)",
+                    "alu_warp_ginstr_per_s": ceil["alu_warp_ginstr_per_s"], "alu_rates_ginstr_per_s": ceil["alu_rates"],
+                    "instr_per_packed_pair_floor": kInstrFloor, "dp_ms": dp_ms, "tb_ms": tb_ms,
+                    "own_recipe_ceiling": {"chip_gcups": ceil["recipe_chip_gcups"], "frac": dp_gcups / ceil["recipe_chip_gcups"],
+                                           "note": "rsa::fast_cell on registers only (no memory, shuffles, skew): loop overhead "
+                                                   "of the kernel, not distance from the hardware"},
+                    "hbm": hbm, "staging": staging}
+    else:
+        roofline = {"bound": "int/DPX issue", "achieved": dp_gcups, "peak": None, "unit": "GCUPS", "frac": None,
+                    "traffic": traffic, "note": "tools/dpx_microbench unavailable: no live ALU issue rate", "hbm": hbm,
+                    "staging": staging}
+
+    # ---- extra legs (rank 0, N=1 only): BASELINE configs[3] and the end-to-end pipeline ----------------------------------
+    leg250 = None
+    pipe = None
+    if n_gpus == 1 and not args.no_extra_legs:
+        try:
+            leg250 = leg_250bp_indel(local_rank, scratch_gb)
+        except Exception as ex:  # noqa: BLE001
+            leg250 = {"error": str(ex)[:200]}
+        eng.close()  # the pipeline binaries need the GPU memory and the host cores
+        eng = None
+        pipe = pipeline_block(cores)
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
     cpu = None
@@ -416,26 +533,28 @@ def main():
                "sample": f"first {sample} pairs of the step's batch, one pass"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
+        "warmup_requested": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s16x2", "data": "synthetic",
-        "config": {"workload": workload_desc(args.pairs, args.read_len), "pairs_per_gpu": batch.n,
-                   "cells_per_gpu_per_step": batch.cells, "l2": "inputs+direction tiles per step (>20 GB) exceed the 126 MB L2",
-                   "pairs_per_s": batch.n * n_gpus / (ms_step * 1e-3),
+        "config": config_dict(args.pairs, args.read_len),
+        "detail": {"cells_per_gpu_per_step": batch.cells, "pairs_per_s": batch.n * n_gpus / (ms_step * 1e-3),
                    "routing": {"packed": st["pairs_fast"], "exact": st["pairs_exact"], "failed": st["pairs_failed"],
                                "redo_last_chunk": st["pairs_redo"]},
                    "resident_equals_e2e_records": same, "records_sane": ok,
                    "slice512_one_worker": {"us_per_call": slice_dt * 1e6, "pairs_per_s": 512 / slice_dt if slice_dt > 0 else None},
-                   "e2e_with_device_align_gpu": aln_stats, "e2e_windows_in_resident_reference": win_stats},
+                   "e2e_with_device_align_gpu": aln_stats, "e2e_windows_in_resident_reference": win_stats,
+                   "leg_250bp_5pct_indel": leg250, "pipeline": pipe},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"],
                 "ms_per_step": dt_max / args.steps * 1e3, "host_plan_ms_per_step": st_e2e["host_plan_ms"]},
         "gpu_launches": int(launches_per_step * args.steps),
-        "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    eng.close()
+    if eng is not None:
+        eng.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

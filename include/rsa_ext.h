@@ -57,6 +57,8 @@ typedef struct {
 } rsa_ext_config_t;
 
 #define RSA_EXT_FLAG_EXACT_ONLY 1 /* route every pair through the exact int32 kernel (testing) */
+#define RSA_EXT_FLAG_HOST_PLAN 4  /* plan every chunk on the host (the round-1 planner); default: batches of >= 4096 pairs
+                                     are planned by device kernels from the raw offset arrays (same records) */
 #define RSA_EXT_FLAG_SERIALIZE 2  /* one stream, no kernel overlap: per-kernel CUDA-event times (dp_ms, tb_ms) are then
                                      clean kernel durations (roofline measurements); slower than the default */
 

@@ -36,6 +36,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_tb.cuh"
 #include "kernels_finish.cuh"
+#include "kernels_plan.cuh"
 
 using namespace rsa;
 
@@ -94,6 +95,12 @@ struct ChunkPlan {
     uint64_t arena_bytes = 0;
     int64_t q_bytes = 0, t_bytes = 0;
     int64_t cells = 0;
+    // device-planned chunks (kernels_plan.cuh): where the planner's inputs and temporaries live in the device blob
+    bool dev = false;
+    size_t off_in_q = 0, off_in_t = 0, off_in_wlen = 0, off_qtab = 0, off_hdr = 0, off_gbytes = 0, off_bsum = 0, off_hist = 0,
+           off_key = 0, off_rank = 0, off_sorted = 0, zero_bytes = 0;
+    int n_group_slots = 0;
+    unsigned int list_base[3] = {0, 0, 0};
 };
 
 struct Slot {
@@ -104,6 +111,7 @@ struct Slot {
     DevBuf d_scratch;                                         // direction tiles, own allocation
     unsigned long long* d_arena_used = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_mid = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_plan = nullptr;  // device planner: offsets copied / planning kernels done
     ChunkPlan plan;
     bool busy = false;
 };
@@ -145,6 +153,13 @@ struct RefBuf {
     }
 };
 
+// per query length, while the device planner's host pass grows a chunk (scan_chunk)
+struct QlenStat {
+    uint32_t count = 0, min4 = 0, max4 = 0;
+    uint64_t sum4 = 0;
+    uint64_t bound = 0;
+};
+
 struct ResidentChunk {
     ChunkPlan plan;
     uint8_t* d_blob = nullptr;
@@ -159,7 +174,7 @@ struct rsa_ext {
     FastConsts fk{};
     bool fast_ok = false;
     int n_sms = 148;
-    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_tb = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_tb = nullptr, s_d2h = nullptr, s_plan = nullptr;
     cudaEvent_t ev_fork = nullptr;  // orders the second DP stream behind what the caller put on the first
     int dp_toggle = 0;              // consecutive chunks alternate between the two DP streams so that the next
                                     // chunk's blocks fill the SMs while the previous kernel's last wave drains
@@ -189,6 +204,7 @@ struct rsa_ext {
     int chunks_enqueued = 0;
     PlanAhead* pa = nullptr;  // created by the first large submit
     bool plan_ahead = false;  // the pending batch is planned by the helper thread
+    bool dev_plan = false;    // the pending batch is planned on the device (kernels_plan.cuh)
     std::unordered_map<int64_t, std::vector<uint8_t>> overflow;
     std::vector<int64_t> retry;  // pairs whose redo found no scratch (status 4): re-run exact-only at wait()
 
@@ -208,6 +224,7 @@ struct rsa_ext {
     std::vector<uint32_t> tmp_list[3];
     std::vector<uint32_t> tmp_sort, tmp_order, tmp_key, tmp_key2;
     std::vector<uint32_t> tmp_count;
+    std::vector<QlenStat> tmp_qstat;
 };
 
 namespace {
@@ -512,6 +529,161 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
 }
 
 
+// ---- device planner, host side -----------------------------------------------------------------------
+//
+// One streaming pass over the chunk's offsets: where the chunk ends (pair / byte caps, direction-scratch budget), how
+// many pairs each kernel family gets and -- per query length -- how many packed candidates there are, which fixes the
+// launch geometry (column classes, group slots) without sorting anything.  The sort, the pairing and every tile offset
+// are computed on the device (kernels_plan.cuh).
+//
+// Scratch budget without knowing the pairing: per query length, with the candidates' 4-row-rounded window lengths
+// sorted t_1 <= ... <= t_m and paired (t_1,t_2), (t_3,t_4), ..., the groups' row counts sum to
+//   sum_k max(t_2k-1, t_2k) <= (sum_i t_i + t_m - t_1) / 2   (+ t_m for a lone last pair),
+// so bytes(q) <= row_bytes(q) * ((sum + max - min + 1) / 2 + max).  Maintained incrementally while the chunk grows.
+constexpr int64_t kDevPlanMinPairs = 16384;  // smaller batches are planned on the host (the planner's nine launches cost
+                                             // more than 13 ns/pair there); RSA_EXT_DEV_PLAN_MIN overrides (tests)
+inline int64_t dev_plan_min_pairs() {
+    static const int64_t v = [] {
+        const char* e = getenv("RSA_EXT_DEV_PLAN_MIN");
+        return e ? (int64_t)atoll(e) : kDevPlanMinPairs;
+    }();
+    return v;
+}
+
+size_t blob_layout_dev(ChunkPlan& plan, int64_t n, int n_group_slots, bool windows) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    plan.off_in_q = take(sizeof(int64_t) * (size_t)(n + 1));
+    plan.off_in_t = take(sizeof(int64_t) * (size_t)(n + 1));
+    plan.off_in_wlen = take(windows ? sizeof(int32_t) * (size_t)n : 0);
+    plan.off_qtab = take(sizeof(PlanQlen) * kPlanQ);
+    plan.off_meta = take(sizeof(PairMeta) * (size_t)n);
+    plan.off_info = take(sizeof(uint32_t) * (size_t)n);
+    plan.off_diroff = take(sizeof(uint64_t) * (size_t)n);
+    plan.off_list = take(sizeof(uint32_t) * (size_t)n);
+    plan.off_groups = take(sizeof(FastGroup) * (size_t)n_group_slots);
+    plan.off_redo = take(sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4));
+    plan.off_key = take(sizeof(uint32_t) * (size_t)n);
+    plan.off_rank = take(sizeof(uint32_t) * (size_t)n);
+    plan.off_sorted = take(sizeof(uint32_t) * (size_t)n);
+    // zeroed before planning, one memset: header, group tile sizes, scan block sums, histogram
+    plan.off_hdr = take(sizeof(PlanHeader));
+    plan.off_gbytes = take(sizeof(uint32_t) * (size_t)n_group_slots);
+    plan.off_bsum = take(sizeof(uint32_t) * kPlanScanBlocks);
+    plan.off_hist = take(sizeof(uint32_t) * kPlanBins);
+    plan.zero_bytes = off - plan.off_hdr;
+    plan.n_group_slots = n_group_slots;
+    plan.blob_bytes = off;
+    return off;
+}
+
+// `qtab` (kPlanQ entries) is filled for the upload.
+int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, PlanQlen* qtab) {
+    const LenTables& LT = len_tables();
+    std::vector<QlenStat>& st = h->tmp_qstat;
+    st.assign(kPlanQ, QlenStat());
+    plan = ChunkPlan();
+    plan.dev = true;
+    int max_tlen_q[kPlanQ];
+    memset(max_tlen_q, 0, sizeof max_tlen_q);
+    const int64_t q0 = in.qoff[lo], t0 = in.win_off ? 0 : in.toff[lo];
+    const int64_t hi_cap = std::min<int64_t>(in.n, lo + std::min<int64_t>(kMaxChunkPairs, in.max_pairs));
+    uint64_t scratch = 0, arena = 0;
+    int64_t cells = 0, hi = lo;
+    int64_t qprev = in.qoff[lo];
+    int64_t tprev = in.win_off ? 0 : in.toff[lo];
+    while (hi < hi_cap) {
+        const int64_t qnext = in.qoff[hi + 1];
+        const int64_t ql = qnext - qprev;
+        int64_t tl, tnext = 0;
+        if (in.win_off) tl = in.win_len[hi];
+        else { tnext = in.toff[hi + 1]; tl = tnext - tprev; }
+        if (ql < 0 || tl < 0) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
+        if (ql > in.max_qlen) {
+            h->err = "read size is too big, " + std::to_string(ql) + " > " + std::to_string(in.max_qlen);
+            return RSA_EXT_ERR_QUERY_LEN;
+        }
+        // what this pair adds to the scratch bound
+        uint64_t add = 0;
+        int route = 0;  // 0 not aligned, 1 packed, 2 exact
+        QlenStat nq;
+        if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
+            if (!in.exact_only && fast_shape_ok((int)ql, (int)tl, in.match)) {
+                route = 1;
+                nq = st[ql];
+                const uint32_t t4 = (uint32_t)((tl + 3) & ~3);
+                if (nq.count == 0) { nq.min4 = nq.max4 = t4; }
+                else { nq.min4 = std::min(nq.min4, t4); nq.max4 = std::max(nq.max4, t4); }
+                nq.count++;
+                nq.sum4 += t4;
+                nq.bound = (uint64_t)LT.fast_row_bytes[ql] * ((nq.sum4 + nq.max4 - nq.min4 + 1) / 2 + nq.max4);
+                add = nq.bound - st[ql].bound;
+            } else {
+                route = 2;
+                add = align_up((size_t)tl * LT.exact_row_bytes_[ql], 16);
+            }
+        }
+        if (hi > lo && (scratch + add + 1024 > in.scratch_cap || qnext - q0 > kMaxChunkSeqBytes ||
+                        (!in.win_off && tnext - t0 > kMaxChunkSeqBytes)))
+            break;
+        scratch += add;
+        cells += ql * tl;
+        if (route == 0) plan.n_failed++;
+        else {
+            arena += (uint64_t)(ql + tl + 1);
+            if (route == 1) {
+                st[ql] = nq;
+                max_tlen_q[ql] = std::max(max_tlen_q[ql], (int)tl);
+                plan.n_fast_pairs++;
+            } else {
+                const int cls = LT.exact_row_bytes_[ql] == 64 ? 0 : (LT.exact_row_bytes_[ql] == 128 ? 1 : 2);
+                plan.n_exact[cls]++;
+                plan.max_tlen_exact[cls] = std::max<int>(plan.max_tlen_exact[cls], (int)tl);
+            }
+        }
+        qprev = qnext;
+        tprev = tnext;
+        ++hi;
+    }
+    const int64_t n = hi - lo;
+    plan.lo = lo; plan.hi = hi; plan.n = n;
+    plan.q_bytes = in.qoff[hi] - q0;
+    plan.t_bytes = in.win_off ? 0 : in.toff[hi] - t0;
+    plan.cells = cells;
+    plan.arena_bytes = arena + 64;
+    plan.scratch_bytes = scratch + 1024;  // upper bound (exact tiles, 256-aligned packed region, 256-aligned redo base)
+    // launch geometry from the per-length counts: classes in increasing |q| (= increasing C within 8 lanes, then 16 lanes),
+    // each padded to whole warps of groups
+    constexpr int kGroupPad = 4;
+    uint32_t pos = 0;
+    int n_groups = 0, cur_C = -1, cur_L = -1;
+    for (int q = 0; q < kPlanQ; ++q) {
+        qtab[q].count = st[q].count;
+        qtab[q].pos_base = pos;
+        qtab[q].group_base = 0;
+        if (st[q].count == 0) continue;
+        const int C = LT.fast_C[q], L = LT.fast_L[q];
+        if (C != cur_C || L != cur_L) {
+            while (n_groups % kGroupPad) ++n_groups;
+            if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
+            plan.fast.push_back({L, C, n_groups, 0, 0});
+            cur_C = C; cur_L = L;
+        }
+        qtab[q].group_base = (uint32_t)n_groups;
+        n_groups += (int)((st[q].count + 1) / 2);
+        pos += st[q].count;
+        plan.fast.back().max_tlen = std::max(plan.fast.back().max_tlen, max_tlen_q[q]);
+    }
+    while (n_groups % kGroupPad) ++n_groups;
+    if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
+    plan.n_fast_classes = (int)plan.fast.size();
+    plan.list_base[0] = 0;
+    plan.list_base[1] = (unsigned)plan.n_exact[0];
+    plan.list_base[2] = (unsigned)(plan.n_exact[0] + plan.n_exact[1]);
+    blob_layout_dev(plan, n, std::max(n_groups, kGroupPad), in.win_off != nullptr);
+    return RSA_EXT_OK;
+}
+
 // ---- launching -------------------------------------------------------------------------------------
 
 struct ChunkDev {
@@ -578,9 +750,10 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
         int max_tlen = 0;
         for (const auto& fc : p.fast) max_tlen = std::max(max_tlen, fc.max_tlen);
         const unsigned long long redo_base = align_up((size_t)p.scratch_bytes, 256);
-        const unsigned long long redo_cap = d.scratch_cap > redo_base ? d.scratch_cap - redo_base : 0ull;
+        const unsigned long long* redo_base_dev =
+            p.dev ? &reinterpret_cast<const PlanHeader*>(d.blob + p.off_hdr)->redo_base : nullptr;
         launch_exact_redo(st, d.q, d.t, meta, diroff, d.scratch, d.ends, redo, redo_list, h->sc, max_tlen, h->n_sms,
-                          redo_base, redo_cap, d.arena_used);
+                          redo_base, d.scratch_cap, redo_base_dev, d.arena_used);
         h->stats.kernel_launches++;
     }
     if (ev) CU_TRY(h, cudaEventRecord(ev[1], st));
@@ -664,6 +837,56 @@ void plan_ahead_finish(rsa_ext* h) {
     h->plan_ahead = false;
 }
 
+// The planning kernels of a device-planned chunk, on their own high-priority stream behind the copy of the offsets:
+// their few small blocks slot in as blocks of the previous chunk's DP kernel retire, while the sequence bytes are still
+// on their way.
+int enqueue_plan_kernels(rsa_ext* h, Slot& s) {
+    const ChunkPlan& p = s.plan;
+    uint8_t* b = s.d_blob.p;
+    cudaStream_t st = h->s_plan;
+    CU_TRY(h, cudaStreamWaitEvent(st, s.ev_in, 0));
+    CU_TRY(h, cudaMemsetAsync(b + p.off_hdr, 0, p.zero_bytes, st));
+    CU_TRY(h, cudaMemsetAsync(b + p.off_groups, 0xFF, sizeof(FastGroup) * (size_t)p.n_group_slots, st));
+    PlanArgs a;
+    a.qoff = reinterpret_cast<const int64_t*>(b + p.off_in_q);
+    a.toff = h->win_off ? nullptr : reinterpret_cast<const int64_t*>(b + p.off_in_t);
+    a.win_off = h->win_off ? reinterpret_cast<const int64_t*>(b + p.off_in_t) : nullptr;
+    a.win_len = h->win_off ? reinterpret_cast<const int32_t*>(b + p.off_in_wlen) : nullptr;
+    a.qtab = reinterpret_cast<const PlanQlen*>(b + p.off_qtab);
+    a.n = (int)p.n;
+    a.max_tlen = h->cfg.max_target_len;
+    a.match = h->sc.match;
+    a.exact_only = ((h->cfg.flags & RSA_EXT_FLAG_EXACT_ONLY) != 0 || !h->fast_ok) ? 1 : 0;
+    for (int c = 0; c < 3; ++c) a.list_base[c] = p.list_base[c];
+    a.meta = reinterpret_cast<PairMeta*>(b + p.off_meta);
+    a.info = reinterpret_cast<uint32_t*>(b + p.off_info);
+    a.diroff = reinterpret_cast<uint64_t*>(b + p.off_diroff);
+    a.list = reinterpret_cast<uint32_t*>(b + p.off_list);
+    a.groups = reinterpret_cast<FastGroup*>(b + p.off_groups);
+    a.key = reinterpret_cast<uint32_t*>(b + p.off_key);
+    a.rank = reinterpret_cast<uint32_t*>(b + p.off_rank);
+    a.sorted = reinterpret_cast<uint32_t*>(b + p.off_sorted);
+    a.gbytes = reinterpret_cast<uint32_t*>(b + p.off_gbytes);
+    a.hist = reinterpret_cast<uint32_t*>(b + p.off_hist);
+    a.bsum = reinterpret_cast<uint32_t*>(b + p.off_bsum);
+    a.hdr = reinterpret_cast<PlanHeader*>(b + p.off_hdr);
+    const unsigned pair_blocks = (unsigned)((p.n + kPlanThreads - 1) / kPlanThreads);
+    plan_classify<<<pair_blocks, kPlanThreads, 0, st>>>(a);
+    h->stats.kernel_launches++;
+    if (p.n_fast_pairs > 0) {
+        plan_bin_sums<<<kPlanScanBlocks, 256, 0, st>>>(a);
+        plan_bin_scan<<<kPlanScanBlocks, 256, 0, st>>>(a);
+        plan_scatter<<<pair_blocks, kPlanThreads, 0, st>>>(a);
+        plan_groups<<<(unsigned)((p.n_fast_pairs + kPlanThreads - 1) / kPlanThreads), kPlanThreads, 0, st>>>(a, (int)p.n_fast_pairs);
+        h->stats.kernel_launches += 4;
+    }
+    plan_offsets<<<1, 1024, 0, st>>>(a, p.n_group_slots);
+    h->stats.kernel_launches++;
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(s.ev_plan, st));
+    return RSA_EXT_OK;
+}
+
 int enqueue_chunk(rsa_ext* h, Slot& s) {
     const auto t_plan0 = std::chrono::steady_clock::now();
     const uint8_t* h_blob = nullptr;
@@ -677,6 +900,14 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
         if (e.rc) return e.rc;
         s.plan = e.plan;
         h_blob = e.blob.p;  // stays untouched until this chunk retires (retire_chunk releases the entry)
+    } else if (h->dev_plan) {
+        PlanInput in = pending_plan_input(h);
+        in.max_pairs = ramp_pairs(false, h->chunks_enqueued);
+        if ((rc = ensure_pin(h, s.h_blob, sizeof(PlanQlen) * kPlanQ))) return rc;
+        rc = scan_chunk(h, in, h->next_pair, s.plan, reinterpret_cast<PlanQlen*>(s.h_blob.p));
+        h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
+        if (rc) return rc;
+        h_blob = s.h_blob.p;
     } else {
         PlanInput in = pending_plan_input(h);
         in.max_pairs = ramp_pairs(false, h->chunks_enqueued);
@@ -703,16 +934,34 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     if ((rc = ensure_slot(h, s, need))) return rc;
     lap("device buffers");
 
-    CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, h_blob, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    if (p.dev) {
+        // device planner: the chunk's raw offsets (16 B/pair, straight from the caller's arrays) + the per-length table
+        const size_t n1 = (size_t)p.n + 1;
+        CU_TRY(h, cudaMemcpyAsync(s.d_blob.p + p.off_in_q, h->qoff + p.lo, sizeof(int64_t) * n1, cudaMemcpyHostToDevice, h->s_h2d));
+        if (h->win_off) {
+            CU_TRY(h, cudaMemcpyAsync(s.d_blob.p + p.off_in_t, h->win_off + p.lo, sizeof(int64_t) * (size_t)p.n, cudaMemcpyHostToDevice, h->s_h2d));
+            CU_TRY(h, cudaMemcpyAsync(s.d_blob.p + p.off_in_wlen, h->win_len + p.lo, sizeof(int32_t) * (size_t)p.n, cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            CU_TRY(h, cudaMemcpyAsync(s.d_blob.p + p.off_in_t, h->toff + p.lo, sizeof(int64_t) * n1, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        CU_TRY(h, cudaMemcpyAsync(s.d_blob.p + p.off_qtab, h_blob, sizeof(PlanQlen) * kPlanQ, cudaMemcpyHostToDevice, h->s_h2d));
+        CU_TRY(h, cudaEventRecord(s.ev_in, h->s_h2d));
+        h->stats.h2d_bytes += (int64_t)(sizeof(int64_t) * n1 * 2 + sizeof(PlanQlen) * kPlanQ);
+        if ((rc = enqueue_plan_kernels(h, s))) return rc;
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(s.d_blob.p, h_blob, p.blob_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        h->stats.h2d_bytes += (int64_t)p.blob_bytes;
+    }
     if (p.q_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_q.p, h->qbuf + h->qoff[p.lo], (size_t)p.q_bytes, cudaMemcpyHostToDevice, h->s_h2d));
     if (p.t_bytes) CU_TRY(h, cudaMemcpyAsync(s.d_t.p, h->tbuf + h->toff[p.lo], (size_t)p.t_bytes, cudaMemcpyHostToDevice, h->s_h2d));  // (0 in window form)
     CU_TRY(h, cudaEventRecord(s.ev_h2d, h->s_h2d));
-    h->stats.h2d_bytes += (int64_t)p.blob_bytes + p.q_bytes + p.t_bytes;
+    h->stats.h2d_bytes += p.q_bytes + p.t_bytes;
     lap("h2d enqueue");
 
     const bool serial = (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) != 0;
     cudaStream_t s_dp = (!serial && (h->dp_toggle++ & 1)) ? h->s_comp2 : h->s_comp;
     CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_h2d, 0));
+    if (p.dev) CU_TRY(h, cudaStreamWaitEvent(s_dp, s.ev_plan, 0));
     const uint8_t* d_targets = h->win_off ? h->ref->d : s.d_t.p;  // window form: meta.toff indexes the resident reference
     ChunkDev d{s.d_blob.p, s.d_q.p, d_targets, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
@@ -836,7 +1085,8 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     h->pending = true;
     std::unique_lock<std::mutex> cold(g_cold_mutex, std::defer_lock);
     if (!h->warmed) cold.lock();
-    if (n > kPlanAheadMinPairs) {
+    h->dev_plan = n >= dev_plan_min_pairs() && (h->cfg.flags & RSA_EXT_FLAG_HOST_PLAN) == 0;
+    if (n > kPlanAheadMinPairs && !h->dev_plan) {
         if (!h->pa) {
             h->pa = new PlanAhead();
             h->pa->th = std::thread(plan_ahead_main, h);
@@ -945,12 +1195,19 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
         if ((e = cudaStreamCreateWithPriority(&h->s_tb, cudaStreamNonBlocking, (pe && atoi(pe) == 0) ? prio_lo : prio_hi)) != cudaSuccess) return fail("stream", e);
     }
     if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
-    lap("6 streams");
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((e = cudaStreamCreateWithPriority(&h->s_plan, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("stream", e);
+    }
+    lap("7 streams");
     for (Slot& s : h->slots) {
         if ((e = cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+        if ((e = cudaEventCreateWithFlags(&s.ev_plan, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
         if ((e = cudaHostAlloc(&s.h_arena_used, kSlotCounters * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
         if ((e = cudaMalloc(&s.d_arena_used, kSlotCounters * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     }
@@ -982,6 +1239,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->s_comp2) cudaStreamSynchronize(h->s_comp2);
     if (h->s_tb) cudaStreamSynchronize(h->s_tb);
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+    if (h->s_plan) cudaStreamSynchronize(h->s_plan);
     if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
     for (Slot& s : h->slots) {
         for (DevBuf* b : {&s.d_slab, &s.d_scratch})
@@ -993,6 +1251,8 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
         if (s.ev_mid) cudaEventDestroy(s.ev_mid);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_plan) cudaEventDestroy(s.ev_plan);
     }
     h->ref.reset();
     for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
@@ -1006,6 +1266,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_tb) cudaStreamDestroy(h->s_tb);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->s_plan) cudaStreamDestroy(h->s_plan);
     delete h;
 }
 

@@ -426,8 +426,12 @@ __global__ void __launch_bounds__(32 * kRedoWarpsPerBlock)
 exact_redo_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                   const PairMeta* __restrict__ meta, uint64_t* __restrict__ diroff, uint8_t* __restrict__ scratch,
                   DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo, const uint32_t* __restrict__ redo_list,
-                  Scoring sc, int tlen_pad, unsigned long long redo_base, unsigned long long redo_cap,
-                  unsigned long long* __restrict__ counters) {
+                  Scoring sc, int tlen_pad, unsigned long long redo_base, unsigned long long scratch_cap,
+                  const unsigned long long* __restrict__ redo_base_dev, unsigned long long* __restrict__ counters) {
+    // the redo head-room starts behind the planned tiles: known to the host (host planner) or left in the chunk's
+    // PlanHeader by plan_offsets (device planner)
+    if (redo_base_dev) redo_base = *redo_base_dev;
+    const unsigned long long redo_cap = scratch_cap > redo_base ? scratch_cap - redo_base : 0ull;
     extern __shared__ uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* tn = smem + warp * tlen_pad;
@@ -545,11 +549,11 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
 inline void launch_exact_redo(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                               uint64_t* diroff, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
                               const uint32_t* redo_list, const Scoring& sc, int max_tlen, int n_sms,
-                              unsigned long long redo_base, unsigned long long redo_cap,
-                              unsigned long long* counters) {
+                              unsigned long long redo_base, unsigned long long scratch_cap,
+                              const unsigned long long* redo_base_dev, unsigned long long* counters) {
     const int tlen_pad = (max_tlen + 15) & ~15;
     exact_redo_kernel<<<n_sms * 2, 32 * kRedoWarpsPerBlock, (size_t)tlen_pad * kRedoWarpsPerBlock, st>>>(
-        q, t, meta, diroff, scratch, ends, redo, redo_list, sc, tlen_pad, redo_base, redo_cap, counters);
+        q, t, meta, diroff, scratch, ends, redo, redo_list, sc, tlen_pad, redo_base, scratch_cap, redo_base_dev, counters);
 }
 
 }  // namespace rsa

@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(_HERE, "librsa_ext.so")
 RLE_INLINE = 40
 FLAG_EXACT_ONLY = 1
 FLAG_SERIALIZE = 2
+FLAG_HOST_PLAN = 4
 
 RESULT_DTYPE = np.dtype([
     ("score", "<i4"), ("query_start", "<i4"), ("query_end", "<i4"), ("ref_start", "<i4"),
@@ -163,10 +164,11 @@ class ExtensionEngine:
 
     def __init__(self, device: int = 0, match: int = 2, mismatch: int = 8, gap_open: int = 12,
                  gap_extend: int = 1, max_query_len: int = 500, max_target_len: int = 2000,
-                 exact_only: bool = False, scratch_bytes: int = 0, serialize: bool = False):
+                 exact_only: bool = False, scratch_bytes: int = 0, serialize: bool = False, host_plan: bool = False):
         self.lib = load_library()
         self.cfg = Config(device, max_query_len, max_target_len, match, mismatch, gap_open, gap_extend,
-                          (FLAG_EXACT_ONLY if exact_only else 0) | (FLAG_SERIALIZE if serialize else 0), scratch_bytes)
+                          (FLAG_EXACT_ONLY if exact_only else 0) | (FLAG_SERIALIZE if serialize else 0) |
+                          (FLAG_HOST_PLAN if host_plan else 0), scratch_bytes)
         h = C.c_void_p()
         rc = self.lib.rsa_ext_create(C.byref(self.cfg), C.byref(h))
         if rc != 0:

@@ -22,3 +22,7 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # both arms print the same `config` dict (the driver compares them): everything arm-specific is outside it
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_dict(2048, 150)
