@@ -92,7 +92,8 @@ const char *rsa_ext_last_error(const rsa_ext_t *h); /* h may be NULL: error of t
 /* gasal_host_batch_fill x 2n + gasal_op_fill + gasal_aln_async (src/gasal2_ssw.cpp:114-153,
  * GASAL2/src/host_batch.cpp:79-153, GASAL2/src/gasal_align.cu:29-307).  Asynchronous: returns once the
  * copies and kernels are enqueued.  Pair i is qbuf[qoff[i] .. qoff[i+1]) against tbuf[toff[i] ..
- * toff[i+1]) (raw ASCII, any case; bases are compared on `byte & 0xF` with 0xE as the zero-scoring
+ * toff[i+1]) (raw ASCII, any case; batches of >= 16384 pairs are validated chunk by chunk while they run, so an
+ * invalid pair (query longer than max_query_len, offsets not monotone) may be reported by rsa_ext_wait instead; bases are compared on `byte & 0xF` with 0xE as the zero-scoring
  * wildcard, GASAL2/src/kernels/pack_rc_seqs.h:13-53, gasal_kernels.h:48-51).  Buffers must stay valid
  * until rsa_ext_wait returns; pinned buffers are copied without staging. */
 int rsa_ext_submit(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff, const char *tbuf,
@@ -202,6 +203,11 @@ int rsa_ext_version(void);
  * in/out: timing repetitions -> mean ns per plan). */
 int rsa_ext_plan_debug(int64_t n, const int64_t *qoff, const int64_t *toff, int64_t scratch_cap, int exact_only,
                        int64_t *out);
+
+/* Same for the host pass of the device planner (batches of >= 16384 pairs: the host only counts pairs per query length
+ * and cuts the chunk; sorting, pairing and tile offsets are computed by kernels).  out[4] = group slots, out[5] = the
+ * scratch bound. */
+int rsa_ext_scan_debug(int64_t n, const int64_t *qoff, const int64_t *toff, int64_t scratch_cap, int64_t *out);
 
 /* Number of usable CUDA devices (0 without a driver/GPU): lets a host pipeline spread its workers over the
  * GPUs of one box (the reference is single-device, src/gasal2_ssw.cpp:34). */

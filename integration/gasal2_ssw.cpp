@@ -263,7 +263,9 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
     int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
     if (rc != RSA_EXT_OK) die("rsa_ext_submit_ptrs", w.h);
-    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    rc = rsa_ext_wait(w.h);
+    if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);  // (large batches are validated chunk by chunk)
+    if (rc != RSA_EXT_OK) die("rsa_ext_wait", w.h);
     unpack_results(w, n, gasal_results, text_free, end_bonus);
 }
 
@@ -334,7 +336,9 @@ void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_r
     int rc = rsa_ext_submit_ref_windows(w.h, (int64_t)n, w.qcat.data(), w.qoff.data(), w.woff.data(), w.wlen.data(), w.res.data());
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
     if (rc != RSA_EXT_OK) die("rsa_ext_submit_ref_windows", w.h);
-    if (rsa_ext_wait(w.h) != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    rc = rsa_ext_wait(w.h);
+    if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
+    if (rc != RSA_EXT_OK) die("rsa_ext_wait", w.h);
     unpack_results(w, n, gasal_results, text_free, end_bonus);
 }
 #endif  // RSA_EXT_WINDOWS

@@ -153,13 +153,6 @@ struct RefBuf {
     }
 };
 
-// per query length, while the device planner's host pass grows a chunk (scan_chunk)
-struct QlenStat {
-    uint32_t count = 0, min4 = 0, max4 = 0;
-    uint64_t sum4 = 0;
-    uint64_t bound = 0;
-};
-
 struct ResidentChunk {
     ChunkPlan plan;
     uint8_t* d_blob = nullptr;
@@ -224,7 +217,6 @@ struct rsa_ext {
     std::vector<uint32_t> tmp_list[3];
     std::vector<uint32_t> tmp_sort, tmp_order, tmp_key, tmp_key2;
     std::vector<uint32_t> tmp_count;
-    std::vector<QlenStat> tmp_qstat;
 };
 
 namespace {
@@ -313,6 +305,7 @@ struct PlanInput {
     // reference; `toff`/`tbuf` are unused then and no window bytes travel
     const int64_t* win_off = nullptr;
     const int32_t* win_len = nullptr;
+    int64_t ref_len = 0;
     int64_t t_start(int64_t i) const { return win_off ? win_off[i] : toff[i]; }
     int64_t t_len(int64_t i) const { return win_off ? (int64_t)win_len[i] : toff[i + 1] - toff[i]; }
 };
@@ -580,88 +573,104 @@ size_t blob_layout_dev(ChunkPlan& plan, int64_t n, int n_group_slots, bool windo
 // `qtab` (kPlanQ entries) is filled for the upload.
 int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, PlanQlen* qtab) {
     const LenTables& LT = len_tables();
-    std::vector<QlenStat>& st = h->tmp_qstat;
-    st.assign(kPlanQ, QlenStat());
     plan = ChunkPlan();
     plan.dev = true;
-    int max_tlen_q[kPlanQ];
-    memset(max_tlen_q, 0, sizeof max_tlen_q);
+    // per-|q| accumulators of the packed candidates; the bound is kept in HALF-row units:
+    //   N(q) = sum4 + 3 * max4 - min4 + 1  >=  2 * (rows of all groups of this |q|)      (see above)
+    uint32_t cnt[kPlanQ], mn4[kPlanQ], mx4[kPlanQ];
+    memset(cnt, 0, sizeof cnt);
+    memset(mx4, 0, sizeof mx4);
     const int64_t q0 = in.qoff[lo], t0 = in.win_off ? 0 : in.toff[lo];
     const int64_t hi_cap = std::min<int64_t>(in.n, lo + std::min<int64_t>(kMaxChunkPairs, in.max_pairs));
-    uint64_t scratch = 0, arena = 0;
-    int64_t cells = 0, hi = lo;
+    const uint64_t cap2 = in.scratch_cap > 2048 ? 2 * ((uint64_t)in.scratch_cap - 2048) : 0;  // budget in half-row bytes
+    const int64_t fast_tmax = std::min<int64_t>(in.max_tlen, kFastMaxTlen);
+    const int64_t fast_qmax = in.exact_only ? -1 : std::min<int64_t>(kFastMaxQlen, 1023 / std::max(1, in.match));
+    uint64_t scratch2 = 0, arena = 0;
+    int64_t cells = 0, hi = lo, n_fast = 0, n_failed = 0;
     int64_t qprev = in.qoff[lo];
     int64_t tprev = in.win_off ? 0 : in.toff[lo];
-    while (hi < hi_cap) {
+    int64_t cur_q = -1;
+    uint32_t c_cnt = 0, c_mn = 0, c_mx = 0, c_rowb = 0;
+    for (; hi < hi_cap; ++hi) {
         const int64_t qnext = in.qoff[hi + 1];
         const int64_t ql = qnext - qprev;
         int64_t tl, tnext = 0;
-        if (in.win_off) tl = in.win_len[hi];
-        else { tnext = in.toff[hi + 1]; tl = tnext - tprev; }
+        if (in.win_off) {
+            tl = in.win_len[hi];
+            const int64_t wo = in.win_off[hi];
+            if (wo < 0 || tl < 0 || wo + tl > in.ref_len) {
+                h->err = "window " + std::to_string(hi) + " lies outside the resident reference";
+                return RSA_EXT_ERR_ARG;
+            }
+        } else {
+            tnext = in.toff[hi + 1];
+            tl = tnext - tprev;
+        }
         if (ql < 0 || tl < 0) { h->err = "offsets are not monotone"; return RSA_EXT_ERR_ARG; }
         if (ql > in.max_qlen) {
-            h->err = "read size is too big, " + std::to_string(ql) + " > " + std::to_string(in.max_qlen);
+            h->err = "gasal2 : read size is too big, " + std::to_string(ql) + " > " + std::to_string(in.max_qlen);
             return RSA_EXT_ERR_QUERY_LEN;
         }
-        // what this pair adds to the scratch bound
-        uint64_t add = 0;
-        int route = 0;  // 0 not aligned, 1 packed, 2 exact
-        QlenStat nq;
-        if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
-            if (!in.exact_only && fast_shape_ok((int)ql, (int)tl, in.match)) {
-                route = 1;
-                nq = st[ql];
-                const uint32_t t4 = (uint32_t)((tl + 3) & ~3);
-                if (nq.count == 0) { nq.min4 = nq.max4 = t4; }
-                else { nq.min4 = std::min(nq.min4, t4); nq.max4 = std::max(nq.max4, t4); }
-                nq.count++;
-                nq.sum4 += t4;
-                nq.bound = (uint64_t)LT.fast_row_bytes[ql] * ((nq.sum4 + nq.max4 - nq.min4 + 1) / 2 + nq.max4);
-                add = nq.bound - st[ql].bound;
-            } else {
-                route = 2;
-                add = align_up((size_t)tl * LT.exact_row_bytes_[ql], 16);
+        if (qnext - q0 > kMaxChunkSeqBytes || tnext - t0 > kMaxChunkSeqBytes) { if (hi > lo) break; }
+        if (ql >= kFastMinQlen && ql <= fast_qmax && tl >= 1 && tl <= fast_tmax) {
+            // packed candidate: what it adds to the bound.  The accumulators of the current |q| live in registers
+            // (batches are runs of equal read lengths); they go back to the tables when |q| changes.
+            if (ql != cur_q) {
+                if (cur_q >= 0) { cnt[cur_q] = c_cnt; mn4[cur_q] = c_mn; mx4[cur_q] = c_mx; }
+                cur_q = ql;
+                c_cnt = cnt[ql]; c_mn = mn4[ql]; c_mx = mx4[ql];
+                c_rowb = LT.fast_row_bytes[ql];
             }
-        }
-        if (hi > lo && (scratch + add + 1024 > in.scratch_cap || qnext - q0 > kMaxChunkSeqBytes ||
-                        (!in.win_off && tnext - t0 > kMaxChunkSeqBytes)))
-            break;
-        scratch += add;
-        cells += ql * tl;
-        if (route == 0) plan.n_failed++;
-        else {
+            const uint32_t t4 = (uint32_t)((tl + 3) & ~3);
+            uint64_t add2;
+            uint32_t nmn = t4, nmx = t4;
+            if (c_cnt == 0) add2 = (uint64_t)c_rowb * (3ull * t4 + 1);
+            else {
+                nmn = std::min(c_mn, t4);
+                nmx = std::max(c_mx, t4);
+                add2 = (uint64_t)c_rowb * (t4 + 3ull * (nmx - c_mx) + (c_mn - nmn));
+            }
+            if (scratch2 + add2 > cap2 && hi > lo) break;
+            scratch2 += add2;
+            ++c_cnt; c_mn = nmn; c_mx = nmx;
+            ++n_fast;
             arena += (uint64_t)(ql + tl + 1);
-            if (route == 1) {
-                st[ql] = nq;
-                max_tlen_q[ql] = std::max(max_tlen_q[ql], (int)tl);
-                plan.n_fast_pairs++;
-            } else {
-                const int cls = LT.exact_row_bytes_[ql] == 64 ? 0 : (LT.exact_row_bytes_[ql] == 128 ? 1 : 2);
-                plan.n_exact[cls]++;
-                plan.max_tlen_exact[cls] = std::max<int>(plan.max_tlen_exact[cls], (int)tl);
-            }
+        } else if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
+            const uint32_t rb = LT.exact_row_bytes_[ql];
+            const uint64_t add2 = 2 * (uint64_t)align_up((size_t)tl * rb, 16);
+            if (scratch2 + add2 > cap2 && hi > lo) break;
+            scratch2 += add2;
+            const int cls = rb == 64 ? 0 : (rb == 128 ? 1 : 2);
+            plan.n_exact[cls]++;
+            plan.max_tlen_exact[cls] = std::max<int>(plan.max_tlen_exact[cls], (int)tl);
+            arena += (uint64_t)(ql + tl + 1);
+        } else {
+            ++n_failed;
         }
+        cells += ql * tl;
         qprev = qnext;
         tprev = tnext;
-        ++hi;
     }
+    if (cur_q >= 0) { cnt[cur_q] = c_cnt; mn4[cur_q] = c_mn; mx4[cur_q] = c_mx; }
     const int64_t n = hi - lo;
     plan.lo = lo; plan.hi = hi; plan.n = n;
+    plan.n_fast_pairs = n_fast;
+    plan.n_failed = n_failed;
     plan.q_bytes = in.qoff[hi] - q0;
     plan.t_bytes = in.win_off ? 0 : in.toff[hi] - t0;
     plan.cells = cells;
     plan.arena_bytes = arena + 64;
-    plan.scratch_bytes = scratch + 1024;  // upper bound (exact tiles, 256-aligned packed region, 256-aligned redo base)
+    plan.scratch_bytes = (scratch2 + 1) / 2 + 2048;  // upper bound (+ the 256-byte alignments of the packed region / redo base)
     // launch geometry from the per-length counts: classes in increasing |q| (= increasing C within 8 lanes, then 16 lanes),
     // each padded to whole warps of groups
     constexpr int kGroupPad = 4;
     uint32_t pos = 0;
     int n_groups = 0, cur_C = -1, cur_L = -1;
     for (int q = 0; q < kPlanQ; ++q) {
-        qtab[q].count = st[q].count;
+        qtab[q].count = cnt[q];
         qtab[q].pos_base = pos;
         qtab[q].group_base = 0;
-        if (st[q].count == 0) continue;
+        if (cnt[q] == 0) continue;
         const int C = LT.fast_C[q], L = LT.fast_L[q];
         if (C != cur_C || L != cur_L) {
             while (n_groups % kGroupPad) ++n_groups;
@@ -670,9 +679,9 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
             cur_C = C; cur_L = L;
         }
         qtab[q].group_base = (uint32_t)n_groups;
-        n_groups += (int)((st[q].count + 1) / 2);
-        pos += st[q].count;
-        plan.fast.back().max_tlen = std::max(plan.fast.back().max_tlen, max_tlen_q[q]);
+        n_groups += (int)((cnt[q] + 1) / 2);
+        pos += cnt[q];
+        plan.fast.back().max_tlen = std::max(plan.fast.back().max_tlen, (int)mx4[q]);  // (rounded up to 4 rows)
     }
     while (n_groups % kGroupPad) ++n_groups;
     if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
@@ -782,6 +791,7 @@ PlanInput pending_plan_input(const rsa_ext* h) {
     in.match = h->sc.match;
     in.win_off = h->win_off;
     in.win_len = h->win_len;
+    in.ref_len = h->ref ? h->ref->len : 0;
     return in;
 }
 
@@ -789,6 +799,14 @@ PlanInput pending_plan_input(const rsa_ext* h) {
 // Inline planning shares the caller's thread with enqueue/retire (16k, 32k, 64k); the plan-ahead thread runs
 // continuously, so its ramp only has to keep (plan + H2D) of chunk k+1 below the GPU time of chunk k.
 int64_t ramp_pairs(bool plan_ahead, long chunk_index) {
+    static const std::vector<int64_t> knob = [] {  // RSA_EXT_RAMP="16384,65536": experiment knob
+        std::vector<int64_t> v;
+        if (const char* e = getenv("RSA_EXT_RAMP")) {
+            for (const char* p = e; *p;) { v.push_back(atoll(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+        }
+        return v;
+    }();
+    if (!knob.empty()) return chunk_index < (long)knob.size() ? std::max<int64_t>(256, knob[chunk_index]) : kMaxChunkPairs;
     if (plan_ahead) {
         static const int64_t r[] = {16384, 24576, 40960, 65536};
         return chunk_index < 4 ? r[chunk_index] : kMaxChunkPairs;
@@ -1051,9 +1069,12 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     if (h->pending) { h->err = "a batch is already pending"; return RSA_EXT_ERR_STATE; }
     const bool windows = win_off != nullptr;
     if (n <= 0 || !qbuf || !qoff || !results || (windows ? !win_len : (!tbuf || !toff))) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    // Large batches are validated chunk by chunk by the device planner's host pass (scan_chunk): a separate pass over a
+    // million offsets would delay the first kernel by 1-2 ms.  An invalid pair then fails the batch at rsa_ext_wait.
+    const bool dev_plan = n >= dev_plan_min_pairs() && (h->cfg.flags & RSA_EXT_FLAG_HOST_PLAN) == 0;
     if (windows) {
         if (!h->ref) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
-        for (int64_t i = 0; i < n; ++i)
+        for (int64_t i = 0; i < (dev_plan ? 0 : n); ++i)
             if (win_len[i] < 0 || win_off[i] < 0 || win_off[i] + win_len[i] > h->ref->len) {
                 h->err = "window " + std::to_string(i) + " lies outside the resident reference";
                 return RSA_EXT_ERR_ARG;
@@ -1061,7 +1082,7 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     }
     CU_TRY(h, cudaSetDevice(h->cfg.device));
     // the reference validates the whole slice before touching the GPU (gasal2_ssw.cpp:74-89)
-    for (int64_t i = 0; i < n; ++i) {
+    for (int64_t i = 0; i < (dev_plan ? 0 : n); ++i) {
         const int64_t ql = qoff[i + 1] - qoff[i];
         if (ql > h->cfg.max_query_len) {
             h->err = "gasal2 : read size is too big, " + std::to_string(ql) + " > " + std::to_string(h->cfg.max_query_len);
@@ -1085,7 +1106,7 @@ int submit_core_ex(rsa_ext* h, int64_t n, const char* qbuf, const int64_t* qoff,
     h->pending = true;
     std::unique_lock<std::mutex> cold(g_cold_mutex, std::defer_lock);
     if (!h->warmed) cold.lock();
-    h->dev_plan = n >= dev_plan_min_pairs() && (h->cfg.flags & RSA_EXT_FLAG_HOST_PLAN) == 0;
+    h->dev_plan = dev_plan;
     if (n > kPlanAheadMinPairs && !h->dev_plan) {
         if (!h->pa) {
             h->pa = new PlanAhead();
@@ -1706,5 +1727,26 @@ extern "C" int rsa_ext_plan_debug(int64_t n, const int64_t* qoff, const int64_t*
     for (auto& fc : p.fast) groups += fc.n_groups;
     out[0] = p.n; out[1] = p.n_fast_pairs; out[2] = p.n_exact[0] + p.n_exact[1] + p.n_exact[2];
     out[3] = p.n_failed; out[4] = groups; out[5] = (int64_t)p.scratch_bytes; out[6] = p.n_fast_classes;
+    return RSA_EXT_OK;
+}
+
+// Host-only probe of the device planner's host pass (scan_chunk; no CUDA call): out[0]=pairs in the first chunk,
+// [1]=packed candidates, [2]=exact pairs, [3]=not aligned, [4]=group slots, [5]=scratch bound, [6]=column classes,
+// [7] in/out: repetitions -> mean ns per pass.
+extern "C" int rsa_ext_scan_debug(int64_t n, const int64_t* qoff, const int64_t* toff, int64_t scratch_cap, int64_t* out) {
+    rsa_ext h;
+    PlanInput in{n, qoff, toff, nullptr, nullptr, 500, 2000, (size_t)scratch_cap, false};
+    ChunkPlan p;
+    std::vector<PlanQlen> qtab(kPlanQ);
+    int rc = scan_chunk(&h, in, 0, p, qtab.data());
+    if (rc) return rc;
+    if (out[7] > 0) {
+        const int reps = (int)out[7];
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r) scan_chunk(&h, in, 0, p, qtab.data());
+        out[7] = (int64_t)(std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / reps);
+    }
+    out[0] = p.n; out[1] = p.n_fast_pairs; out[2] = p.n_exact[0] + p.n_exact[1] + p.n_exact[2];
+    out[3] = p.n_failed; out[4] = p.n_group_slots; out[5] = (int64_t)p.scratch_bytes; out[6] = p.n_fast_classes;
     return RSA_EXT_OK;
 }

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "rsa_ext_poll", "rsa_ext_wait", "rsa_ext_rle_overflow", "rsa_ext_rle_to_text",
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
-    "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows", "rsa_ext_share_reference",
+    "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows", "rsa_ext_share_reference", "rsa_ext_scan_debug",
 ]
 
 _lib = None
@@ -114,6 +114,8 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_request_alninfo.restype = C.c_int
     lib.rsa_ext_plan_debug.argtypes = [i64, vp, vp, i64, C.c_int, vp]
     lib.rsa_ext_plan_debug.restype = C.c_int
+    lib.rsa_ext_scan_debug.argtypes = [i64, vp, vp, i64, vp]
+    lib.rsa_ext_scan_debug.restype = C.c_int
     lib.rsa_ext_reserve.argtypes = [vp, i64, i32, i32]
     lib.rsa_ext_reserve.restype = C.c_int
     lib.rsa_ext_set_reference.argtypes = [vp, vp, i64]
@@ -337,4 +339,16 @@ def plan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, e
     if rc != 0:
         raise ExtensionError(rc, "plan_debug failed")
     keys = ["pairs", "fast_pairs", "exact_pairs", "failed", "groups", "scratch_bytes", "fast_classes", "plan_ns"]
+    return dict(zip(keys, out.tolist()))
+
+
+def scan_debug(qoff: np.ndarray, toff: np.ndarray, scratch_cap: int = 1 << 32, time_reps: int = 0) -> dict:
+    """Host pass of the device planner (no CUDA call): chunk cut, routing counts, launch geometry, scratch bound."""
+    lib = load_library()
+    out = np.zeros(8, np.int64)
+    out[7] = time_reps
+    rc = lib.rsa_ext_scan_debug(len(qoff) - 1, qoff.ctypes.data, toff.ctypes.data, scratch_cap, out.ctypes.data)
+    if rc != 0:
+        raise ExtensionError(rc, "scan_debug failed")
+    keys = ["pairs", "fast_pairs", "exact_pairs", "failed", "group_slots", "scratch_bound", "fast_classes", "scan_ns"]
     return dict(zip(keys, out.tolist()))

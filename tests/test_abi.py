@@ -78,3 +78,32 @@ def test_planner_chunks_by_scratch_budget():
     full = ext.plan_debug(b.qoff, b.toff)
     small = ext.plan_debug(b.qoff, b.toff, scratch_cap=full["scratch_bytes"] // 3)
     assert 0 < small["pairs"] < 300 and small["scratch_bytes"] <= full["scratch_bytes"] // 3 + 65536
+
+
+def test_device_planner_host_pass_agrees_with_host_planner():
+    """The host pass of the device planner (chunk cut, routing counts, group slots) against the full host planner on the
+    same batch; its scratch bound must cover what the host planner lays out and stay within a few percent of it."""
+    b = W.extension_pairs(3000, seed=6, fixed_query_len=False, indel_rate=0.01)
+    hp = ext.plan_debug(b.qoff, b.toff)
+    sp = ext.scan_debug(b.qoff, b.toff)
+    for k in ("pairs", "fast_pairs", "exact_pairs", "failed", "fast_classes"):
+        assert sp[k] == hp[k], k
+    assert sp["group_slots"] == hp["groups"]
+    assert hp["scratch_bytes"] <= sp["scratch_bound"] <= hp["scratch_bytes"] * 1.15 + (1 << 20)
+    q = [b"ACGT", b"A" * 300, b"", b"ACGTACGTAC", b"ACGT" * 30]
+    t = [b"ACGTTT", b"A" * 400, b"ACGT", b"", b"ACGT" * 600]
+    bb = W.from_lists(q, t)
+    sp = ext.scan_debug(bb.qoff, bb.toff)
+    assert sp["exact_pairs"] == 1 and sp["failed"] == 3 and sp["fast_pairs"] == 1
+    # chunk cut by the scratch budget
+    small = ext.scan_debug(b.qoff, b.toff, scratch_cap=hp["scratch_bytes"] // 3)
+    assert 0 < small["pairs"] < 3000 and small["scratch_bound"] <= hp["scratch_bytes"] // 3
+
+
+def test_device_planner_host_pass_is_cheap():
+    b = W.extension_pairs_fast(131072, seed=8)
+    sp = ext.scan_debug(b.qoff, b.toff, time_reps=20)
+    hp = ext.plan_debug(b.qoff, b.toff, time_reps=5)
+    assert sp["pairs"] == 131072
+    assert sp["scan_ns"] < hp["plan_ns"] / 2, (sp["scan_ns"], hp["plan_ns"])
+    print("host pass ns/pair", sp["scan_ns"] / 131072, "host planner ns/pair", hp["plan_ns"] / 131072)
