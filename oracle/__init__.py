@@ -233,3 +233,90 @@ def reference_gpu() -> Optional[GasalGpuReference]:
         p = os.path.join(_HERE, "_ref", "libgasal_gpu.so")
         _cache["gasal_gpu"] = GasalGpuReference(p) if os.path.exists(p) else None
     return _cache["gasal_gpu"]
+
+
+NAM_DTYPE = np.dtype([("query_start", "<i4"), ("query_end", "<i4"), ("query_prev_hit_startpos", "<i4"),
+                      ("ref_start", "<i4"), ("ref_end", "<i4"), ("ref_prev_hit_startpos", "<i4"),
+                      ("n_hits", "<i4"), ("ref_id", "<i4"), ("score", "<f4"), ("is_rc", "<i4")])
+
+
+class SeedIndex:
+    """An index built by the reference's own StrobemerIndex::populate (src/index.cpp:141), with views of its arrays."""
+
+    def __init__(self, lib, handle, keep):
+        self.lib, self.h, self._keep = lib, handle, keep
+        rs, n, st, ns, q = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64(), C.c_uint64()
+        ints = (C.c_int32 * 8)()
+        lib.seedref_export(handle, C.byref(rs), C.byref(n), C.byref(st), C.byref(ns), ints, C.byref(q))
+        self.randstrobes = np.ctypeslib.as_array(C.cast(rs, C.POINTER(C.c_uint8)), shape=(n.value * 16,)) if n.value else np.zeros(0, np.uint8)
+        self.n_randstrobes = n.value
+        self.starts = np.ctypeslib.as_array(C.cast(st, C.POINTER(C.c_uint64)), shape=(ns.value,))
+        (self.bits, self.filter_cutoff, self.k, self.s, self.t_syncmer, self.w_min, self.w_max, self.max_dist) = [int(x) for x in ints]
+        self.q = int(q.value)
+
+    def params(self) -> dict:
+        return dict(bits=self.bits, filter_cutoff=self.filter_cutoff, k=self.k, s=self.s, t_syncmer=self.t_syncmer,
+                    w_min=self.w_min, w_max=self.w_max, max_dist=self.max_dist, q=self.q)
+
+    def rescue_cutoff(self, rescue_level: int = 2) -> int:
+        return rescue_level * self.filter_cutoff if rescue_level < 100 else 1000  # src/main.cpp:415
+
+    def find_nams(self, reads: np.ndarray, roff: np.ndarray, rescue_level: int = 2):
+        """-> (nam_count[n], fraction[n], rescued[n], nams[total] as NAM_DTYPE) in the reference's pre-sort order."""
+        n = len(roff) - 1
+        cnt = np.zeros(n, np.int32); frac = np.zeros(n, np.float32); resc = np.zeros(n, np.uint8)
+        rc = self.rescue_cutoff(rescue_level)
+        total = self.lib.seedref_find_nams(self.h, reads.ctypes.data, roff.ctypes.data, n, rescue_level, rc,
+                                           cnt.ctypes.data, frac.ctypes.data, resc.ctypes.data, None, 0)
+        nams = np.zeros(max(1, total), NAM_DTYPE)
+        got = self.lib.seedref_find_nams(self.h, reads.ctypes.data, roff.ctypes.data, n, rescue_level, rc,
+                                         cnt.ctypes.data, frac.ctypes.data, resc.ctypes.data, nams.ctypes.data, total)
+        assert got == total
+        return cnt, frac, resc, nams[:total]
+
+    def time_find_nams(self, reads, roff, threads: int, rescue_level: int = 2) -> int:
+        return int(self.lib.seedref_time(self.h, reads.ctypes.data, roff.ctypes.data, len(roff) - 1, rescue_level,
+                                         self.rescue_cutoff(rescue_level), threads))
+
+    def map_order(self, keys) -> np.ndarray:
+        k = np.ascontiguousarray(keys, dtype=np.uint32)
+        out = np.zeros(len(k), np.uint32)
+        self.lib.seedref_map_order(k.ctypes.data, len(k), out.ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.seedref_free(self.h)
+            self.h = None
+
+
+def seed_reference_lib():
+    """The reference's seeding path (oracle/_ref/libseed_ref.so) or None when it was not built."""
+    if "seed" not in _cache:
+        p = os.path.join(_HERE, "_ref", "libseed_ref.so")
+        lib = None
+        if os.path.exists(p):
+            lib = C.CDLL(p)
+            lib.seedref_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+            lib.seedref_build.restype = C.c_void_p
+            lib.seedref_free.argtypes = [C.c_void_p]
+            lib.seedref_export.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+            lib.seedref_find_nams.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+            lib.seedref_find_nams.restype = C.c_int64
+            lib.seedref_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]
+            lib.seedref_time.restype = C.c_int64
+            lib.seedref_map_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _cache["seed"] = lib
+    return _cache["seed"]
+
+
+def build_seed_index(contigs: Sequence[np.ndarray], read_len: int = 150, threads: int = 8) -> Optional[SeedIndex]:
+    lib = seed_reference_lib()
+    if lib is None:
+        return None
+    concat = np.ascontiguousarray(np.concatenate(contigs), dtype=np.uint8)
+    off = np.zeros(len(contigs) + 1, np.int64)
+    off[1:] = np.cumsum([len(c) for c in contigs])
+    h = lib.seedref_build(concat.ctypes.data, off.ctypes.data, len(contigs), read_len, threads)
+    return SeedIndex(lib, h, (concat, off))

@@ -243,15 +243,17 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
     const double warps_per_sm = (double)blocks_per_sm * threads / 32.0;
     if (OP == CELL) {
         const double cellpairs = (double)ITERS * CH;  // per thread
-        const double cells_per_clk_sm = 2.0 * cellpairs * 32.0 * warps_per_sm / mean;
         const double gcups = 2.0 * cellpairs * (double)blocks * threads / (ms * 1e-3) / 1e9;
+        // per-clock figures from the kernel's wall time (CUDA events) and the SM clock measured inside it -- the mean of
+        // the blocks' own clock64 spans does not cover the kernel's wall time (blocks start and finish at different times)
+        const double cells_per_clk_sm = gcups * 1e9 / ((double)n_sms * sm_mhz * 1e6);
         printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"cells_per_clk_per_sm\": %.2f, \"clk_per_cellpair_per_smsp_warp\": %.2f, "
                "\"chip_gcups\": %.1f, \"ms\": %.3f, \"sm_mhz_in_kernel\": %.0f}\n",
-               kNames[OP], warps_per_sm, cells_per_clk_sm, mean / cellpairs / (warps_per_sm / 4.0), gcups, ms, sm_mhz);
+               kNames[OP], warps_per_sm, cells_per_clk_sm, (double)n_sms * sm_mhz * 1e6 * (ms * 1e-3) / cellpairs / (warps_per_sm / 4.0), gcups, ms, sm_mhz);
     } else {
         const double instr = (double)ITERS * kInstrPerIter[OP];  // per warp
-        const double ipc_sm = instr * warps_per_sm / mean;
         const double chip = instr * (double)blocks * threads / 32.0 / (ms * 1e-3);
+        const double ipc_sm = chip / ((double)n_sms * sm_mhz * 1e6);  // from the event time, see above
         printf("{\"test\": \"%s\", \"warps_per_sm\": %.0f, \"warp_instr_per_clk_per_sm\": %.3f, \"chip_warp_ginstr_per_s\": %.1f, "
                "\"ms\": %.3f, \"sm_mhz_in_kernel\": %.0f}\n",
                kNames[OP], warps_per_sm, ipc_sm, chip / 1e9, ms, sm_mhz);
@@ -285,12 +287,12 @@ int main(int argc, char** argv) {
     for (int threads : {256, 512}) {
         const int bps = 2;
         run<VIMNMX3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+        run<VIADDMNMX>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+        run<LOP3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         if (!quick) {
-            run<VIADDMNMX>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<VIMNMX>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<VIADD16>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<IADD3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
-            run<LOP3>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<PRMT>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<SHF>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
