@@ -10,8 +10,13 @@ all: $(LIB) tools/dpx_microbench oracle
 tools/dpx_microbench: tools/dpx_microbench.cu $(CSRC)/fast_cell.cuh $(CSRC)/common.cuh
 	$(NVCC) -O3 -std=c++17 -lineinfo $(ARCH) -o $@ $<
 
-$(LIB): $(CSRC)/engine.cu $(wildcard $(CSRC)/*.cuh) include/rsa_ext.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/engine.cu
+# two translation units (extension engine, seeding) compiled in parallel, one product library
+$(CSRC)/engine.o: $(CSRC)/engine.cu $(wildcard $(CSRC)/*.cuh) include/rsa_ext.h
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(CSRC)/seed.o: $(CSRC)/seed.cu $(CSRC)/kernels_seed.cuh include/rsa_seed.h
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(LIB): $(CSRC)/engine.o $(CSRC)/seed.o
+	$(NVCC) $(ARCH) -shared -o $@ $^
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/engine.cu
@@ -20,6 +25,6 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(LIB)
+	rm -f $(LIB) $(CSRC)/*.o
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean ptxas-info

@@ -121,6 +121,19 @@ int64_t seedref_find_nams(void* h, const char* reads, const int64_t* roff, int64
     return total;
 }
 
+// randstrobes_query of one read (src/randstrobes.cpp:207): out = n x {hash, start, end, is_reverse} as uint64; returns n
+int64_t seedref_randstrobes(void* h, const char* seq, int64_t len, uint64_t* out, int64_t cap) {
+    SeedRef* s = static_cast<SeedRef*>(h);
+    auto qr = randstrobes_query(std::string_view(seq, (size_t)len), s->params);
+    int64_t n = 0;
+    for (const auto& r : qr) {
+        if (n >= cap) return -1;
+        out[4 * n] = r.hash; out[4 * n + 1] = r.start; out[4 * n + 2] = r.end; out[4 * n + 3] = r.is_reverse ? 1 : 0;
+        ++n;
+    }
+    return n;
+}
+
 // CPU baseline: the same per-read work on `threads` threads (reads split into contiguous ranges); returns NAMs found.
 int64_t seedref_time(void* h, const char* reads, const int64_t* roff, int64_t n_reads, int rescue_level, int rescue_cutoff,
                      int threads) {

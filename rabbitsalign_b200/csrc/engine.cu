@@ -811,7 +811,9 @@ int64_t ramp_pairs(bool plan_ahead, long chunk_index) {
         static const int64_t r[] = {16384, 24576, 40960, 65536};
         return chunk_index < 4 ? r[chunk_index] : kMaxChunkPairs;
     }
-    return chunk_index < 3 ? ((int64_t)16384 << chunk_index) : kMaxChunkPairs;
+    // inline planning (device planner or small batches): measured on the bench batch (1 M pairs, e2e / resident):
+    // 16k,32k,64k 0.946; 32k,64k 0.957; 64k 0.945; none 0.916 (profiles/r2_e2e_ramp.md)
+    return chunk_index < 2 ? ((int64_t)32768 << chunk_index) : kMaxChunkPairs;
 }
 
 void plan_ahead_main(rsa_ext* h) {

@@ -293,3 +293,67 @@ def window_edge_pairs(seed: int = 221, tlens=(2046, 2047, 2048, 2049), qlens=(15
             qs.append(q.tobytes())
             ts.append(t.tobytes())
     return from_lists(qs, ts)
+
+
+# ---- seeding workloads: synthetic genome with injected repeats + simulated reads -------------------
+
+_COMP = np.zeros(256, np.uint8)
+_COMP[_ACGT] = np.frombuffer(b"TGCA", dtype=np.uint8)
+_COMP[ord("N")] = ord("N")
+
+
+def seeding_genome(n_contigs: int = 3, contig_len: int = 1_000_000, seed: int = 5, repeat_families: int = 4,
+                   copies_per_contig: int = 10, family_len: int = 2000, divergence: float = 0.02,
+                   low_complexity: int = 20) -> List[np.ndarray]:
+    """Random contigs with (a) repeat families copied into every contig at `divergence` (BASELINE configs[2]: "random +
+    injected repeats"), so reads from them hit many loci on several reference sequences, and (b) a few low-complexity
+    stretches (homopolymers, dinucleotide repeats) where equal s-mer hashes exercise the syncmer tie rules."""
+    rng = np.random.default_rng(seed)
+    contigs = [_ACGT[rng.integers(0, 4, size=contig_len)] for _ in range(n_contigs)]
+    fams = [_ACGT[rng.integers(0, 4, size=family_len)] for _ in range(repeat_families)]
+    for c in contigs:
+        for fam in fams:
+            for _ in range(copies_per_contig):
+                if len(c) <= family_len + 10:
+                    continue
+                p = int(rng.integers(0, len(c) - family_len - 1))
+                seg = fam.copy()
+                m = rng.random(family_len) < divergence
+                seg[m] = _ACGT[rng.integers(0, 4, size=int(m.sum()))]
+                c[p:p + family_len] = seg
+        for _ in range(low_complexity):
+            ln = int(rng.integers(30, 120))
+            if len(c) <= ln + 10:
+                continue
+            p = int(rng.integers(0, len(c) - ln - 1))
+            unit = _ACGT[rng.integers(0, 4, size=int(rng.integers(1, 4)))]
+            c[p:p + ln] = np.resize(unit, ln)
+    return contigs
+
+
+def seeding_reads(contigs: List[np.ndarray], n: int, read_len: int = 150, seed: int = 6, sub_rate: float = 0.01,
+                  indel_rate: float = 0.002, n_rate: float = 0.0, junk_frac: float = 0.01,
+                  vary_len: bool = False):
+    """Reads sampled from the contigs (both strands), mutated; `junk_frac` of them are random (no locus), some are
+    shorter than a seed.  Returns (buf uint8, offsets int64)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        ln = read_len if not vary_len else int(rng.integers(max(8, read_len // 3), read_len + 1))
+        if rng.random() < junk_frac:
+            s = _ACGT[rng.integers(0, 4, size=ln)] if rng.random() < 0.7 else _ACGT[rng.integers(0, 4, size=int(rng.integers(1, 30)))]
+        else:
+            c = contigs[int(rng.integers(0, len(contigs)))]
+            ln = min(ln, len(c))
+            p = int(rng.integers(0, len(c) - ln + 1))
+            s = _mutate(rng, c[p:p + ln], sub_rate, indel_rate, 3)
+            if rng.random() < 0.5:
+                s = _COMP[s][::-1]
+        if n_rate > 0 and len(s):
+            m = rng.random(len(s)) < n_rate
+            s = s.copy()
+            s[m] = ord("N")
+        out.append(np.ascontiguousarray(s, dtype=np.uint8))
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in out])
+    return (np.concatenate(out) if out else np.zeros(0, np.uint8)), off

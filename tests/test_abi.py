@@ -22,6 +22,28 @@ def test_exports_every_declared_symbol():
     assert lib.rsa_ext_version() >= 1
 
 
+def test_exports_every_declared_seeding_symbol():
+    from rabbitsalign_b200 import seed
+    lib = ext.load_library()
+    header = open(os.path.join(ROOT, "include", "rsa_seed.h")).read()
+    declared = set(re.findall(r"\b(rsa_seed_[a-z_]+)\s*\(", header))
+    assert declared == set(seed.SEED_ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert C.sizeof(seed.SeedConfig) == 56 and seed.NAM_DTYPE.itemsize == 40 and seed.READ_DTYPE.itemsize == 16
+
+
+def test_seeding_has_no_cpu_fallback():
+    import torch
+    from rabbitsalign_b200 import seed
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = seed.make_config(dict(bits=8, filter_cutoff=10, k=20, s=16, t_syncmer=3, w_min=5, w_max=11, max_dist=80, q=255))
+    with pytest.raises(seed.SeedError) as ei:
+        seed.SeedIndexGpu(cfg, np.zeros(16, np.uint8), np.zeros(257, np.uint64))
+    assert "no CPU path" in str(ei.value)
+
+
 def test_result_record_is_64_bytes():
     assert ext.RESULT_DTYPE.itemsize == 64
 
