@@ -100,6 +100,7 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
     double kernel_ms; /* device time of the seeding kernels (CUDA events) */
     int64_t kernel_launches;
+    double kernel_ms_large; /* part of kernel_ms spent in the large scratch tier */
 } rsa_seed_stats_t;
 int rsa_seed_get_stats(const rsa_seed_t *h, rsa_seed_stats_t *out);
 

@@ -150,4 +150,21 @@ $CXX -o "$OUT/rabbitsalign_b200_win" $WINOBJS "$OUT/obj_win/veneer.o" -L"$ROOT/r
 WINFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_win/pc_fx.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
 $CXX -o "$OUT/rabbitsalign_fx_b200_win" $WINFXOBJS $FXIO "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
      -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# ---- GPU seeding build: the window build + patch_seed.py: a chunk's reads are seeded
+#      in one rsa_seed_find_nams call (randstrobes, index lookup, NAM merge, rescue on the GPU); the per-read loop of the
+#      reference consumes the precomputed NAM lists.  Index replicated per GPU, shared by the workers.
+mkdir -p "$OUT/seed" "$OUT/obj_seed"
+python3 "$HERE/patch_seed.py" "$REF_ROOT/src/aln.cpp" "$OUT/seed/aln.cpp" "$OUT/windows/pc.cpp" "$OUT/seed/pc.cpp"
+pids=()
+( $CXX $WINFLAGS -c "$OUT/seed/aln.cpp" -o "$OUT/obj_seed/aln.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$OUT/seed/pc.cpp" -o "$OUT/obj_seed/pc.o" ) & pids+=($!)
+( $CXX $WINFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$OUT/seed/pc.cpp" -o "$OUT/obj_seed/pc_fx.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$HERE/seed_glue.cpp" -o "$OUT/obj_seed/seed_glue.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+SEEDOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_seed/pc.o";; aln) echo "$OUT/obj_seed/aln.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_gpuseed" $SEEDOBJS "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+SEEDFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_seed/pc_fx.o";; aln) echo "$OUT/obj_seed/aln.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_gpuseed" $SEEDFXOBJS $FXIO "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
 ls -la "$OUT"/rabbitsalign_*

@@ -37,7 +37,7 @@ struct rsa_seed_index {
 struct rsa_seed {
     rsa_seed_index* ix = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     // device
     uint8_t* d_reads = nullptr; size_t reads_cap = 0;
     int64_t* d_roff = nullptr; size_t roff_cap = 0;
@@ -118,6 +118,7 @@ int run_kernels(rsa_seed* h, int64_t n_reads) {
                                                      h->d_retry, 0);
     h->stats.kernel_launches++;
     SEED_TRY(h, cudaGetLastError());
+    SEED_TRY(h, cudaEventRecord(h->evm, h->st));
     SEED_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
     SEED_TRY(h, cudaStreamSynchronize(h->st));
     const int64_t n_retry = (int64_t)h->h_counters[3];
@@ -137,9 +138,11 @@ int run_kernels(rsa_seed* h, int64_t n_reads) {
     SEED_TRY(h, cudaEventRecord(h->ev1, h->st));
     SEED_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
     SEED_TRY(h, cudaStreamSynchronize(h->st));
-    float ms = 0;
+    float ms = 0, ms_small = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&ms_small, h->ev0, h->evm);
     h->stats.kernel_ms += ms;
+    h->stats.kernel_ms_large += ms - ms_small;
     return h->h_counters[0] > (unsigned long long)h->nams_cap ? 1 : RSA_SEED_OK;
 }
 
@@ -232,6 +235,7 @@ extern "C" int rsa_seed_create(rsa_seed_index_t* ix, rsa_seed_t** out) {
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("event", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreate(&h->evm)) != cudaSuccess) return fail("event", e);
     if ((e = cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&h->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return fail("pinned", e);
     *out = h.release();
@@ -249,6 +253,7 @@ extern "C" void rsa_seed_destroy(rsa_seed_t* h) {
         if (p) cudaFreeHost(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evm) cudaEventDestroy(h->evm);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -315,6 +320,7 @@ extern "C" int rsa_seed_run_staged(rsa_seed_t* h) {
     SEED_TRY(h, cudaSetDevice(h->ix->cfg.device));
     h->stats.reads = h->staged_reads;
     h->stats.kernel_ms = 0;
+    h->stats.kernel_ms_large = 0;
     h->stats.kernel_launches = 0;
     for (int attempt = 0;; ++attempt) {
         int rc = run_kernels(h, h->staged_reads);

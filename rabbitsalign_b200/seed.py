@@ -34,7 +34,7 @@ class SeedConfig(C.Structure):
 class SeedStats(C.Structure):
     _fields_ = [("reads", C.c_int64), ("nams", C.c_int64), ("reads_rescued", C.c_int64), ("reads_retried", C.c_int64),
                 ("reads_failed", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("kernel_ms_large", C.c_double)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -80,7 +80,8 @@ def main():
                     g.write(f.readline())
             sub_files[k] = path
         names = a.binaries.split(",") if a.binaries else ["rabbitsalign_cpussw", "rabbitsalign_gasalgpu", "rabbitsalign_b200",
-                                                          "rabbitsalign_b200_alninfo", "rabbitsalign_b200_big", "rabbitsalign_b200_win"]
+                                                          "rabbitsalign_b200_alninfo", "rabbitsalign_b200_big", "rabbitsalign_b200_win",
+                                                          "rabbitsalign_b200_gpuseed"]
         for name in names:
             exe = os.path.join(B, name)
             if not os.path.exists(exe):
