@@ -121,6 +121,7 @@ RSA_SEED_HD __forceinline__ int nt4(uint8_t ch) {
 
 // ---- syncmers (SyncmerIterator::next, src/randstrobes.cpp:57-127) -----------------------------------------------------
 // Returns the number of syncmers, or -1 when they do not fit `cap`.
+template <class Co>
 RSA_SEED_HD inline int read_syncmers(const uint8_t* seq, int len, const Params& P, uint64_t* out_hash, int32_t* out_pos, int cap) {
     const int k = P.k, s = P.s, t = P.t_syncmer;
     const uint64_t kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1), smask = s >= 32 ? ~0ull : ((1ull << (2 * s)) - 1);
@@ -168,8 +169,10 @@ RSA_SEED_HD inline int read_syncmers(const uint8_t* seq, int len, const Params& 
             }
             if (min_pos == (long long)i - k + t) {
                 if (n >= cap) return -1;
-                out_hash[n] = xxh64_u64(xk0 < xk1 ? xk0 : xk1);
-                out_pos[n] = i - k + 1;
+                if (Co::leader()) {
+                    out_hash[n] = xxh64_u64(xk0 < xk1 ? xk0 : xk1);
+                    out_pos[n] = i - k + 1;
+                }
                 ++n;
             }
         } else {
@@ -258,7 +261,57 @@ RSA_SEED_HD inline uint32_t index_get_count(const Index& ix, const Params& P, lo
     return (uint32_t)(lo - pos);
 }
 
+// ---- cooperation policy ------------------------------------------------------------------------------------------------
+// The per-read code below is written once and instantiated twice:
+//   CoThread  one thread per read (small scratch tier; also what tests/seed_host_check.cu compiles for the host);
+//   CoWarp    one warp per read (large tier: reads from repeats, whose hit lists run into the thousands).  All 32 lanes
+//             execute the same sequential program on the same values (registers replicated, control flow warp-uniform);
+//             scratch lists are written by lane 0 only and become visible to the others at the next sync().  The loops
+//             that make such reads slow -- "which open NAM takes this hit" over hundreds of open NAMs, gathering a group
+//             out of thousands of hits -- are split over the lanes, with ballots keeping the reference's first-match order.
+struct CoThread {
+    static constexpr int kLanes = 1;
+    RSA_SEED_HD static int lane() { return 0; }
+    RSA_SEED_HD static bool leader() { return true; }
+    RSA_SEED_HD static void sync() {}
+    RSA_SEED_HD static unsigned ballot(bool p) { return p ? 1u : 0u; }
+    RSA_SEED_HD static int bcast(int v, int) { return v; }
+    RSA_SEED_HD static int first_conflict(int) { return 1; }  // a single lane cannot collide with a lower one
+};
+#ifdef __CUDACC__
+struct CoWarp {
+    static constexpr int kLanes = 32;
+    __device__ static int lane() { return (int)(threadIdx.x & 31u); }
+    __device__ static bool leader() { return (threadIdx.x & 31u) == 0; }
+    __device__ static void sync() { __syncwarp(); }
+    __device__ static unsigned ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ static int bcast(int v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+    // lowest lane whose candidate (>= 0) is also the candidate of a lower lane; 32 when there is none
+    __device__ static int first_conflict(int cand) {
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, cand);
+        const bool conflict = cand >= 0 && (peers & ((1u << (threadIdx.x & 31u)) - 1u)) != 0;
+        const unsigned cm = __ballot_sync(0xFFFFFFFFu, conflict);
+        return cm ? __ffs((int)cm) - 1 : 32;
+    }
+};
+#endif
+RSA_SEED_HD __forceinline__ int first_bit(unsigned m) {  // index of the lowest set bit (m != 0)
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ffs((int)m) - 1;
+#endif
+}
+RSA_SEED_HD __forceinline__ int pop_count(unsigned m) {
+#ifdef __CUDA_ARCH__
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+
 // ---- per-read state ---------------------------------------------------------------------------------------------------
+template <class Co>
 struct ReadCtx {
     const Index& ix;
     const Params& P;
@@ -277,7 +330,8 @@ struct ReadCtx {
         for (int i = 0; i < n_groups[strand]; ++i)
             if (g[i] == ref_id) return i;
         if (n_groups[strand] >= caps.groups) { overflow = true; return 0; }
-        g[n_groups[strand]] = ref_id;
+        if (Co::leader()) g[n_groups[strand]] = ref_id;
+        Co::sync();
         return n_groups[strand]++;
     }
 
@@ -293,14 +347,17 @@ struct ReadCtx {
             const int diff = d < 0 ? -d : d;
             if (diff <= min_diff) {
                 const int g = group_of(strand, en.packed >> 8);
+                if (overflow) return;
                 if (!pre) {
                     if (n_hits >= caps.hits) { overflow = true; return; }
-                    Hit h;
-                    h.qs = (uint16_t)qs; h.qe = (uint16_t)qe; h.rs = ref_start; h.re = ref_end; h.grp = (uint16_t)g; h.pad = 0;
-                    sc.hits[n_hits++] = h;
+                    if (Co::leader()) {
+                        Hit h;
+                        h.qs = (uint16_t)qs; h.qe = (uint16_t)qe; h.rs = ref_start; h.re = ref_end; h.grp = (uint16_t)g; h.pad = 0;
+                        sc.hits[n_hits] = h;
+                    }
+                    ++n_hits;
                 }
                 min_diff = diff;
-                if (overflow) return;
             }
         }
     }
@@ -311,14 +368,21 @@ struct ReadCtx {
         n.score = (2 * n_min - n_max) > 0 ? (float)(n.n_hits * (2 * n_min - n_max)) : 1.0f;
         n.flags = (uint32_t)strand | ((uint32_t)grp << 8);
         if (n_nams >= caps.nams) { overflow = true; return; }
-        sc.nams[n_nams++] = n;
+        if (Co::leader()) sc.nams[n_nams] = n;
+        ++n_nams;
     }
 
     // the hits of group g of the current strand, in emission order, contiguous in sc.grouped; returns their number
     RSA_SEED_HD int gather_group(int g) {
         int m = 0;
-        for (int i = 0; i < n_hits; ++i)
-            if (sc.hits[i].grp == g) sc.grouped[m++] = sc.hits[i];
+        for (int base = 0; base < n_hits; base += Co::kLanes) {
+            const int i = base + Co::lane();
+            const bool mine = i < n_hits && sc.hits[i].grp == g;
+            const unsigned mask = Co::ballot(mine);
+            if (mine) sc.grouped[m + pop_count(mask & ((1u << Co::lane()) - 1u))] = sc.hits[i];
+            m += pop_count(mask);
+        }
+        Co::sync();
         return m;
     }
 
@@ -326,13 +390,16 @@ struct ReadCtx {
     // gives the reference's order; the hits arrive sorted (increasing strobe positions, index entries sorted by position),
     // which makes this insertion sort a single pass.
     RSA_SEED_HD void sort_group(int m) {
-        Hit* a = sc.grouped;
-        for (int i = 1; i < m; ++i) {
-            const Hit x = a[i];
-            int j = i - 1;
-            while (j >= 0 && (a[j].qs > x.qs || (a[j].qs == x.qs && a[j].rs > x.rs))) { a[j + 1] = a[j]; --j; }
-            a[j + 1] = x;
+        if (Co::leader()) {
+            Hit* a = sc.grouped;
+            for (int i = 1; i < m; ++i) {
+                const Hit x = a[i];
+                int j = i - 1;
+                while (j >= 0 && (a[j].qs > x.qs || (a[j].qs == x.qs && a[j].rs > x.rs))) { a[j + 1] = a[j]; --j; }
+                a[j + 1] = x;
+            }
         }
+        Co::sync();
     }
 
     RSA_SEED_HD static rsa_seed_nam_t new_nam(const Hit& h, uint32_t ref_id) {
@@ -346,12 +413,19 @@ struct ReadCtx {
 
     // flush the open NAMs the current hit has passed (query_end < c) and drop them, keeping the others' order
     RSA_SEED_HD void flush_passed(int& n_open, int c, int strand, int grp) {
-        for (int o = 0; o < n_open; ++o)
+        int keep = 0;
+        for (int o = 0; o < n_open; ++o) {
             if (sc.open[o].query_end < c) push_nam(sc.open[o], strand, grp);
-        int w = 0;
-        for (int o = 0; o < n_open; ++o)
-            if (!(sc.open[o].query_end < c)) sc.open[w++] = sc.open[o];
-        n_open = w;
+            else ++keep;
+        }
+        Co::sync();  // every lane has read the list before lane 0 compacts it
+        if (Co::leader()) {
+            int w = 0;
+            for (int o = 0; o < n_open; ++o)
+                if (!(sc.open[o].query_end < c)) sc.open[w++] = sc.open[o];
+        }
+        n_open = keep;
+        Co::sync();
     }
 
     // merge_hits_into_nams for one (strand, reference id) group of m sorted hits (src/nam.cpp:400-500)
@@ -360,39 +434,53 @@ struct ReadCtx {
         unsigned int prev_q_start = 0;
         for (int i = 0; i < m && !overflow; ++i) {
             const Hit h = sc.grouped[i];
-            bool is_added = false;
-            for (int oi = 0; oi < n_open; ++oi) {
-                rsa_seed_nam_t& o = sc.open[oi];
-                if (o.query_prev_hit_startpos < (int)h.qs && (int)h.qs <= o.query_end && o.ref_prev_hit_startpos < h.rs && h.rs <= o.ref_end) {
-                    if ((int)h.qe > o.query_end && h.re > o.ref_end) {
-                        o.query_end = h.qe; o.ref_end = h.re;
-                        o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
-                        o.n_hits++;
-                        is_added = true;
-                        break;
-                    } else if ((int)h.qe <= o.query_end && h.re <= o.ref_end) {
-                        o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
-                        o.n_hits++;
-                        is_added = true;
-                        break;
+            // the first open NAM (in list order) this hit extends (kind 1) or lies inside (kind 2)
+            int found = -1, kind = 0;
+            for (int base = 0; base < n_open; base += Co::kLanes) {
+                const int oi = base + Co::lane();
+                int k = 0;
+                if (oi < n_open) {
+                    const rsa_seed_nam_t o = sc.open[oi];
+                    if (o.query_prev_hit_startpos < (int)h.qs && (int)h.qs <= o.query_end && o.ref_prev_hit_startpos < h.rs && h.rs <= o.ref_end) {
+                        if ((int)h.qe > o.query_end && h.re > o.ref_end) k = 1;
+                        else if ((int)h.qe <= o.query_end && h.re <= o.ref_end) k = 2;
                     }
                 }
+                const unsigned mask = Co::ballot(k != 0);
+                if (mask) {
+                    const int src = first_bit(mask);
+                    found = base + src;
+                    kind = Co::bcast(k, src);
+                    break;
+                }
             }
-            if (!is_added) {
+            if (found >= 0) {
+                if (Co::leader()) {
+                    rsa_seed_nam_t& o = sc.open[found];
+                    if (kind == 1) { o.query_end = h.qe; o.ref_end = h.re; }
+                    o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
+                    o.n_hits++;
+                }
+            } else {
                 if (n_open >= caps.open) { overflow = true; return; }
-                sc.open[n_open++] = new_nam(h, ref_id);
+                if (Co::leader()) sc.open[n_open] = new_nam(h, ref_id);
+                ++n_open;
             }
+            Co::sync();
             if ((unsigned int)h.qs > prev_q_start + (unsigned int)P.k) {
                 flush_passed(n_open, (int)h.qs, strand, grp);
                 prev_q_start = h.qs;
             }
         }
         for (int o = 0; o < n_open; ++o) push_nam(sc.open[o], strand, grp);
+        Co::sync();
     }
 
     // merge_hits_into_nams_fast (sort == false) for one group (src/nam.cpp:170-366): hits are taken in runs of equal
-    // query_start; each open NAM looks, by binary search on ref_start, at the run's hits inside
-    // (ref_prev_hit_startpos, ref_end] and takes the first one that is not taken yet and extends it or lies inside it.
+    // query_start; each open NAM, in list order, looks (binary search on ref_start) at the run's hits inside
+    // (ref_prev_hit_startpos, ref_end] and takes the first one not taken yet that extends it or lies inside it.
+    // With several lanes, kLanes open NAMs pick their hit at once; two lanes picking the same hit means the later one would
+    // have seen it taken, so only the lanes before the first such collision commit and the rest look again.
     RSA_SEED_HD void merge_group_fast(int m, int strand, int grp, uint32_t ref_id) {
         Hit* hits = sc.grouped;
         int n_open = 0;
@@ -405,66 +493,76 @@ struct ReadCtx {
             const int i_size = i_end - i_start;
             const int query_start = hits[i_start].qs;
             int cnt_done = 0;
-            // std::sort(hits.begin() + i_start, hits.begin() + i_end): (query_start equal) by ref_start, unique
-            for (int a = i_start + 1; a < i_end; ++a) {
-                const Hit x = hits[a];
-                int j = a - 1;
-                while (j >= i_start && hits[j].rs > x.rs) { hits[j + 1] = hits[j]; --j; }
-                hits[j + 1] = x;
+            Co::sync();
+            if (Co::leader()) {
+                // std::sort(hits.begin() + i_start, hits.begin() + i_end): (query_start equal) by ref_start, unique
+                for (int a = i_start + 1; a < i_end; ++a) {
+                    const Hit x = hits[a];
+                    int j = a - 1;
+                    while (j >= i_start && hits[j].rs > x.rs) { hits[j + 1] = hits[j]; --j; }
+                    hits[j + 1] = x;
+                }
+                for (int a = i_start; a < i_end; ++a) hits[a].pad = 0;  // is_added[]
             }
-            // is_added[]: the pad field of the run's hits
-            for (int a = i_start; a < i_end; ++a) hits[a].pad = 0;
-            for (int oi = 0; oi < n_open; ++oi) {
-                rsa_seed_nam_t& o = sc.open[oi];
-                // lower_bound(ref_start >= value) twice
-                int lo = i_start, hi = i_end;
-                const int v1 = o.ref_prev_hit_startpos + 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid].rs < v1) lo = mid + 1; else hi = mid; }
-                const int lower = lo;
-                lo = i_start; hi = i_end;
-                const int v2 = o.ref_end + 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid].rs < v2) lo = mid + 1; else hi = mid; }
-                const int upper = lo;
-                for (int j = lower; j < upper; ++j) {
-                    if (hits[j].pad) continue;
+            Co::sync();
+            for (int oi0 = 0; oi0 < n_open && cnt_done < i_size;) {
+                const int oi = oi0 + Co::lane();
+                int cand = -1, kind = 0;
+                if (oi < n_open) {
+                    const rsa_seed_nam_t o = sc.open[oi];
+                    int lo = i_start, hi = i_end;  // lower_bound(ref_start >= value), twice
+                    const int v1 = o.ref_prev_hit_startpos + 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid].rs < v1) lo = mid + 1; else hi = mid; }
+                    const int lower = lo;
+                    lo = i_start; hi = i_end;
+                    const int v2 = o.ref_end + 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (hits[mid].rs < v2) lo = mid + 1; else hi = mid; }
+                    const int upper = lo;
                     if (query_start <= o.query_end) {
-                        const Hit h = hits[j];
-                        if (o.ref_prev_hit_startpos < h.rs && h.rs <= o.ref_end) {
-                            if ((int)h.qe > o.query_end && h.re > o.ref_end) {
-                                o.query_end = h.qe; o.ref_end = h.re;
-                                o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
-                                o.n_hits++;
-                                hits[j].pad = 1;
-                                cnt_done++;
-                                break;
-                            } else if ((int)h.qe <= o.query_end && h.re <= o.ref_end) {
-                                o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
-                                o.n_hits++;
-                                hits[j].pad = 1;
-                                cnt_done++;
-                                break;
+                        for (int j = lower; j < upper; ++j) {
+                            const Hit h = hits[j];
+                            if (h.pad) continue;
+                            if (o.ref_prev_hit_startpos < h.rs && h.rs <= o.ref_end) {
+                                if ((int)h.qe > o.query_end && h.re > o.ref_end) { cand = j; kind = 1; break; }
+                                else if ((int)h.qe <= o.query_end && h.re <= o.ref_end) { cand = j; kind = 2; break; }
                             }
                         }
                     }
                 }
-                if (cnt_done == i_size) break;
+                const int stop = Co::first_conflict(cand);  // lanes [0, stop) commit
+                const bool commit = cand >= 0 && Co::lane() < stop;
+                if (commit) {
+                    const Hit h = hits[cand];
+                    rsa_seed_nam_t& o = sc.open[oi];
+                    if (kind == 1) { o.query_end = h.qe; o.ref_end = h.re; }
+                    o.query_prev_hit_startpos = h.qs; o.ref_prev_hit_startpos = h.rs;
+                    o.n_hits++;
+                    hits[cand].pad = 1;
+                }
+                cnt_done += pop_count(Co::ballot(commit));
+                oi0 += stop < Co::kLanes ? stop : Co::kLanes;
+                Co::sync();
             }
             for (int a = i_start; a < i_end; ++a) {
                 if (!hits[a].pad) {
                     if (n_open >= caps.open) { overflow = true; return; }
-                    sc.open[n_open++] = new_nam(hits[a], ref_id);
+                    if (Co::leader()) sc.open[n_open] = new_nam(hits[a], ref_id);
+                    ++n_open;
                 }
             }
+            Co::sync();
             if ((unsigned int)query_start > prev_q_start + (unsigned int)P.k) {
                 flush_passed(n_open, query_start, strand, grp);
                 prev_q_start = (unsigned int)query_start;
             }
         }
         for (int o = 0; o < n_open; ++o) push_nam(sc.open[o], strand, grp);
+        Co::sync();
     }
 
     // all groups of the current strand -> NAMs (merge_hits_into_nams_forward_and_reverse[_fast], one strand)
     RSA_SEED_HD void merge_strand(int strand, bool fast) {
+        Co::sync();  // the strand's hits are complete
         for (int g = 0; g < n_groups[strand] && !overflow; ++g) {
             const int m = gather_group(g);
             const uint32_t ref_id = sc.group_ref[strand * caps.groups + g];
@@ -476,16 +574,18 @@ struct ReadCtx {
 
 // One read: find_nams, then find_nams_rescue when the reference would run it.  Returns the number of NAMs left in
 // sc.nams (strand 0 groups in first-touch order, then strand 1), or -1 on scratch overflow.
+template <class Co>
 RSA_SEED_HD inline int seed_read(const uint8_t* seq, int len, const Index& ix, const Params& P, const Caps& caps, Scratch& sc,
-                                float& fraction, bool& rescued) {
+                                 float& fraction, bool& rescued) {
     fraction = 1.0f;
     rescued = false;
-    ReadCtx rc(ix, P, caps, sc);
+    ReadCtx<Co> rc(ix, P, caps, sc);
     int n_syn = 0;
     if (len >= P.w_max) {  // randstrobes_query: `if (seq.length() < parameters.randstrobe.w_max) return` (src/randstrobes.cpp:209)
-        n_syn = read_syncmers(seq, len, P, sc.syn_hash, sc.syn_pos, caps.syn);
+        n_syn = read_syncmers<Co>(seq, len, P, sc.syn_hash, sc.syn_pos, caps.syn);
         if (n_syn < 0) return -1;
     }
+    Co::sync();
     const int n_rs = n_syn > P.w_min ? n_syn - P.w_min : 0;  // randstrobes per strand (has_next: idx + w_min < size)
     // ---- find_nams (src/nam.cpp:771-922)
     int total_hits = 0, good_hits = 0;
@@ -527,16 +627,19 @@ RSA_SEED_HD inline int seed_read(const uint8_t* seq, int len, const Index& ix, c
             if (pos < 0) continue;
             RescueHit r;
             r.position = (uint32_t)pos; r.count = index_get_count(ix, P, pos); r.qs = (uint16_t)qs; r.qe = (uint16_t)qe; r.pad = 0;
-            // std::sort(..., cmp1): by (count, query_start, query_end), keys unique: insert in place
-            int j = n_resc[strand] - 1;
-            while (j >= 0 && (rh[j].count > r.count || (rh[j].count == r.count && (rh[j].qs > r.qs || (rh[j].qs == r.qs && rh[j].qe > r.qe))))) {
-                rh[j + 1] = rh[j];
-                --j;
+            if (Co::leader()) {
+                // std::sort(..., cmp1): by (count, query_start, query_end), keys unique: insert in place
+                int j = n_resc[strand] - 1;
+                while (j >= 0 && (rh[j].count > r.count || (rh[j].count == r.count && (rh[j].qs > r.qs || (rh[j].qs == r.qs && rh[j].qe > r.qe))))) {
+                    rh[j + 1] = rh[j];
+                    --j;
+                }
+                rh[j + 1] = r;
             }
-            rh[j + 1] = r;
             n_resc[strand]++;
         }
     }
+    Co::sync();
     for (int strand = 0; strand < 2; ++strand) {
         RescueHit* rh = sc.resc + strand * caps.resc;
         // the hits to use: in count order until the cutoff; the keys of hits_per_ref are created in THIS order (_pre)
@@ -547,13 +650,17 @@ RSA_SEED_HD inline int seed_read(const uint8_t* seq, int len, const Index& ix, c
             if (rc.overflow) return -1;
             ++n_use;
         }
-        // std::sort(rhs, cmp2): by query_start (unique per strand)
-        for (int a = 1; a < n_use; ++a) {
-            const RescueHit x = rh[a];
-            int j = a - 1;
-            while (j >= 0 && rh[j].qs > x.qs) { rh[j + 1] = rh[j]; --j; }
-            rh[j + 1] = x;
+        Co::sync();
+        if (Co::leader()) {
+            // std::sort(rhs, cmp2): by query_start (unique per strand)
+            for (int a = 1; a < n_use; ++a) {
+                const RescueHit x = rh[a];
+                int j = a - 1;
+                while (j >= 0 && rh[j].qs > x.qs) { rh[j + 1] = rh[j]; --j; }
+                rh[j + 1] = x;
+            }
         }
+        Co::sync();
         rc.n_hits = 0;
         for (int a = 0; a < n_use; ++a) {
             rc.emit_hits(strand, rh[a].qs, rh[a].qe, (long long)rh[a].position, false);
@@ -567,15 +674,17 @@ RSA_SEED_HD inline int seed_read(const uint8_t* seq, int len, const Index& ix, c
 
 constexpr int kSeedThreads = 128;
 
-// Grid-stride over the reads (or over `list`, the reads the small tier could not hold); every thread owns one scratch slice.
+// Grid-stride over the reads (or over `list`, the reads the small tier could not hold).  Co = CoThread: every thread owns
+// one scratch slice and one read at a time; Co = CoWarp: every warp does.
+template <class Co>
 __global__ void __launch_bounds__(kSeedThreads)
 seed_kernel(const uint8_t* __restrict__ reads, const int64_t* __restrict__ roff, const uint32_t* __restrict__ list, int n,
             Index ix, Params P, Caps caps, uint8_t* __restrict__ scratch, size_t scratch_stride,
             rsa_seed_read_t* __restrict__ per_read, rsa_seed_nam_t* __restrict__ nam_out, unsigned long long nam_cap,
             unsigned long long* __restrict__ counters /* [0] NAM cursor, [1] overflowed reads, [2] rescued, [3] retry list length */,
             uint32_t* __restrict__ retry_list, int final_tier) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int stride = gridDim.x * blockDim.x;
+    const int tid = (int)((blockIdx.x * blockDim.x + threadIdx.x) / Co::kLanes);   // worker = thread or warp
+    const int stride = (int)(gridDim.x * blockDim.x / Co::kLanes);
     Scratch sc(scratch + (size_t)tid * scratch_stride, caps);
     for (int it = tid; it < n; it += stride) {
         const uint32_t r = list ? list[it] : (uint32_t)it;
@@ -583,22 +692,32 @@ seed_kernel(const uint8_t* __restrict__ reads, const int64_t* __restrict__ roff,
         const int len = (int)(roff[r + 1] - off);
         float fraction;
         bool rescued;
-        const int cnt = seed_read(reads + off, len, ix, P, caps, sc, fraction, rescued);
+        Co::sync();  // the previous read's lists are dead
+        const int cnt = seed_read<Co>(reads + off, len, ix, P, caps, sc, fraction, rescued);
+        Co::sync();
         rsa_seed_read_t pr;
         pr.nam_off = 0; pr.n_nams = 0; pr.nonrepetitive_fraction = fraction; pr.flags = rescued ? RSA_SEED_READ_RESCUED : 0u;
         if (cnt < 0) {
-            if (final_tier) { pr.flags = RSA_SEED_READ_FAILED; atomicAdd(&counters[1], 1ull); }
-            else { const unsigned long long slot = atomicAdd(&counters[3], 1ull); retry_list[slot] = r; pr.flags = RSA_SEED_READ_FAILED; }
-            per_read[r] = pr;
+            if (Co::leader()) {
+                pr.flags = RSA_SEED_READ_FAILED;
+                if (final_tier) atomicAdd(&counters[1], 1ull);
+                else { const unsigned long long slot = atomicAdd(&counters[3], 1ull); retry_list[slot] = r; }
+                per_read[r] = pr;
+            }
             continue;
         }
-        if (rescued) atomicAdd(&counters[2], 1ull);
-        const unsigned long long at = atomicAdd(&counters[0], (unsigned long long)cnt);
-        pr.nam_off = (uint32_t)at;
-        pr.n_nams = cnt;
+        unsigned long long at = 0;
+        if (Co::leader()) {
+            if (rescued) atomicAdd(&counters[2], 1ull);
+            at = atomicAdd(&counters[0], (unsigned long long)cnt);
+            pr.nam_off = (uint32_t)at;
+            pr.n_nams = cnt;
+            per_read[r] = pr;
+        }
+        const unsigned lo = (unsigned)Co::bcast((int)(uint32_t)(at & 0xFFFFFFFFull), 0), hi = (unsigned)Co::bcast((int)(uint32_t)(at >> 32), 0);
+        at = ((unsigned long long)hi << 32) | lo;
         if (at + (unsigned long long)cnt <= nam_cap)
-            for (int i = 0; i < cnt; ++i) nam_out[at + i] = sc.nams[i];
-        per_read[r] = pr;
+            for (int i = Co::lane(); i < cnt; i += Co::kLanes) nam_out[at + i] = sc.nams[i];
     }
 }
 

@@ -5,6 +5,7 @@
 // ::randstrobe_start_indices, src/index.hpp:163-184) is uploaded once per GPU and shared by that GPU's workers.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -22,8 +23,8 @@ std::mutex g_seed_cold;  // allocations / first launches take process-wide drive
 // small tier: what an ordinary read needs (150-250 bp: ~30-50 syncmers, tens of hits, a handful of NAMs)
 constexpr Caps kCapsSmall{128, 384, 16, 48, 128, 128};
 // large tier: reads from repeats, long reads, many reference sequences
-constexpr Caps kCapsLarge{512, 65536, 512, 8192, 32768, 512};
-constexpr int kLargeSlots = 1024;  // reads processed at once by the large tier
+constexpr Caps kCapsLarge{512, 32768, 512, 8192, 16384, 512};
+constexpr int kLargeWarpsPerSm = 16;  // the large tier runs one WARP per read (kernels_seed.cuh, CoWarp)
 }  // namespace
 
 struct rsa_seed_index {
@@ -107,13 +108,16 @@ int run_kernels(rsa_seed* h, int64_t n_reads) {
     const Params P = make_params(ix);
     const Index I{ix->d_entries, ix->d_starts, (long long)ix->n};
     const int blocks = (int)std::min<int64_t>((n_reads + kSeedThreads - 1) / kSeedThreads, (int64_t)ix->n_sms * 4);
+    // RSA_SEED_FORCE_LARGE=1 (tests): a small tier that holds nothing, so every read with seeds takes the warp-per-read tier
+    static const bool force_large = getenv("RSA_SEED_FORCE_LARGE") != nullptr;
+    const Caps caps_small = force_large ? Caps{1, 1, 1, 1, 1, 1} : kCapsSmall;
     const size_t stride = scratch_bytes(kCapsSmall);
     int rc;
     if ((rc = grow_dev(h, h->d_scratch, h->scratch_cap, stride * (size_t)blocks * kSeedThreads))) return rc;
     if ((rc = grow_dev(h, h->d_retry, h->retry_cap, (size_t)n_reads))) return rc;
     SEED_TRY(h, cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->st));
     SEED_TRY(h, cudaEventRecord(h->ev0, h->st));
-    seed_kernel<<<blocks, kSeedThreads, 0, h->st>>>(h->d_reads, h->d_roff, nullptr, (int)n_reads, I, P, kCapsSmall, h->d_scratch,
+    seed_kernel<CoThread><<<blocks, kSeedThreads, 0, h->st>>>(h->d_reads, h->d_roff, nullptr, (int)n_reads, I, P, caps_small, h->d_scratch,
                                                      stride, h->d_per, h->d_nams, (unsigned long long)h->nams_cap, h->d_counters,
                                                      h->d_retry, 0);
     h->stats.kernel_launches++;
@@ -124,14 +128,15 @@ int run_kernels(rsa_seed* h, int64_t n_reads) {
     const int64_t n_retry = (int64_t)h->h_counters[3];
     h->stats.reads_retried = n_retry;
     if (n_retry > 0) {
-        // the reads the small tier could not hold, kLargeSlots at a time with the large scratch
+        // the reads the small tier could not hold: one warp per read, large scratch slices
         const size_t lstride = scratch_bytes(kCapsLarge);
-        const int slots = (int)std::min<int64_t>(n_retry, kLargeSlots);
-        if ((rc = grow_dev(h, h->d_scratch_large, h->scratch_large_cap, lstride * (size_t)((slots + kSeedThreads - 1) / kSeedThreads * kSeedThreads)))) return rc;
-        const int lblocks = (slots + kSeedThreads - 1) / kSeedThreads;
-        seed_kernel<<<lblocks, kSeedThreads, 0, h->st>>>(h->d_reads, h->d_roff, h->d_retry, (int)n_retry, I, P, kCapsLarge,
-                                                          h->d_scratch_large, lstride, h->d_per, h->d_nams,
-                                                          (unsigned long long)h->nams_cap, h->d_counters, nullptr, 1);
+        const int warps_per_block = kSeedThreads / 32;
+        const int64_t want_warps = std::min<int64_t>(n_retry, (int64_t)ix->n_sms * kLargeWarpsPerSm);
+        const int lblocks = (int)((want_warps + warps_per_block - 1) / warps_per_block);
+        if ((rc = grow_dev(h, h->d_scratch_large, h->scratch_large_cap, lstride * (size_t)lblocks * warps_per_block))) return rc;
+        seed_kernel<CoWarp><<<lblocks, kSeedThreads, 0, h->st>>>(h->d_reads, h->d_roff, h->d_retry, (int)n_retry, I, P, kCapsLarge,
+                                                                  h->d_scratch_large, lstride, h->d_per, h->d_nams,
+                                                                  (unsigned long long)h->nams_cap, h->d_counters, nullptr, 1);
         h->stats.kernel_launches++;
         SEED_TRY(h, cudaGetLastError());
     }

@@ -17,7 +17,7 @@ extern "C" int64_t seed_host_check(const rsa_seed_config_t* cfg, const void* ent
     P.bits = cfg->bits; P.rescue_level = cfg->rescue_level; P.filter_cutoff = cfg->filter_cutoff; P.rescue_cutoff = cfg->rescue_cutoff;
     P.q = cfg->q; P.n_entries = n_entries;
     const Index I{static_cast<const IndexEntry*>(entries), starts, (long long)n_entries};
-    const Caps small{128, 384, 16, 48, 128, 128}, large{512, 65536, 512, 8192, 32768, 512};
+    const Caps small{128, 384, 16, 48, 128, 128}, large{512, 32768, 512, 8192, 16384, 512};
     const Caps caps = large_tier ? large : small;
     std::vector<uint8_t> buf(scratch_bytes(caps) + 64);
     Scratch sc(buf.data(), caps);
@@ -25,7 +25,7 @@ extern "C" int64_t seed_host_check(const rsa_seed_config_t* cfg, const void* ent
     for (int64_t r = 0; r < n_reads; ++r) {
         float fraction;
         bool rescued;
-        const int cnt = seed_read(reinterpret_cast<const uint8_t*>(reads) + roff[r], (int)(roff[r + 1] - roff[r]), I, P, caps, sc,
+        const int cnt = seed_read<CoThread>(reinterpret_cast<const uint8_t*>(reads) + roff[r], (int)(roff[r + 1] - roff[r]), I, P, caps, sc,
                                   fraction, rescued);
         rsa_seed_read_t pr;
         pr.nam_off = (uint32_t)total; pr.n_nams = 0; pr.nonrepetitive_fraction = fraction;
@@ -50,7 +50,7 @@ extern "C" int64_t seed_host_randstrobes(const rsa_seed_config_t* cfg, const cha
     std::vector<uint64_t> sh(4096);
     std::vector<int32_t> sp(4096);
     if (len < P.w_max) return 0;
-    const int n_syn = read_syncmers(reinterpret_cast<const uint8_t*>(seq), (int)len, P, sh.data(), sp.data(), 4096);
+    const int n_syn = read_syncmers<CoThread>(reinterpret_cast<const uint8_t*>(seq), (int)len, P, sh.data(), sp.data(), 4096);
     if (n_syn < 0) return -2;
     const int n_rs = n_syn > P.w_min ? n_syn - P.w_min : 0;
     int64_t n = 0;

@@ -45,7 +45,7 @@ def host_harness():
     hdr = os.path.join(HERE, "..", "rabbitsalign_b200", "csrc", "kernels_seed.cuh")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", out, src])
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared", "-o", out, src])
     lib = C.CDLL(out)
     lib.seed_host_check.restype = C.c_int64
     lib.seed_host_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int,

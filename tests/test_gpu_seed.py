@@ -105,3 +105,28 @@ def test_staged_run_matches_and_arguments_are_checked():
         p["bits"] = 5
         S.SeedIndexGpu(S.make_config(p), idx.randstrobes, idx.starts)
     idx.close()
+
+
+def test_warp_per_read_tier_alone_equals_reference():
+    """RSA_SEED_FORCE_LARGE=1 sends every read through the large tier (one warp per read, cooperative merge loops): same
+    records.  Run in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import seed_util as U\n"
+        "from rabbitsalign_b200 import seed as S\n"
+        "for name in ('r150_repeats', 'rescue_heavy', 'many_contigs', 'low_complexity', 'r50_short'):\n"
+        "    idx, buf, off = U.make_case(name)\n"
+        "    gi = S.SeedIndexGpu(S.make_config(idx.params()), idx.randstrobes, idx.starts)\n"
+        "    sd = S.Seeder(gi)\n"
+        "    per, nams = sd.find_nams(buf, off)\n"
+        "    st = sd.stats()\n"
+        "    U.assert_equals_reference(idx, buf, off, per, nams)\n"
+        "    assert st['reads_retried'] > 0.5 * st['reads'], st\n"
+        "    sd.close(); gi.close(); idx.close()\n"
+        "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RSA_SEED_FORCE_LARGE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
