@@ -225,13 +225,73 @@ def leg_250bp_indel(device, scratch_gb):
     return out
 
 
+def leg_seeding(device, cores, peaks):
+    """SURVEY 8f rank 2, the second kernel family: randstrobe seeding + index lookup + NAM merge (+ rescue) for 1 M reads of
+    150 bp against a 20 Mb genome with injected repeats.  The index is INPUT DATA built by the reference's own host code
+    (StrobemerIndex::populate, out of scope) through oracle/_ref/libseed_ref.so -- the same library that provides this
+    leg's CPU baseline (the reference's randstrobes_query + find_nams + find_nams_rescue on all host cores).  The kernels
+    and the C ABI measured are the product's (include/rsa_seed.h)."""
+    import oracle
+    import torch
+    from rabbitsalign_b200 import seed as S, workload as W
+    if oracle.seed_reference_lib() is None:
+        return None
+    contigs = W.seeding_genome(n_contigs=4, contig_len=5_000_000, seed=41, repeat_families=8, copies_per_contig=20)
+    idx = oracle.build_seed_index(contigs, 150, cores)
+    small, soff = W.seeding_reads(contigs, 50_000, seed=42)
+    reps = 20
+    buf = np.tile(small, reps)
+    off = np.concatenate([soff[:-1] + k * int(soff[-1]) for k in range(reps)] + [np.array([reps * int(soff[-1])])]).astype(np.int64)
+    n = len(off) - 1
+    tb = torch.empty(buf.nbytes, dtype=torch.uint8).pin_memory()
+    pbuf = tb.numpy(); pbuf[...] = buf
+    gi = S.SeedIndexGpu(S.make_config(idx.params(), device=device), idx.randstrobes, idx.starts)
+    sd = S.Seeder(gi)
+    sd.stage(pbuf, off)
+    for _ in range(3):
+        sd.run_staged()
+    ms, ms_large = [], []
+    for _ in range(5):
+        sd.run_staged()
+        st = sd.stats()
+        ms.append(st["kernel_ms"]); ms_large.append(st["kernel_ms_large"])
+    st = sd.stats()
+    sd.find_nams(pbuf, off, copy=False)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        per, nams = sd.find_nams(pbuf, off, copy=False)  # H2D of the reads, kernels, D2H of the NAMs into pinned memory
+    dt = (time.perf_counter() - t0) / 3
+    st2 = sd.stats()
+    sub = 200_000
+    t0 = time.perf_counter()
+    idx.time_find_nams(buf, np.ascontiguousarray(off[:sub + 1]), cores)
+    t_cpu = time.perf_counter() - t0
+    kms = float(np.median(ms))
+    # algorithmic HBM bytes per read: its bases in, per query randstrobe one 32-byte sector of bucket starts, one of index
+    # entries for the search, one for the filter probe, 16 bytes per hit entry read, 40 bytes per NAM + 16 per read out
+    n_rs = 2 * 26  # ~26 randstrobes per strand at 150 bp (k 20, s 16)
+    alg_bytes = float(off[-1]) + n * n_rs * 96.0 + 40.0 * st["nams"] + 16.0 * n
+    out = {"reads": n, "genome_bp": 20_000_000, "index_entries": idx.n_randstrobes, "nams": st["nams"],
+           "reads_rescued": st["reads_rescued"], "reads_large_tier": st["reads_retried"], "reads_failed": st["reads_failed"],
+           "kernel_ms": kms, "kernel_ms_large_tier": float(np.median(ms_large)),
+           "reads_per_s_resident": n / (kms * 1e-3), "nams_per_s_resident": st["nams"] / (kms * 1e-3),
+           "reads_per_s_e2e": n / dt, "h2d_bytes": st2["h2d_bytes"], "d2h_bytes": st2["d2h_bytes"],
+           "cpu_baseline": {"kind": "reference", "cores": cores, "reads_per_s": sub / t_cpu, "sample": f"first {sub} reads, one pass"},
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": alg_bytes / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "note": "random 16-32 byte index probes: latency x sectors bound, not streaming bandwidth; algorithmic "
+                                "bytes = read bases + 96 B per query randstrobe (bucket starts, entry, filter probe) + NAMs out"}}
+    sd.close(); gi.close(); idx.close()
+    return out
+
+
 def pipeline_block(threads):
     """BASELINE metric (i), end-to-end reads/s: the reference's host pipeline (integration/_build, compiled from the
     reference by integration/build.sh) with the reference's own GPU path vs this engine, same synthetic FASTQ/FASTA,
     same threads.  A small job (600 k single-end reads, 20 Mb): process start-up weighs in, so the pipeline's own
     "Total time mapping" is reported next to the wall clock.  Larger runs: profiles/r2_e2e_*.json."""
     exe = os.path.join(ROOT, "tools", "e2e_reads_bench.py")
-    bins = ["rabbitsalign_gasalgpu", "rabbitsalign_b200_big", "rabbitsalign_b200_win"]
+    bins = ["rabbitsalign_gasalgpu", "rabbitsalign_b200_big", "rabbitsalign_b200_gpuseed"]
     if not all(os.path.exists(os.path.join(ROOT, "integration", "_build", b)) for b in bins[:2]):
         return None
     try:
@@ -246,7 +306,8 @@ def pipeline_block(threads):
             out[b] = {k: d[b].get(k) for k in ("wall_s", "mapping_s", "reads_per_s_wall", "reads_per_s_mapping", "sam_md5")}
     try:
         out["sam_identical"] = len({out[b]["sam_md5"] for b in bins if b in out}) == 1
-        out["mapping_speedup_vs_reference_gpu_build"] = out[bins[0]]["mapping_s"] / out[bins[1]]["mapping_s"]
+        out["mapping_speedup_vs_reference_gpu_build"] = out[bins[0]]["mapping_s"] / out[bins[2]]["mapping_s"]
+        out["wall_speedup_vs_reference_gpu_build"] = out[bins[0]]["wall_s"] / out[bins[2]]["wall_s"]
     except Exception:  # noqa: BLE001
         pass
     return out
@@ -515,6 +576,7 @@ def main():
     # ---- extra legs (rank 0, N=1 only): BASELINE configs[3] and the end-to-end pipeline ----------------------------------
     leg250 = None
     pipe = None
+    seeding = None
     if n_gpus == 1 and not args.no_extra_legs:
         try:
             leg250 = leg_250bp_indel(local_rank, scratch_gb)
@@ -522,6 +584,10 @@ def main():
             leg250 = {"error": str(ex)[:200]}
         eng.close()  # the pipeline binaries need the GPU memory and the host cores
         eng = None
+        try:
+            seeding = leg_seeding(local_rank, cores, peaks)
+        except Exception as ex:  # noqa: BLE001
+            seeding = {"error": str(ex)[:300]}
         pipe = pipeline_block(cores)
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
@@ -544,7 +610,7 @@ def main():
                    "resident_equals_e2e_records": same, "records_sane": ok,
                    "slice512_one_worker": {"us_per_call": slice_dt * 1e6, "pairs_per_s": 512 / slice_dt if slice_dt > 0 else None},
                    "e2e_with_device_align_gpu": aln_stats, "e2e_windows_in_resident_reference": win_stats,
-                   "leg_250bp_5pct_indel": leg250, "pipeline": pipe},
+                   "leg_250bp_5pct_indel": leg250, "seeding": seeding, "pipeline": pipe},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e2e["h2d_bytes"],
                 "d2h_bytes_per_step": st_e2e["d2h_bytes"],

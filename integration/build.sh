@@ -167,4 +167,20 @@ $CXX -o "$OUT/rabbitsalign_b200_gpuseed" $SEEDOBJS "$OUT/obj_seed/seed_glue.o" "
 SEEDFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_seed/pc_fx.o";; aln) echo "$OUT/obj_seed/aln.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
 $CXX -o "$OUT/rabbitsalign_fx_b200_gpuseed" $SEEDFXOBJS $FXIO "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
      -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# ---- profiling builds: the reference's own per-phase timers (time1 seeding loop, time2_1..4 extension phases, time3_1..2
+#      SAM + output; their summary fprintf is commented out in src/pc.cpp:806-809 and siblings) switched back on
+mkdir -p "$OUT/timed"
+sed -E '/^ *\/\/fprintf\($/,/^ *\/\/\);$/ s,^( *)//,\1,' "$REF_ROOT/src/pc.cpp" > "$OUT/timed/pc_ref.cpp"
+sed -E '/^ *\/\/fprintf\($/,/^ *\/\/\);$/ s,^( *)//,\1,' "$OUT/seed/pc.cpp" > "$OUT/timed/pc_seed.cpp"
+pids=()
+( $CXX $FLAGS -c "$OUT/timed/pc_ref.cpp" -o "$OUT/timed/pc_ref.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$OUT/timed/pc_seed.cpp" -o "$OUT/timed/pc_seed.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+if [ -f "$ROOT/oracle/_ref/libgasal_gpu.so" ]; then
+  TOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/timed/pc_ref.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+  $CXX -o "$OUT/rabbitsalign_gasalgpu_timed" $TOBJS "$ROOT/oracle/_ref/libgasal_gpu.so" -Wl,-rpath,'$ORIGIN/../../oracle/_ref' -lz -lpthread
+fi
+TSOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/timed/pc_seed.o";; aln) echo "$OUT/obj_seed/aln.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_gpuseed_timed" $TSOBJS "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
 ls -la "$OUT"/rabbitsalign_*

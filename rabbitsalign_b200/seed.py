@@ -116,16 +116,17 @@ class Seeder:
         if rc != 0:
             raise SeedError(f"rsa_seed status {rc}: {self.lib.rsa_seed_last_error(self.h).decode()}")
 
-    def find_nams(self, reads: np.ndarray, roff: np.ndarray):
-        """-> (per_read[n] as READ_DTYPE, nams[total] as NAM_DTYPE): copies of the handle's pinned result buffers."""
+    def find_nams(self, reads: np.ndarray, roff: np.ndarray, copy: bool = True):
+        """-> (per_read[n] as READ_DTYPE, nams[total] as NAM_DTYPE).  copy=False returns views of the handle's pinned result
+        buffers (valid until the next call on this handle), which is what a C caller gets."""
         assert reads.dtype == np.uint8 and roff.dtype == np.int64
         n = len(roff) - 1
         pr, nm, tot = C.c_void_p(), C.c_void_p(), C.c_int64()
         self._check(self.lib.rsa_seed_find_nams(self.h, n, reads.ctypes.data, roff.ctypes.data, C.byref(pr), C.byref(nm), C.byref(tot)))
-        per = np.frombuffer((C.c_uint8 * (16 * n)).from_address(pr.value), dtype=READ_DTYPE).copy() if n else np.zeros(0, READ_DTYPE)
-        nams = (np.frombuffer((C.c_uint8 * (40 * tot.value)).from_address(nm.value), dtype=NAM_DTYPE).copy()
+        per = np.frombuffer((C.c_uint8 * (16 * n)).from_address(pr.value), dtype=READ_DTYPE) if n else np.zeros(0, READ_DTYPE)
+        nams = (np.frombuffer((C.c_uint8 * (40 * tot.value)).from_address(nm.value), dtype=NAM_DTYPE)
                 if tot.value else np.zeros(0, NAM_DTYPE))
-        return per, nams
+        return (per.copy(), nams.copy()) if copy else (per, nams)
 
     def stage(self, reads, roff):
         self._keep = (reads, roff)
