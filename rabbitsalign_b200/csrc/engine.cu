@@ -168,6 +168,8 @@ struct rsa_ext {
     bool fast_ok = false;
     int n_sms = 148;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_tb = nullptr, s_d2h = nullptr, s_plan = nullptr;
+    cudaStream_t s_cls[2] = {nullptr, nullptr};  // side streams for the column classes of one chunk
+    cudaEvent_t ev_cls_fork = nullptr, ev_cls_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr;  // orders the second DP stream behind what the caller put on the first
     int dp_toggle = 0;              // consecutive chunks alternate between the two DP streams so that the next
                                     // chunk's blocks fill the SMs while the previous kernel's last wave drains
@@ -734,14 +736,31 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     RedoHeader* redo = reinterpret_cast<RedoHeader*>(const_cast<uint8_t*>(d.blob) + p.off_redo);
     uint32_t* redo_list = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(d.blob) + p.off_redo + sizeof(RedoHeader));
     TbArgs tba{d.q, d.t, meta, info, diroff, d.scratch, d.res, h->sc, d.arena, d.arena_used, d.arena_cap};
-    // packed kernel, one launch per column class
+    // packed kernel, one launch per column class.  A chunk of variable-length reads (indel-rich 250-bp data: five or more
+    // classes) would run them back to back, each with its own partially filled last wave; classes are independent, so
+    // they are spread over the chunk's stream and two side streams and joined before the redo pass.
+    const bool spread = p.fast.size() > 1 && (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) == 0;
+    if (spread) {
+        CU_TRY(h, cudaEventRecord(h->ev_cls_fork, st));
+        for (int k = 0; k < 2; ++k) CU_TRY(h, cudaStreamWaitEvent(h->s_cls[k], h->ev_cls_fork, 0));
+    }
+    int cls_i = 0;
+    bool used_side[2] = {false, false};
     for (const auto& fc : p.fast) {
-        int rc = launch_fast_class(st, fc.L, fc.C, d.q, d.t, meta,
+        cudaStream_t cst = st;
+        if (spread && cls_i % 3 != 0) { cst = h->s_cls[cls_i % 3 - 1]; used_side[cls_i % 3 - 1] = true; }
+        ++cls_i;
+        int rc = launch_fast_class(cst, fc.L, fc.C, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
                                    fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen);
         if (rc != 0) { h->err = "no packed-kernel instance for L=" + std::to_string(fc.L) + " C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
+    for (int k = 0; k < 2; ++k)
+        if (used_side[k]) {
+            CU_TRY(h, cudaEventRecord(h->ev_cls_join[k], h->s_cls[k]));
+            CU_TRY(h, cudaStreamWaitEvent(st, h->ev_cls_join[k], 0));
+        }
     // exact kernel: statically routed pairs
     int begin = 0;
     for (int c = 0; c < 3; ++c) {
@@ -1209,6 +1228,11 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
     if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_cls_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    for (int k = 0; k < 2; ++k) {
+        if ((e = cudaStreamCreateWithFlags(&h->s_cls[k], cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_cls_join[k], cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
+    }
     {
         // the traceback stream outranks the DP stream: its small blocks are placed first whenever a DP block
         // retires, so the records of chunk k are not held back by the DP kernel of chunk k+1
@@ -1287,6 +1311,11 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_cls_fork) cudaEventDestroy(h->ev_cls_fork);
+    for (int k = 0; k < 2; ++k) {
+        if (h->s_cls[k]) { cudaStreamSynchronize(h->s_cls[k]); cudaStreamDestroy(h->s_cls[k]); }
+        if (h->ev_cls_join[k]) cudaEventDestroy(h->ev_cls_join[k]);
+    }
     if (h->s_tb) cudaStreamDestroy(h->s_tb);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->s_plan) cudaStreamDestroy(h->s_plan);

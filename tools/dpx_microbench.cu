@@ -21,11 +21,13 @@ static rsa::FastConsts g_consts;
 constexpr int CH = 8;
 
 enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL,
-          HFMA2, HMNMX2, FFMA, MIX_ALU_HFMA2, MIX_ALU3_HFMA2, MIX_ALU3_IMAD, N_OPS };
+          HFMA2, HMNMX2, FFMA, MIX_ALU_HFMA2, MIX_ALU3_HFMA2, MIX_ALU3_IMAD, HSET2, MIX_ALU_HSET2, MIX_DPX_HSET2, MIX_ALU3_HSET2, N_OPS };
 static const char* kNames[N_OPS] = {"VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "IADD3", "LOP3", "PRMT",
                                     "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (rsa::fast_cell, 2 cells per call)",
-                                    "HFMA2", "HMNMX2", "FFMA", "LOP3+HFMA2 1:1", "LOP3+HFMA2 3:1", "LOP3+IMAD 3:1"};
-static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0, CH, CH, CH, 2 * CH, 4 * CH, 4 * CH};
+                                    "HFMA2", "HMNMX2", "FFMA", "LOP3+HFMA2 1:1", "LOP3+HFMA2 3:1", "LOP3+IMAD 3:1",
+                                    "HSET2", "LOP3+HSET2 1:1", "VIADDMNMX+HSET2 1:1", "LOP3+HSET2 3:1"};
+static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0, CH, CH, CH, 2 * CH, 4 * CH, 4 * CH,
+                                         CH, 2 * CH, 2 * CH, 4 * CH};
 
 __device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -35,6 +37,18 @@ __device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// per-half compare of two f16x2 registers -> 0xFFFF / 0 per half (one HSET2).  On the biased, non-negative s16 values of
+// the packed DP (all below 0x7C00) the fp16 order of the bit patterns IS the integer order (denormals are not flushed).
+__device__ __forceinline__ uint32_t hset2_ge(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hset2_gt(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -159,6 +173,73 @@ __device__ __forceinline__ void cell_variant(const rsa::FastConsts& k, uint32_t 
     key = rsa::imad(h, k.k32, colconst);
 }
 
+// V4 (gap_extend == 1): the four direction facts as HSET2 masks (0xFFFF / 0 per half) instead of carry tricks:
+//   opened F  <=> F' >= F,  opened E <=> E' >= E,  H != diagonal <=> max(F,E,0) > diag+sub,  max(F,E,0) != F <=> max(F,E,0) > F.
+// A mask is the same in every bit of its half, so three bit-selects leave the cell's nibble replicated in all four nibble
+// positions and inserting it into the 4-column word needs no shift: 4 HSET2 + 4 LOP3 per cell pair instead of
+// 3 IADD3 + 2 IMAD + 3 LOP3 + SHF + LOP3.
+__device__ __forceinline__ void cell_v4(const rsa::FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
+                                        uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
+    const uint32_t tg = s + k.neg_xoe;
+    const uint32_t sx = s - k.x_pair;                           // diag + sub (ring subtraction: every half >= x)
+    const uint32_t u = __vimax3_s16x2(F, e, k.zero);
+    h = __vmaxs2(sx, u);
+    fn = __viaddmax_s16x2(F, k.neg_e, tg);
+    en = __viaddmax_s16x2(e, k.neg_e, tg);
+    const uint32_t mf = hset2_ge(fn, F), me = hset2_ge(en, e), md = hset2_gt(u, sx), mn = hset2_gt(u, F);
+    fl = rsa::bitsel(0x88888888u, mf, me);
+    fl = rsa::bitsel(0xCCCCCCCCu, fl, md);
+    fl = rsa::bitsel(0xEEEEEEEEu, fl, mn);
+    key = rsa::imad(h, k.k32, colconst);
+}
+
+__global__ void bench_cell_v4(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+    uint32_t S[CH], E[CH], qsel[CH];
+    uint32_t px = in[8] + threadIdx.x, py = in[9];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = k.zero; qsel[c] = in[10 + c]; }
+    uint32_t F = k.zero, Hl = k.zero, rowkey = 0, sink = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = CH - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
+        uint32_t acc = 0, key_prev = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uint32_t h, fn, en, fl, key;
+            cell_v4(k, S[c], F, E[c], rsa::key_colconst(c), h, fn, en, fl, key);
+            acc = rsa::bitsel(0x000F000Fu << (4 * (c & 3)), fl, acc);
+            if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
+            key_prev = key;
+            S[c] = h;
+            E[c] = en;
+            F = fn;
+            if ((c & 3) == 3) { sink ^= acc; acc = 0; }
+        }
+        Hl = F;
+        px += py;
+    }
+    uint32_t s = sink + rowkey + F;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s += S[c] + E[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) { cycles[blockIdx.x] = 0; cycles[gridDim.x + blockIdx.x] = 0; }
+}
+
+// exhaustive check of the HSET2-as-integer-compare claim on [0, 2048) x [0, 2048)
+__global__ void check_hset2(unsigned int* bad) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2047
+    if (a >= 2048) return;
+    for (uint32_t b = 0; b < 2048; ++b) {
+        const uint32_t pa = a | (b << 16), pb = b | (a << 16);
+        const uint32_t ge = hset2_ge(pa, pb), gt = hset2_gt(pa, pb);
+        const uint32_t want_ge = (a >= b ? 0xFFFFu : 0u) | (b >= a ? 0xFFFF0000u : 0u);
+        const uint32_t want_gt = (a > b ? 0xFFFFu : 0u) | (b > a ? 0xFFFF0000u : 0u);
+        if (ge != want_ge || gt != want_gt) atomicAdd(bad, 1u);
+    }
+}
+
 template <int V>
 __global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
     uint32_t S[CH], E[CH], qsel[CH];
@@ -207,7 +288,8 @@ void run_variant(int n_sms, int threads, uint32_t* d_out, uint32_t* d_in, unsign
     CHECK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 3; ++rep) {
         CHECK(cudaEventRecord(e0));
-        bench_cell_variant<V><<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
+        if (V == 4) bench_cell_v4<<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
+        else bench_cell_variant<(V == 4 ? 2 : V)><<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
         CHECK(cudaEventRecord(e1));
         CHECK(cudaEventSynchronize(e1));
     }
@@ -309,7 +391,21 @@ int main(int argc, char** argv) {
         if (!quick) {
             run_variant<2>(n_sms, threads, d_out, d_in, d_cyc);
             run_variant<3>(n_sms, threads, d_out, d_in, d_cyc);
+            run_variant<4>(n_sms, threads, d_out, d_in, d_cyc);
+            run<HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_DPX_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_ALU3_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         }
+    }
+    if (!quick) {
+        unsigned int* d_bad;
+        CHECK(cudaMalloc(&d_bad, sizeof(unsigned int)));
+        CHECK(cudaMemset(d_bad, 0, sizeof(unsigned int)));
+        check_hset2<<<16, 128>>>(d_bad);
+        unsigned int bad = 0;
+        CHECK(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+        printf("{\"test\": \"HSET2 as integer compare on [0,2048)^2\", \"mismatches\": %u}\n", bad);
     }
     return 0;
 }
