@@ -315,7 +315,7 @@ struct PlanInput {
 // A pair may ride the packed kernel when its shape is inside what that kernel was instantiated for.
 inline bool fast_shape_ok(int qlen, int tlen, int match = 2) {
     return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen &&
-           match * qlen <= 1023;  // the maximum-tracking key holds (score << 5 | column) in a positive s16
+           fast_key_ok(qlen, match);  // the maximum-tracking key holds (score << 5 or 6 | column) in a positive s16
 }
 
 // per-query-length geometry, computed once
@@ -343,7 +343,7 @@ size_t blob_layout(ChunkPlan& plan, int64_t n) {
     plan.off_info = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
     plan.off_diroff = off; off = align_up(off + sizeof(uint64_t) * n, 16);
     plan.off_list = off;   off = align_up(off + sizeof(uint32_t) * n, 16);
-    plan.off_groups = off; off = align_up(off + sizeof(FastGroup) * (size_t)(n + 8 * 64), 16);
+    plan.off_groups = off; off = align_up(off + sizeof(FastGroup) * (size_t)(n + 8 * 128), 16);
     plan.off_redo = off;   off = align_up(off + sizeof(RedoHeader) + sizeof(uint32_t) * (size_t)(n + 4), 16);
     plan.blob_bytes = off;
     return off;
@@ -474,7 +474,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         const FastGroup empty{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
         size_t k = 0;
         int cur_C = -1, cur_L = -1;
-        constexpr int kGroupPad = 4;  // classes start on a warp boundary for either group width (4 or 2 groups/warp)
+        constexpr int kGroupPad = 8;  // classes start on a warp boundary for every group width (8, 4 or 2 groups per warp)
         while (k < m) {
             const uint32_t a = sidx[k], ka = skey[k];
             const uint32_t ql = ka >> 16;
@@ -586,7 +586,9 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
     const int64_t hi_cap = std::min<int64_t>(in.n, lo + std::min<int64_t>(kMaxChunkPairs, in.max_pairs));
     const uint64_t cap2 = in.scratch_cap > 2048 ? 2 * ((uint64_t)in.scratch_cap - 2048) : 0;  // budget in half-row bytes
     const int64_t fast_tmax = std::min<int64_t>(in.max_tlen, kFastMaxTlen);
-    const int64_t fast_qmax = in.exact_only ? -1 : std::min<int64_t>(kFastMaxQlen, 1023 / std::max(1, in.match));
+    const int64_t fast_qmax = in.exact_only ? -1 : kFastMaxQlen;
+    bool key_ok[kPlanQ];  // the maximum-tracking key of this |q| fits its s16 half with this handle's match score
+    for (int q = 0; q < kPlanQ; ++q) key_ok[q] = fast_key_ok(q, in.match);
     uint64_t scratch2 = 0, arena = 0;
     int64_t cells = 0, hi = lo, n_fast = 0, n_failed = 0;
     int64_t qprev = in.qoff[lo];
@@ -614,7 +616,7 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
             return RSA_EXT_ERR_QUERY_LEN;
         }
         if (qnext - q0 > kMaxChunkSeqBytes || tnext - t0 > kMaxChunkSeqBytes) { if (hi > lo) break; }
-        if (ql >= kFastMinQlen && ql <= fast_qmax && tl >= 1 && tl <= fast_tmax) {
+        if (ql >= kFastMinQlen && ql <= fast_qmax && tl >= 1 && tl <= fast_tmax && key_ok[ql]) {
             // packed candidate: what it adds to the bound.  The accumulators of the current |q| live in registers
             // (batches are runs of equal read lengths); they go back to the tables when |q| changes.
             if (ql != cur_q) {
@@ -665,7 +667,7 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
     plan.scratch_bytes = (scratch2 + 1) / 2 + 2048;  // upper bound (+ the 256-byte alignments of the packed region / redo base)
     // launch geometry from the per-length counts: classes in increasing |q| (= increasing C within 8 lanes, then 16 lanes),
     // each padded to whole warps of groups
-    constexpr int kGroupPad = 4;
+    constexpr int kGroupPad = 8;
     uint32_t pos = 0;
     int n_groups = 0, cur_C = -1, cur_L = -1;
     for (int q = 0; q < kPlanQ; ++q) {

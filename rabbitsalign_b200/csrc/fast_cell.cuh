@@ -17,14 +17,16 @@ struct FastConsts {
     uint32_t k_f, k_e, k_d, k_n;
     uint32_t x_pair;   // (mismatch, mismatch): biased profile value of a zero-scoring cell
     uint32_t prof_match;  // match + mismatch (byte)
-    uint32_t k32, one, minus1;  // multipliers kept in registers so that the adds below stay IMADs (FMA pipe)
+    uint32_t k32, k64, one, minus1;  // multipliers kept in registers so that the adds below stay IMADs (FMA pipe)
     int bias;
 };
 
 __host__ __device__ inline uint32_t pair16(int v) { return ((uint32_t)(v & 0xFFFF) << 16) | (uint32_t)(v & 0xFFFF); }
 
-// per-column constant of the maximum-tracking key: (31 - column) - bias*32 in both halves, as a ring constant
-__host__ __device__ constexpr uint32_t key_colconst(int c) { return (uint32_t)(31 - c - kBias * 32) * 0x00010001u; }
+// per-column constant of the maximum-tracking key: (2^B - 1 - column) - bias * 2^B in both halves, as a ring constant.
+// B = 5 column bits for 8- and 16-lane groups (C <= 32 columns per lane), 6 for 4-lane groups (C <= 40).
+template <int B = 5>
+__host__ __device__ constexpr uint32_t key_colconst(int c) { return (uint32_t)(((1 << B) - 1) - c - kBias * (1 << B)) * 0x00010001u; }
 
 __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
     FastConsts k;
@@ -40,6 +42,7 @@ __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
     k.x_pair = pair16(sc.mismatch);
     k.prof_match = (uint32_t)(sc.match + sc.mismatch);
     k.k32 = 32u;
+    k.k64 = 64u;
     k.one = 1u;
     k.minus1 = 0xFFFFFFFFu;
     return k;
@@ -73,7 +76,7 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 //      term and the -bias*32 correction (ring constant), so the key of an all-zero cell is just its column term.
 // ALU pipe: VIMNMX3, 3x VIADDMNMX (H takes its "- mismatch" inside the fused add+max, so diag+sub is never
 // materialised), 3x IADD3, 3x LOP3, one add.  FMA pipe: the adds below written as IMADs.
-__device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
+__device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst, uint32_t kmul,
                                           uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
     const uint32_t tg = s + k.neg_xoe;
     const uint32_t u = __vimax3_s16x2(F, e, k.zero);
@@ -87,7 +90,7 @@ __device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t s, uint3
     fl = bitsel(0x80008000u, fo, eo);
     fl = bitsel(0xC000C000u, fl, nd);
     fl = bitsel(0xE000E000u, fl, nf);
-    key = imad(h, k.k32, colconst);                               // ((h-bias) << 5) | (31 - column), FMA pipe
+    key = imad(h, kmul, colconst);                                // ((h-bias) << B) | (2^B - 1 - column), FMA pipe
 }
 
 }  // namespace rsa

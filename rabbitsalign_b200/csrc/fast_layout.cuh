@@ -1,6 +1,6 @@
 // fast_layout.cuh -- geometry of the packed kernel's column ownership and direction-bit scratch.
 //
-// A "group" is L lanes (8 for |q| <= 256, 16 for 257..512) working on TWO pairs of equal query length (pair A in the low 16-bit halves of every
+// A "group" is L lanes (4 for |q| <= 160, 8 for 161..256, 16 for 257..512) working on TWO pairs of equal query length (pair A in the low 16-bit halves of every
 // packed register, pair B in the high halves).  The query's columns are dealt to the 8 lanes in order:
 // with C = ceil(qlen/L), the first `rem` lanes own C columns and the remaining lanes own C-1, so that
 // every owned column is a real query base (no padding columns exist).
@@ -21,7 +21,10 @@
 namespace rsa {
 
 // lanes per group as a function of the query length (one rule for planner, kernels and traceback)
-__host__ __device__ inline int fast_lanes_for(int qlen) { return qlen <= 256 ? 8 : 16; }
+// 4 lanes up to 160 bases (C <= 40 columns per lane: the per-row overhead of a lane -- shuffles, profile loads, maximum
+// tracking, loop control -- is spread over twice the columns of an 8-lane group and the wavefront skew shrinks from 7 to 3
+// idle steps per window), 8 lanes up to 256 (C <= 32), 16 lanes beyond.
+__host__ __device__ inline int fast_lanes_for(int qlen) { return qlen <= 160 ? 4 : (qlen <= 256 ? 8 : 16); }
 
 struct FastGeom {
     int L;    // lanes per group

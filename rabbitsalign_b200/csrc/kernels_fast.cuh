@@ -7,10 +7,10 @@
 //   * inter-query packing: every 32-bit register holds the same DP quantity of TWO pairs of equal query
 //     length (pair A in the low 16 bits, pair B in the high 16 bits), so one DPX instruction
 //     (VIMNMX3.S16x2, VIADDMNMX.S16x2, VIMNMX.S16x2) advances two cells;
-//   * 8 lanes ("group") sweep one such double-pair as an anti-diagonal wavefront: lane l owns a contiguous
-//     run of query columns in registers (H of the previous row, E, column maximum) and is one target row
-//     behind lane l-1; H and F of a lane's last column reach the next lane with one shuffle each per row;
-//     a warp carries 4 groups = 8 pairs;
+//   * L lanes ("group"; 4 for |q| <= 160, 8 up to 256, 16 beyond) sweep one such double-pair as an anti-diagonal
+//     wavefront: lane l owns a contiguous run of C = ceil(|q|/L) query columns in registers (H of the previous row, E)
+//     and is one target row behind lane l-1; H and F of a lane's last column reach the next lane with one shuffle each
+//     per row; a warp carries 32/L groups;
 //   * scores are kept BIASED (value + kBias in every half) so every half stays a non-negative 16-bit
 //     number: plain 32-bit IADD3 then adds/subtracts both halves at once with no cross-half borrow, and a
 //     "difference >= 1" predicate becomes one IADD3 with a constant that carries into a chosen bit;
@@ -20,10 +20,9 @@
 //   * the four direction facts per cell (F opened, E opened, H != diagonal, max(F,E,0) != F) are gathered
 //     with bit-selects into one nibble per cell per pair and streamed to a global scratch tile
 //     (fast_layout.cuh); the match/mismatch bit is not stored (the traceback recomputes it from the bases);
-//   * the end cell: per lane the packed running maximum, the row where it last strictly improved and a
-//     sticky "same maximum seen again in a later row" flag, plus a per-column maximum.  If the maximum is
-//     unique in the sense the reference's first-maximum rule needs, the end cell follows
-//     from those; otherwise the pair is flagged and the exact kernel recomputes the end cell (score-only).
+//   * the end cell: every cell's key (H << B | 2^B-1 - column in lane), B = 5 or 6 column bits, is one IMAD; per lane and
+//     half the kernel keeps the key of the first cell, in the reference's visiting order (8-row block, column, row in
+//     block), among the cells with the largest H seen so far (exact, no fallback);
 //   * symbols outside {A,C,G,T,N}: the pair is flagged and fully redone by the exact kernel.
 #pragma once
 #include <mutex>
@@ -36,14 +35,14 @@
 namespace rsa {
 
 constexpr int kFastMinQlen = 8;
-constexpr int kFastMaxC = 32;
-constexpr int kFastMaxQlen = 16 * kFastMaxC;  // 512: 8 lanes x C<=32 up to 256 bases, 16 lanes x C<=32 beyond
+constexpr int kFastMaxC = 40;                 // 4-lane groups: C <= 40 (160 bases); 8- and 16-lane groups: C <= 32
+constexpr int kFastMaxQlen = 16 * 32;         // 512: 4 lanes x C<=40, 8 lanes x C<=32 up to 256 bases, 16 lanes x C<=32 beyond
 constexpr int kFastMaxTlen = 2047;
 // 8-lane groups: 4 groups per warp, 4 warps per block; 16-lane groups: 2 groups per warp, 2 warps per block
 // (their shared-memory ring is deeper and wider)
 __host__ __device__ constexpr int fast_groups_per_warp(int L) { return 32 / L; }
-__host__ __device__ constexpr int fast_warps_per_block(int L) { return L == 8 ? 4 : 2; }
-__host__ __device__ constexpr int fast_ring_slots(int L) { return L == 8 ? 16 : 32; }  // >= L - 1 + 4, power of two
+__host__ __device__ constexpr int fast_warps_per_block(int L) { return L == 16 ? 2 : 4; }
+__host__ __device__ constexpr int fast_ring_slots(int L) { return L == 4 ? 8 : (L == 8 ? 16 : 32); }  // >= L - 1 + 4, power of two
 // (Tracing pairs back inside this kernel was tried in round 1 and dropped: 1.36 vs 1.50 TCUPS per step)
 
 struct FastGroup {
@@ -95,7 +94,11 @@ __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)
 // per pair (H = unbiased score < 1024, i.e. match * |q| <= 1023: checked per pair by the planner).  The larger key wins, i.e. the larger H and, for equal H in one row,
 // the smaller column -- the reference's order inside a row (SURVEY.md 8a rule 3).  Building the key is one
 // IMAD (FMA pipe, otherwise idle); no per-column maximum registers are needed.
-constexpr uint32_t kColMask = 0x001F001Fu;
+// 4-lane groups own up to 40 columns per lane: 6 column bits, H < 512 (match * |q| <= 511, |q| <= 160).
+__host__ __device__ constexpr int fast_col_bits(int L) { return L == 4 ? 6 : 5; }
+__host__ __device__ inline bool fast_key_ok(int qlen, int match) {
+    return match * qlen <= (fast_lanes_for(qlen) == 4 ? 511 : 1023);
+}
 
 template <int L, int C, bool HASN>
 struct FastDp {
@@ -120,6 +123,9 @@ struct FastDp {
         firstrow[0] = firstrow[1] = 0;
         constexpr int NW = (C + 3) / 4;
         constexpr int RS = fast_ring_slots(L);
+        constexpr int CB = fast_col_bits(L);
+        constexpr uint32_t kColMask = (uint32_t)((1 << CB) - 1) * 0x00010001u;
+        const uint32_t kmul = CB == 6 ? k.k64 : k.k32;
         const int rmax = rows > 0 ? rows - 1 : 0;
         uint2 pr;
         {
@@ -153,7 +159,7 @@ struct FastDp {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
                     if (c < C - 1 || wide) {
                         uint32_t h, fn, en, fl, key;
-                        fast_cell(k, S[c], F, E[c], key_colconst(c), h, fn, en, fl, key);
+                        fast_cell(k, S[c], F, E[c], key_colconst<CB>(c), kmul, h, fn, en, fl, key);
                         acc = bitsel(0xF000F000u, fl, acc >> 4);
                         if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
                         else if (c == C - 1) rowkey = __vmaxs2(rowkey, key);
@@ -216,7 +222,7 @@ struct FastDp {
 };
 
 template <int L, int C>
-__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))
+__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))  // (L = 4 and 8 alike)
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
@@ -280,7 +286,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         // carries the PRMT selector that expands to the per-half "query base is not N" mask
         qsel[c] = ca | ((8u | ca) << 4) | ((4u + cb) << 8) | ((12u + cb) << 12) | ((msel ^ 0x4444u) << 16);
     }
-    const unsigned gmask = (L == 16 ? 0xFFFFu : 0xFFu) << (L * gi);
+    const unsigned gmask = ((1u << L) - 1u) << (L * gi);
     bad_a = (__ballot_sync(0xFFFFFFFFu, bad_a) & gmask) != 0;
     bad_b = (__ballot_sync(0xFFFFFFFFu, bad_b) & gmask) != 0;
     const bool warp_has_n = __any_sync(0xFFFFFFFFu, has_n);
@@ -307,8 +313,9 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     for (int h = 0; h < 2; ++h) {
         const uint32_t pi = h ? grp.b : grp.a;
         const bool bad = h ? bad_b : bad_a;
+        constexpr int CB = fast_col_bits(L);
         const int kh = half_s(bestkey, h);
-        const int mine = kh >> 5;
+        const int mine = kh >> CB;
         int S = mine;
 #pragma unroll
         for (int off = L / 2; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(0xFFFFFFFFu, S, off));
@@ -317,7 +324,7 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
 #pragma unroll
         for (int off = L / 2; off >= 1; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));
         const int wl = (S > 0) ? (key & 0xFF) : 0;  // winner lane of the group (S == 0: trackers stay at (0,0))
-        const int qend = __shfl_sync(0xFFFFFFFFu, col0 + (31 - (kh & 31)), wl, L);
+        const int qend = __shfl_sync(0xFFFFFFFFu, col0 + (((1 << CB) - 1) - (kh & ((1 << CB) - 1))), wl, L);
         const int tend = __shfl_sync(0xFFFFFFFFu, firstrow[h], wl, L);
         if (!live || (h == 1 && grp.b == grp.a) || gl != h) continue;
         my_pair = (int)pi;
@@ -533,14 +540,24 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
             default: return -1;
         }
     }
+    if (L == 4) {
+        switch (C) {
+#define RSA_FAST_CASE4(c) case c: launch_fast_one<4, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+            RSA_FAST_CASE4(2) RSA_FAST_CASE4(3) RSA_FAST_CASE4(4) RSA_FAST_CASE4(5) RSA_FAST_CASE4(6) RSA_FAST_CASE4(7) RSA_FAST_CASE4(8)
+            RSA_FAST_CASE4(9) RSA_FAST_CASE4(10) RSA_FAST_CASE4(11) RSA_FAST_CASE4(12) RSA_FAST_CASE4(13) RSA_FAST_CASE4(14)
+            RSA_FAST_CASE4(15) RSA_FAST_CASE4(16) RSA_FAST_CASE4(17) RSA_FAST_CASE4(18) RSA_FAST_CASE4(19) RSA_FAST_CASE4(20)
+            RSA_FAST_CASE4(21) RSA_FAST_CASE4(22) RSA_FAST_CASE4(23) RSA_FAST_CASE4(24) RSA_FAST_CASE4(25) RSA_FAST_CASE4(26)
+            RSA_FAST_CASE4(27) RSA_FAST_CASE4(28) RSA_FAST_CASE4(29) RSA_FAST_CASE4(30) RSA_FAST_CASE4(31) RSA_FAST_CASE4(32)
+            RSA_FAST_CASE4(33) RSA_FAST_CASE4(34) RSA_FAST_CASE4(35) RSA_FAST_CASE4(36) RSA_FAST_CASE4(37) RSA_FAST_CASE4(38)
+            RSA_FAST_CASE4(39) RSA_FAST_CASE4(40)
+#undef RSA_FAST_CASE4
+            default: return -1;
+        }
+    }
     switch (C) {
 #define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
-        RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6)
-        RSA_FAST_CASE(7) RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12)
-        RSA_FAST_CASE(13) RSA_FAST_CASE(14) RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18)
-        RSA_FAST_CASE(19) RSA_FAST_CASE(20) RSA_FAST_CASE(21) RSA_FAST_CASE(22) RSA_FAST_CASE(23) RSA_FAST_CASE(24)
-        RSA_FAST_CASE(25) RSA_FAST_CASE(26) RSA_FAST_CASE(27) RSA_FAST_CASE(28) RSA_FAST_CASE(29) RSA_FAST_CASE(30)
-        RSA_FAST_CASE(31) RSA_FAST_CASE(32)
+        RSA_FAST_CASE(21) RSA_FAST_CASE(22) RSA_FAST_CASE(23) RSA_FAST_CASE(24) RSA_FAST_CASE(25) RSA_FAST_CASE(26)
+        RSA_FAST_CASE(27) RSA_FAST_CASE(28) RSA_FAST_CASE(29) RSA_FAST_CASE(30) RSA_FAST_CASE(31) RSA_FAST_CASE(32)
 #undef RSA_FAST_CASE
         default: return -1;
     }

@@ -76,7 +76,7 @@ struct PlanArgs {
 };
 
 __device__ __forceinline__ bool plan_fast_shape_ok(int qlen, int tlen, int match) {
-    return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen && match * qlen <= 1023;
+    return qlen >= kFastMinQlen && qlen <= kFastMaxQlen && tlen >= 1 && tlen <= kFastMaxTlen && fast_key_ok(qlen, match);
 }
 
 constexpr int kPlanThreads = 256;

@@ -127,7 +127,7 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             uint32_t h, fn, en, fl, key;
-            rsa::fast_cell(k, S[c], F, E[c], rsa::key_colconst(c), h, fn, en, fl, key);
+            rsa::fast_cell(k, S[c], F, E[c], rsa::key_colconst(c), k.k32, h, fn, en, fl, key);
             acc = rsa::bitsel(0xF000F000u, fl, acc >> 4);
             if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
             key_prev = key;

@@ -1,0 +1,17 @@
+#!/bin/bash
+set -x
+cd /root/repo
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py tests/test_gpu_alninfo.py tests/test_gpu_reference_gpu.py -m gpu -x -q > gpurun_out/r2c11_pytest.txt 2>&1
+tail -5 gpurun_out/r2c11_pytest.txt
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-legs > gpurun_out/r2c11_bench.json 2> gpurun_out/r2c11_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2c11_bench.json'))
+print("value", round(d['value']), "e2e", round(d['e2e']['value']), "roofline", d['roofline']['achieved'], d['roofline']['frac'], "tb_ms", d['roofline'].get('tb_ms'), "dp_ms", d['roofline'].get('dp_ms'))
+PY
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-legs --read-len 100 --pairs 524288 > gpurun_out/r2c11_bench_100.json 2>> gpurun_out/r2c11_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2c11_bench_100.json'))
+print("100bp value", round(d['value']), "e2e", round(d['e2e']['value']))
+PY
