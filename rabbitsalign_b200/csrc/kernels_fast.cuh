@@ -153,7 +153,6 @@ struct FastDp {
                 // ---- phase 2
                 uint32_t F = (gl == 0) ? k.zero : Fl;
                 uint32_t rowkey = 0, acc = 0, Fsave = F, key_prev = 0;
-                uint32_t words[NW];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
@@ -172,15 +171,13 @@ struct FastDp {
                         if (!(c & 1)) {}  // (an even last column has no pending key)
                         else rowkey = __vmaxs2(rowkey, key_prev);
                     }
-                    if ((c & 3) == 3) { words[c >> 2] = acc; acc = 0; }
-                    else if (c == C - 1) words[c >> 2] = acc >> (4 * (3 - (c & 3)));  // right-align partial word
+                    // direction words of this lane and row: parked in this lane's shared-memory ring (as soon as a word is
+                    // complete, so that it does not occupy a register) until every lane of the group has reached the same row
+                    if ((c & 3) == 3) { ring[(((s & (RS - 1)) * NW + (c >> 2)) << 5) + lane] = acc; acc = 0; }
+                    else if (c == C - 1) ring[(((s & (RS - 1)) * NW + (c >> 2)) << 5) + lane] = acc >> (4 * (3 - (c & 3)));  // right-align partial word
                 }
                 Hlast = wide ? S[C - 1] : S[(C >= 2) ? C - 2 : 0];
                 Fout = wide ? F : Fsave;
-                // direction words of this lane and row: parked in this lane's shared-memory ring until every
-                // lane of the group has reached the same row (see below)
-#pragma unroll
-                for (int wv = 0; wv < NW; ++wv) ring[(((s & (RS - 1)) * NW + wv) << 5) + lane] = words[wv];
                 // Running maximum of this lane, per half, kept as the FIRST cell in the reference's visiting order
                 // (8-row block, column, row in block) among the cells seen so far with the largest H:
                 //   row H > best H                      -> this row's key wins;
@@ -222,7 +219,9 @@ struct FastDp {
 };
 
 template <int L, int C>
-__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))  // (L = 4 and 8 alike)
+// (4-lane groups with C = 33..40 columns need ~250 registers: two blocks per SM.  Capping them at 168 registers for three
+// blocks spills ~55 words per thread and measured slower: DP phase 1737 vs 1811 GCUPS, value 1691 vs 1745.)
+__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
