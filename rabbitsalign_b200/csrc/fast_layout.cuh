@@ -11,8 +11,8 @@
 // chunks are contiguous (one 128-byte line), so the DP kernel stores full lines with one STG.128 per lane and
 // the traceback, which moves diagonally, finds ~2-3 consecutive path cells in the chunk it just fetched.
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
-//     bit3 open_f   (F of the next column opened from the diagonal; reference bit3 is the negation)
-//     bit2 open_e   (reference bit2 negated)
+//     bit3 F of the next column NOT opened from the diagonal (extended; = reference bit3)
+//     bit2 E of the next row NOT opened from the diagonal (= reference bit2)
 //     bit1 not_diag (H != diag+sub)
 //     bit0 not_f    (max(F,E,0) != F, i.e. with not_diag: source is E -> code 2, else F -> code 3)
 #pragma once

@@ -38,6 +38,7 @@ constexpr int kFastMinQlen = 8;
 constexpr int kFastMaxC = 40;                 // 4-lane groups: C <= 40 (160 bases); 8- and 16-lane groups: C <= 32
 constexpr int kFastMaxQlen = 16 * 32;         // 512: 4 lanes x C<=40, 8 lanes x C<=32 up to 256 bases, 16 lanes x C<=32 beyond
 constexpr int kFastMaxTlen = 2047;
+constexpr int kFastLutBytes = 64;             // two 8-word profile tables (pair A, pair B) at the head of the shared memory
 // 8-lane groups: 4 groups per warp, 4 warps per block; 16-lane groups: 2 groups per warp, 2 warps per block
 // (their shared-memory ring is deeper and wider)
 __host__ __device__ constexpr int fast_groups_per_warp(int L) { return 32 / L; }
@@ -61,9 +62,10 @@ struct RedoHeader {
     unsigned long long scratch_used; // bytes handed out from the redo scratch region
 };
 
-// Can the packed kernel represent this scoring?  (biased halves must stay in [0, 2^12) for the flag trick)
+// Can the packed kernel represent this scoring?  (biased halves must stay positive; the signed profile bytes
+// score - gap_oe [- 1] must all be negative and fit a byte: fast_cell.cuh)
 __host__ inline bool fast_scoring_ok(const Scoring& sc) {
-    return sc.match > 0 && sc.mismatch > 0 && sc.gap_ext >= 0 && sc.gap_oe >= sc.gap_ext &&
+    return sc.match > 0 && sc.mismatch > 0 && sc.gap_ext >= 0 && sc.gap_oe >= sc.gap_ext && sc.gap_oe > sc.match &&
            sc.mismatch + sc.gap_oe < kBias - 2 && sc.match + sc.mismatch < 128 &&
            sc.match * kFastMinQlen < 1024;  // per-pair bound match*|q| <= 1023 is applied by the planner
 }
@@ -77,15 +79,6 @@ __device__ __forceinline__ uint32_t base_code(uint32_t nib) {
     c = (nib == 4u) ? 3u : c;
     c = (nib == 0xEu) ? 4u : c;
     return c;
-}
-
-// 4-byte biased score profile of one target-row code: byte k = score(query code k, target) + mismatch.
-// code 0..3 = base, 4 = N (scores 0 against everything), 5 = row past the pair's own window (everything
-// mismatches, so H only decays there and can never reach the pair's maximum).
-__host__ __device__ inline uint32_t profile_word(uint32_t code, const FastConsts& k) {
-    if (code < 4u) return k.prof_match << (8u * code);
-    if (code == 4u) return (k.x_pair & 0xFFu) * 0x01010101u;
-    return 0u;
 }
 
 __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
@@ -131,7 +124,7 @@ struct FastDp {
         {
             const uint32_t tc = tcodes[0];
             pr.x = lut[tc & 0xFu];
-            pr.y = lut[tc >> 4];
+            pr.y = lut[8u + (tc >> 4)];
         }
         for (int s = 0; s < nsteps; ++s) {
             // ---- phase 0
@@ -141,40 +134,42 @@ struct FastDp {
             const uint32_t tcn = tcodes[min(max(r + 1, 0), rmax)];
             uint2 prn;
             prn.x = lut[tcn & 0xFu];
-            prn.y = lut[tcn >> 4];
+            prn.y = lut[8u + (tcn >> 4)];
             if (r >= 0 && r < rows) {
                 // ---- phase 1
 #pragma unroll
                 for (int c = C - 1; c >= 0; --c) {
                     uint32_t sub = prmt(pr.x, pr.y, qsel[c]);
-                    if (HASN) sub = bitsel(prmt(0xFFFFFFFFu, 0u, qsel[c] >> 16), sub, k.x_pair);
+                    if (HASN) sub = bitsel(prmt(0xFFFFFFFFu, 0u, qsel[c] >> 16), sub, k.sub_n);
                     S[c] = (c == 0 ? Hl_prev : S[c - 1]) + sub;
                 }
                 // ---- phase 2
                 uint32_t F = (gl == 0) ? k.zero : Fl;
-                uint32_t rowkey = 0, acc = 0, Fsave = F, key_prev = 0;
+                uint32_t rowkey = 0, nib_even = 0, p_lo = 0, Fsave = F, key_prev = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
+                    uint32_t nib = 0;           // (absent last column of a narrow lane: zero nibble)
                     if (c < C - 1 || wide) {
-                        uint32_t h, fn, en, fl, key;
-                        fast_cell(k, S[c], F, E[c], key_colconst<CB>(c), kmul, h, fn, en, fl, key);
-                        acc = bitsel(0xF000F000u, fl, acc >> 4);
+                        uint32_t h, fn, en, key;
+                        fast_cell(k, S[c], F, E[c], key_colconst<CB>(c), kmul, h, fn, en, nib, key);
                         if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
                         else if (c == C - 1) rowkey = __vmaxs2(rowkey, key);
                         key_prev = key;
                         S[c] = h;
                         E[c] = en;
                         F = fn;
-                    } else {
-                        acc >>= 4;  // absent last column of a narrow lane: keep the nibble positions
-                        if (!(c & 1)) {}  // (an even last column has no pending key)
-                        else rowkey = __vmaxs2(rowkey, key_prev);
+                    } else if (c & 1) {
+                        rowkey = __vmaxs2(rowkey, key_prev);  // (an even last column has no pending key)
                     }
-                    // direction words of this lane and row: parked in this lane's shared-memory ring (as soon as a word is
-                    // complete, so that it does not occupy a register) until every lane of the group has reached the same row
-                    if ((c & 3) == 3) { ring[(((s & (RS - 1)) * NW + (c >> 2)) << 5) + lane] = acc; acc = 0; }
-                    else if (c == C - 1) ring[(((s & (RS - 1)) * NW + (c >> 2)) << 5) + lane] = acc >> (4 * (3 - (c & 3)));  // right-align partial word
+                    // direction words of this lane and row (fast_cell.cuh: dir_pair / dir_word): parked in this lane's
+                    // shared-memory ring as soon as a word is complete, so that it does not occupy a register, until every
+                    // lane of the group has reached the same row
+                    uint32_t* const slot = ring + ((((s & (RS - 1)) * NW + (c >> 2)) << 5) + lane);
+                    if ((c & 3) == 0) { nib_even = nib; if (c == C - 1) *slot = nib; }
+                    else if ((c & 3) == 1) { p_lo = dir_pair(k, nib_even, nib); if (c == C - 1) *slot = p_lo; }
+                    else if ((c & 3) == 2) { nib_even = nib; if (c == C - 1) *slot = dir_word(p_lo, nib); }
+                    else *slot = dir_word(p_lo, dir_pair(k, nib_even, nib));
                 }
                 Hlast = wide ? S[C - 1] : S[(C >= 2) ? C - 2 : 0];
                 Fout = wide ? F : Fsave;
@@ -227,8 +222,8 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
                uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad) {
     extern __shared__ uint8_t fast_smem[];
-    uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 words
-    if (threadIdx.x < 8) lut[threadIdx.x] = profile_word(threadIdx.x, k);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 profile words for pair A (low halves), 8 for pair B
+    if (threadIdx.x < 16) lut[threadIdx.x] = profile_word(threadIdx.x & 7, k, threadIdx.x >> 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int GPW = fast_groups_per_warp(L), WPB = fast_warps_per_block(L);
     const int gi = lane / L, gl = lane % L;
@@ -239,9 +234,9 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     grp.a = 0xFFFFFFFFu; grp.b = 0xFFFFFFFFu; grp.dir_off = 0; grp.qlen = 0; grp.rows = 0;
     if (g_index < n_groups) grp = groups[g_index];
     const bool live = grp.a != 0xFFFFFFFFu;
-    uint8_t* tcodes = fast_smem + 32 + (size_t)(warp * GPW + gi) * rows_pad;
+    uint8_t* tcodes = fast_smem + kFastLutBytes + (size_t)(warp * GPW + gi) * rows_pad;
     constexpr int kRingWords = fast_ring_slots(L) * ((C + 3) / 4) * 32;  // per warp: row slots x words x lanes
-    uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + 32 + (size_t)WPB * GPW * rows_pad) + warp * kRingWords;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + kFastLutBytes + (size_t)WPB * GPW * rows_pad) + warp * kRingWords;
 
     // ---- staging: target profiles into shared memory, query selectors into registers ----------------
     bool bad_a = false, bad_b = false;
@@ -503,7 +498,7 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
     constexpr int WPB = fast_warps_per_block(L);
     const int groups_per_block = WPB * fast_groups_per_warp(L);
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-    const size_t smem = 32 + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4;
+    const size_t smem = kFastLutBytes + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4;
     if (smem > 48 * 1024) {
         // Long windows / wide lanes need the opt-in shared-memory limit.  The attribute belongs to the FUNCTION (per
         // device), not to the launch: setting it to this launch's size raced with other workers launching the same

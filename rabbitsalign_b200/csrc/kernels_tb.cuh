@@ -29,18 +29,18 @@ __device__ __forceinline__ uint32_t tb_fetch(const TbCtx& c, int i, int j) {
         const uint8_t b = c.dir[(size_t)i * c.row_bytes + (j >> 1)];
         return (j & 1) ? (b >> 4) : (b & 0xFu);
     }
-    // fast layout stores [open_f, open_e, not_diag, not_f] per cell; rebuild the reference code.
+    // fast layout stores [F not opened, E not opened, not_diag, not_f] per cell (fast_layout.cuh): the two gap bits are the
+    // reference's bits 3 and 2 as they are; rebuild the reference's 2-bit source code.
     const uint32_t f = fast_fetch_flags(c.fg, c.dir, i, j, c.half);
-    const bool not_diag = f & 2u, not_f = f & 1u, open_e = f & 4u, open_f = f & 8u;
     uint32_t lo2;
-    if (!not_diag) {
+    if (!(f & 2u)) {
         const uint32_t qb = nibble_of(c.q[j]), tb = nibble_of(c.t[i]);
         const bool mism = (qb != tb) && qb != kWildcard && tb != kWildcard;  // tmp < diag <=> sub < 0
         lo2 = mism ? 1u : 0u;
     } else {
-        lo2 = not_f ? 2u : 3u;
+        lo2 = (f & 1u) ? 2u : 3u;
     }
-    return lo2 | (open_e ? 0u : 4u) | (open_f ? 0u : 8u);
+    return lo2 | (f & 0xCu);
 }
 
 // One walk.  Bytes 0..inline_cap-1 go to `inl`; if `full` != nullptr every byte also goes there.

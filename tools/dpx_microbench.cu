@@ -21,34 +21,19 @@ static rsa::FastConsts g_consts;
 constexpr int CH = 8;
 
 enum Op { VIMNMX3 = 0, VIADDMNMX, VIMNMX, VIADD16, IADD3, LOP3, PRMT, IMAD, SHF, MIX_ALU_IMAD, MIX_DPX_IMAD, CELL,
-          HFMA2, HMNMX2, FFMA, MIX_ALU_HFMA2, MIX_ALU3_HFMA2, MIX_ALU3_IMAD, HSET2, MIX_ALU_HSET2, MIX_DPX_HSET2, MIX_ALU3_HSET2, N_OPS };
+          HFMA2, HMNMX2, FFMA, MIX_ALU_HFMA2, MIX_ALU3_HFMA2, MIX_ALU3_IMAD, VIADDMNMX_RELU, IMAD_RR,
+          MIX_DPX2_HFMA2_IMAD, CELL_PREV, N_OPS };
 static const char* kNames[N_OPS] = {"VIMNMX3.S16x2", "VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "IADD3", "LOP3", "PRMT",
                                     "IMAD", "SHF", "LOP3+IMAD 1:1", "VIMNMX3+IMAD 1:1", "SW cell recipe (rsa::fast_cell, 2 cells per call)",
                                     "HFMA2", "HMNMX2", "FFMA", "LOP3+HFMA2 1:1", "LOP3+HFMA2 3:1", "LOP3+IMAD 3:1",
-                                    "HSET2", "LOP3+HSET2 1:1", "VIADDMNMX+HSET2 1:1", "LOP3+HSET2 3:1"};
+                                    "VIADDMNMX.S16x2.RELU", "IMAD (register multiplier)",
+                                    "VIADDMNMX+HFMA2+IMAD 2:1:1", "previous cell recipe (round 1: carry-trick flags, LOP3 gather)"};
 static const int kInstrPerIter[N_OPS] = {CH, CH, CH, CH, CH, CH, CH, CH, CH, 2 * CH, 2 * CH, 0, CH, CH, CH, 2 * CH, 4 * CH, 4 * CH,
-                                         CH, 2 * CH, 2 * CH, 4 * CH};
+                                         CH, CH, 4 * CH, 0};
 
-__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
     uint32_t d;
     asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-// per-half compare of two f16x2 registers -> 0xFFFF / 0 per half (one HSET2).  On the biased, non-negative s16 values of
-// the packed DP (all below 0x7C00) the fp16 order of the bit patterns IS the integer order (denormals are not flushed).
-__device__ __forceinline__ uint32_t hset2_ge(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t hset2_gt(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -83,13 +68,18 @@ __global__ void bench(uint32_t* out, const uint32_t* in, unsigned long long* cyc
             else if (OP == SHF) a[k] = __funnelshift_r(a[k], b, 5);
             else if (OP == MIX_ALU_IMAD) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = m[k] * 3u + b; }
             else if (OP == MIX_DPX_IMAD) { a[k] = __vimax3_s16x2(a[k], b, c); m[k] = m[k] * 3u + b; }
-            else if (OP == HFMA2) a[k] = hfma2(a[k], b, c);
+            else if (OP == HFMA2) a[k] = rsa::hfma2(a[k], b, c);
             else if (OP == HMNMX2) a[k] = hmax2(a[k], b);
             else if (OP == FFMA) a[k] = __float_as_uint(fmaf(__uint_as_float(a[k]), __uint_as_float(b), __uint_as_float(c)));
-            else if (OP == MIX_ALU_HFMA2) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = hfma2(m[k], b, c); }
+            else if (OP == MIX_ALU_HFMA2) { a[k] = (a[k] & b) | (c & ~a[k]); m[k] = rsa::hfma2(m[k], b, c); }
             else if (OP == MIX_ALU3_HFMA2) {
-                a[k] = (a[k] & b) | (c & ~a[k]); m[k] = hfma2(m[k], b, c);
+                a[k] = (a[k] & b) | (c & ~a[k]); m[k] = rsa::hfma2(m[k], b, c);
                 a[k] = (a[k] & c) | (b & ~a[k]); a[k] = (a[k] & d) | (c & ~a[k]);
+            } else if (OP == VIADDMNMX_RELU) a[k] = __viaddmin_s16x2_relu(a[k], b, c);
+            else if (OP == IMAD_RR) a[k] = rsa::imad(a[k], c, b);
+            else if (OP == MIX_DPX2_HFMA2_IMAD) {
+                a[k] = __viaddmax_s16x2(a[k], b, c); m[k] = rsa::hfma2(m[k], b, c);
+                a[k] = __viaddmin_s16x2_relu(a[k], c, b); m[k] = rsa::imad(m[k], c, b);
             } else if (OP == MIX_ALU3_IMAD) {
                 a[k] = (a[k] & b) | (c & ~a[k]); m[k] = m[k] * 3u + b;
                 a[k] = (a[k] & c) | (b & ~a[k]); a[k] = (a[k] & d) | (c & ~a[k]);
@@ -123,18 +113,20 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int c = CH - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
-        uint32_t acc = 0, key_prev = 0;
+        uint32_t nib_even = 0, p_lo = 0, key_prev = 0;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            uint32_t h, fn, en, fl, key;
-            rsa::fast_cell(k, S[c], F, E[c], rsa::key_colconst(c), k.k32, h, fn, en, fl, key);
-            acc = rsa::bitsel(0xF000F000u, fl, acc >> 4);
+            uint32_t h, fn, en, nib, key;
+            rsa::fast_cell(k, S[c], F, E[c], rsa::key_colconst(c), k.k32, h, fn, en, nib, key);
             if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
             key_prev = key;
             S[c] = h;
             E[c] = en;
             F = fn;
-            if ((c & 3) == 3) { sink ^= acc; acc = 0; }
+            // the kernel's gather of four columns' direction nibbles into one word (fast_cell.cuh)
+            if ((c & 3) == 0 || (c & 3) == 2) nib_even = nib;
+            else if ((c & 3) == 1) p_lo = rsa::dir_pair(k, nib_even, nib);
+            else sink ^= rsa::dir_word(p_lo, rsa::dir_pair(k, nib_even, nib));
         }
         Hl = F;
         px += py;
@@ -148,106 +140,33 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
     if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
-// ---- experimental recipe variants (same outputs as rsa::fast_cell; evaluated here before the kernel adopts one) ----
-// V2: F and E kept shifted by (mismatch + gap_oe), so that F' = max(F^ - e, S) and E' = max(E^ - e, S) need neither
-//     tmp nor tg; H^ = max(S + oe, max3(F^, E^, Z)), H = H^ - (x + oe).  One IMAD less per cell.
-// V3: V2 + the "max(F,E,0) != F" flag through two IMADs instead of one IADD3 (ALU -> FMA pipe).
-template <int V>
-__device__ __forceinline__ void cell_variant(const rsa::FastConsts& k, uint32_t oeP, uint32_t zS, uint32_t negD, uint32_t kd2,
-                                             uint32_t s, uint32_t F, uint32_t e, uint32_t colconst, uint32_t& h, uint32_t& fn,
-                                             uint32_t& en, uint32_t& fl, uint32_t& key) {
-    const uint32_t U = __vimax3_s16x2(F, e, zS);
-    const uint32_t hh = __viaddmax_s16x2(s, oeP, U);   // H + (x + oe)
-    h = hh + negD;                                      // ring add: back to the stored form
-    fn = __viaddmax_s16x2(F, k.neg_e, s);
-    en = __viaddmax_s16x2(e, k.neg_e, s);
+// ---- the previous recipe (rounds 1-2a), kept for comparison ------------------------------------------------------
+// s = diag + sub + mismatch (biased, unsigned profile); the four direction facts are carries of ring subtractions into
+// bits 15..12 (3 IADD3 + 2 IMAD), merged with three bit-selects, shifted into the word per cell.
+struct PrevConsts { uint32_t zero, neg_x16, neg_xoe, neg_e, k_f, k_e, k_d, k_n, k32, one, minus1; };
+__device__ __forceinline__ void prev_cell(const PrevConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
+                                          uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
+    const uint32_t tg = s + k.neg_xoe;
+    const uint32_t u = __vimax3_s16x2(F, e, k.zero);
+    h = __viaddmax_s16x2(s, k.neg_x16, u);
+    fn = __viaddmax_s16x2(F, k.neg_e, tg);
+    en = __viaddmax_s16x2(e, k.neg_e, tg);
     const uint32_t fo = fn - F + k.k_f;
     const uint32_t eo = en - e + k.k_e;
-    const uint32_t nd = rsa::imad(s, k.minus1, rsa::imad(hh, k.one, kd2));   // hh - s + (k_d - oe)
-    uint32_t nf;
-    if (V == 3) nf = rsa::imad(F, k.minus1, rsa::imad(U, k.one, k.k_n));
-    else nf = U - F + k.k_n;
+    const uint32_t nd = rsa::imad(s, k.minus1, rsa::imad(h, k.one, k.k_d));
+    const uint32_t nf = u - F + k.k_n;
     fl = rsa::bitsel(0x80008000u, fo, eo);
     fl = rsa::bitsel(0xC000C000u, fl, nd);
     fl = rsa::bitsel(0xE000E000u, fl, nf);
     key = rsa::imad(h, k.k32, colconst);
 }
-
-// V4 (gap_extend == 1): the four direction facts as HSET2 masks (0xFFFF / 0 per half) instead of carry tricks:
-//   opened F  <=> F' >= F,  opened E <=> E' >= E,  H != diagonal <=> max(F,E,0) > diag+sub,  max(F,E,0) != F <=> max(F,E,0) > F.
-// A mask is the same in every bit of its half, so three bit-selects leave the cell's nibble replicated in all four nibble
-// positions and inserting it into the 4-column word needs no shift: 4 HSET2 + 4 LOP3 per cell pair instead of
-// 3 IADD3 + 2 IMAD + 3 LOP3 + SHF + LOP3.
-__device__ __forceinline__ void cell_v4(const rsa::FastConsts& k, uint32_t s, uint32_t F, uint32_t e, uint32_t colconst,
-                                        uint32_t& h, uint32_t& fn, uint32_t& en, uint32_t& fl, uint32_t& key) {
-    const uint32_t tg = s + k.neg_xoe;
-    const uint32_t sx = s - k.x_pair;                           // diag + sub (ring subtraction: every half >= x)
-    const uint32_t u = __vimax3_s16x2(F, e, k.zero);
-    h = __vmaxs2(sx, u);
-    fn = __viaddmax_s16x2(F, k.neg_e, tg);
-    en = __viaddmax_s16x2(e, k.neg_e, tg);
-    const uint32_t mf = hset2_ge(fn, F), me = hset2_ge(en, e), md = hset2_gt(u, sx), mn = hset2_gt(u, F);
-    fl = rsa::bitsel(0x88888888u, mf, me);
-    fl = rsa::bitsel(0xCCCCCCCCu, fl, md);
-    fl = rsa::bitsel(0xEEEEEEEEu, fl, mn);
-    key = rsa::imad(h, k.k32, colconst);
-}
-
-__global__ void bench_cell_v4(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
+static PrevConsts g_prev;
+__global__ void bench_cell_prev(uint32_t* out, const PrevConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
     uint32_t S[CH], E[CH], qsel[CH];
     uint32_t px = in[8] + threadIdx.x, py = in[9];
 #pragma unroll
     for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = k.zero; qsel[c] = in[10 + c]; }
     uint32_t F = k.zero, Hl = k.zero, rowkey = 0, sink = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int c = CH - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
-        uint32_t acc = 0, key_prev = 0;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            uint32_t h, fn, en, fl, key;
-            cell_v4(k, S[c], F, E[c], rsa::key_colconst(c), h, fn, en, fl, key);
-            acc = rsa::bitsel(0x000F000Fu << (4 * (c & 3)), fl, acc);
-            if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
-            key_prev = key;
-            S[c] = h;
-            E[c] = en;
-            F = fn;
-            if ((c & 3) == 3) { sink ^= acc; acc = 0; }
-        }
-        Hl = F;
-        px += py;
-    }
-    uint32_t s = sink + rowkey + F;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) s += S[c] + E[c];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) { cycles[blockIdx.x] = 0; cycles[gridDim.x + blockIdx.x] = 0; }
-}
-
-// exhaustive check of the HSET2-as-integer-compare claim on [0, 2048) x [0, 2048)
-__global__ void check_hset2(unsigned int* bad) {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2047
-    if (a >= 2048) return;
-    for (uint32_t b = 0; b < 2048; ++b) {
-        const uint32_t pa = a | (b << 16), pb = b | (a << 16);
-        const uint32_t ge = hset2_ge(pa, pb), gt = hset2_gt(pa, pb);
-        const uint32_t want_ge = (a >= b ? 0xFFFFu : 0u) | (b >= a ? 0xFFFF0000u : 0u);
-        const uint32_t want_gt = (a > b ? 0xFFFFu : 0u) | (b > a ? 0xFFFF0000u : 0u);
-        if (ge != want_ge || gt != want_gt) atomicAdd(bad, 1u);
-    }
-}
-
-template <int V>
-__global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, unsigned long long* cycles, int ITERS) {
-    uint32_t S[CH], E[CH], qsel[CH];
-    uint32_t px = in[8] + threadIdx.x, py = in[9];
-    const uint32_t oeP = in[20], zS = in[21], negD = in[22], kd2 = in[23];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { S[c] = k.zero; E[c] = zS; qsel[c] = in[10 + c]; }
-    uint32_t F = zS, Hl = k.zero, rowkey = 0, sink = 0;
     __syncthreads();
     const unsigned long long n0 = globaltimer_ns();
     const unsigned long long t0 = clock64();
@@ -259,7 +178,7 @@ __global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             uint32_t h, fn, en, fl, key;
-            cell_variant<V>(k, oeP, zS, negD, kd2, S[c], F, E[c], rsa::pair16(31 - c), h, fn, en, fl, key);
+            prev_cell(k, S[c], F, E[c], rsa::key_colconst(c), h, fn, en, fl, key);
             acc = rsa::bitsel(0xF000F000u, fl, acc >> 4);
             if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
             key_prev = key;
@@ -280,23 +199,30 @@ __global__ void bench_cell_variant(uint32_t* out, const rsa::FastConsts k, const
     if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
-template <int V>
-void run_variant(int n_sms, int threads, uint32_t* d_out, uint32_t* d_in, unsigned long long* d_cyc) {
-    const int blocks = n_sms * 2;
-    cudaEvent_t e0, e1;
-    CHECK(cudaEventCreate(&e0));
-    CHECK(cudaEventCreate(&e1));
-    for (int rep = 0; rep < 3; ++rep) {
-        CHECK(cudaEventRecord(e0));
-        if (V == 4) bench_cell_v4<<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
-        else bench_cell_variant<(V == 4 ? 2 : V)><<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
-        CHECK(cudaEventRecord(e1));
-        CHECK(cudaEventSynchronize(e1));
+// Exhaustive check of the two arithmetic claims the recipe rests on (fast_cell.cuh):
+//  (1) HFMA2 on halves holding small integers is exact integer arithmetic on the bit patterns (no flush of denormals):
+//      x * 2 + y, x * 4 + y, x * 16 + y for every x, y the recipe can feed it;
+//  (2) VIADDMNMX.S16x2.RELU(a, b, (1,1)) == clamp(a + b, 0, 1) per half for a in [0, 2048), b in (-2048, 0].
+__global__ void check_claims(unsigned int* bad) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2047
+    if (a >= 2048) return;
+    const uint32_t h2 = 0x40004000u, h4 = 0x44004400u, h16 = 0x4C004C00u, one = 0x00010001u;
+    for (uint32_t b = 0; b < 2048; ++b) {
+        const int nb = -(int)b;
+        const uint32_t pb = ((uint32_t)nb & 0xFFFFu) | ((uint32_t)(nb + 1) << 16);      // halves: -b, -b + 1
+        const uint32_t got = __viaddmin_s16x2_relu(a | (a << 16), pb, one);
+        const int lo = (int)a - (int)b, hi = lo + 1;
+        const uint32_t want = (uint32_t)(lo < 0 ? 0 : (lo > 1 ? 1 : lo)) | ((uint32_t)(hi < 0 ? 0 : (hi > 1 ? 1 : hi)) << 16);
+        if (got != want) atomicAdd(bad, 1u);
     }
-    float ms = 0;
-    CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    const double gcups = 2.0 * (double)g_iters * CH * (double)blocks * threads / (ms * 1e-3) / 1e9;
-    printf("{\"test\": \"experimental recipe V%d\", \"threads\": %d, \"chip_gcups\": %.1f, \"ms\": %.3f}\n", V, threads, gcups, ms);
+    if (a < 16) {
+        for (uint32_t y = 0; y < 256; ++y) {
+            const uint32_t x = a;
+            if (x < 2 && y < 2 && rsa::hfma2(x | (y << 16), h2, y | (x << 16)) != ((2 * x + y) | ((2 * y + x) << 16))) atomicAdd(bad + 1, 1u);
+            if (x < 4 && y < 4 && rsa::hfma2(x | (y << 16), h4, y | (x << 16)) != ((4 * x + y) | ((4 * y + x) << 16))) atomicAdd(bad + 1, 1u);
+            if (y < 16 && rsa::hfma2(x | (y << 16), h16, y | (x << 16)) != ((16 * x + y) | ((16 * y + x) << 16))) atomicAdd(bad + 1, 1u);
+        }
+    }
 }
 
 template <int OP>
@@ -308,6 +234,7 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
     for (int rep = 0; rep < 3; ++rep) {
         CHECK(cudaEventRecord(e0));
         if (OP == CELL) bench_cell<<<blocks, threads>>>(d_out, g_consts, d_in, d_cyc, g_iters);
+        else if (OP == CELL_PREV) bench_cell_prev<<<blocks, threads>>>(d_out, g_prev, d_in, d_cyc, g_iters);
         else bench<OP><<<blocks, threads>>>(d_out, d_in, d_cyc, g_iters);
         CHECK(cudaEventRecord(e1));
         CHECK(cudaEventSynchronize(e1));
@@ -323,7 +250,7 @@ void run(int n_sms, int blocks_per_sm, int threads, uint32_t* d_out, uint32_t* d
     const double sm_mhz = mean / mean_ns * 1e3;  // clock64 ticks per %globaltimer ns inside the kernel: the SM clock under this load
     const int ITERS = g_iters;
     const double warps_per_sm = (double)blocks_per_sm * threads / 32.0;
-    if (OP == CELL) {
+    if (OP == CELL || OP == CELL_PREV) {
         const double cellpairs = (double)ITERS * CH;  // per thread
         const double gcups = 2.0 * cellpairs * (double)blocks * threads / (ms * 1e-3) / 1e9;
         // per-clock figures from the kernel's wall time (CUDA events) and the SM clock measured inside it -- the mean of
@@ -350,15 +277,18 @@ int main(int argc, char** argv) {
     const int n_sms = prop.multiProcessorCount;
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, n_sms, prop.clockRate);
     g_consts = rsa::make_fast_consts(rsa::Scoring{2, 8, 12, 1});
+    g_prev = PrevConsts{rsa::pair16(64), rsa::pair16(-8), 0u - 20u * 0x10001u, rsa::pair16(-1), rsa::pair16(1 + 0x7FFF),
+                        rsa::pair16(1 + 0x3FFF), rsa::pair16(0x1FFF + 8), rsa::pair16(0x0FFF), 32u, 1u, 0xFFFFFFFFu};
     uint32_t *d_out, *d_in;
     unsigned long long* d_cyc;
     CHECK(cudaMalloc(&d_out, sizeof(uint32_t) * n_sms * 8 * 1024));
     CHECK(cudaMalloc(&d_cyc, sizeof(unsigned long long) * n_sms * 16));
     std::vector<uint32_t> in(64);
-    in[0] = 0x00400040u; in[1] = 0u - 8u * 0x10001u; in[2] = 0u - 20u * 0x10001u; in[3] = 0xFFFFFFFFu;
+    // in[0..2]: loop-invariant operands b, c, d of the single-opcode tests (d == 1);
+    // in[8], in[9]: the two profile words of the cell tests; in[10..]: per-column PRMT selectors
+    in[0] = 0x00400040u; in[1] = 0u - 8u * 0x10001u; in[2] = 1u; in[3] = 0xFFFFFFFFu;
     in[4] = 0x80008000u; in[5] = 0x40004000u; in[6] = 0x1FFF1FFFu; in[7] = 0x0FFF0FFFu; in[8] = 0x0A000000u; in[9] = 0x00000A00u;
     for (int k = 10; k < 64; ++k) in[k] = 0x9480u + (k & 3) + ((k & 3) << 4);
-    in[20] = 0x000C000Cu; in[21] = 0x00540054u; in[22] = 0u - 20u * 0x10001u; in[23] = 0x1FFF1FFFu - 0x000C000Cu;
     CHECK(cudaMalloc(&d_in, sizeof(uint32_t) * 64));
     CHECK(cudaMemcpy(d_in, in.data(), sizeof(uint32_t) * 64, cudaMemcpyHostToDevice));
     // ramp the clocks before measuring
@@ -389,23 +319,21 @@ int main(int argc, char** argv) {
         }
         run<CELL>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         if (!quick) {
-            run_variant<2>(n_sms, threads, d_out, d_in, d_cyc);
-            run_variant<3>(n_sms, threads, d_out, d_in, d_cyc);
-            run_variant<4>(n_sms, threads, d_out, d_in, d_cyc);
-            run<HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
-            run<MIX_ALU_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
-            run<MIX_DPX_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
-            run<MIX_ALU3_HSET2>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<CELL_PREV>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<VIADDMNMX_RELU>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<IMAD_RR>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
+            run<MIX_DPX2_HFMA2_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         }
     }
-    if (!quick) {
+    {
         unsigned int* d_bad;
-        CHECK(cudaMalloc(&d_bad, sizeof(unsigned int)));
-        CHECK(cudaMemset(d_bad, 0, sizeof(unsigned int)));
-        check_hset2<<<16, 128>>>(d_bad);
-        unsigned int bad = 0;
-        CHECK(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
-        printf("{\"test\": \"HSET2 as integer compare on [0,2048)^2\", \"mismatches\": %u}\n", bad);
+        CHECK(cudaMalloc(&d_bad, 2 * sizeof(unsigned int)));
+        CHECK(cudaMemset(d_bad, 0, 2 * sizeof(unsigned int)));
+        check_claims<<<16, 128>>>(d_bad);
+        unsigned int bad[2] = {0, 0};
+        CHECK(cudaMemcpy(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+        printf("{\"test\": \"exactness: VIADDMNMX.S16x2.RELU as clamp(a+b,0,1); HFMA2 on integer bit patterns\", "
+               "\"clamp_mismatches\": %u, \"hfma2_mismatches\": %u}\n", bad[0], bad[1]);
     }
     return 0;
 }

@@ -45,7 +45,7 @@ for a, t in ins:
         lo = int(m.group(1), 16)
         seq = [(x, y) for x, y in ins if lo <= x <= a]
         n_dpx = sum(1 for _, y in seq if "VIADDMNMX" in y)
-        if sum(1 for _, y in seq if y.startswith("SHFL.UP")) >= 2 and 3 * C <= n_dpx < 4 * C:  # one row: 3 fused add+max per column
+        if sum(1 for _, y in seq if y.startswith("SHFL.UP")) >= 2 and 7 * C <= n_dpx < 8 * C:  # one row: 3 fused add+max and 4 clamp facts per column
             loops.append((lo, a, seq))
 out = [f"kernel {name}", f"{len(ins)} instructions; row loops found: " + ", ".join(f"[{lo:#x}, {hi:#x}] {len(s)} instr" for lo, hi, s in loops), ""]
 regs = re.search(r"REG:(\d+)", subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout.split(want, 1)[-1][:400] if want else "")
@@ -58,8 +58,9 @@ if loops:
     h = hist(seq)
     alu = sum(h[o] for o in ("LOP3", "IADD3", "VIADDMNMX", "VIMNMX3", "VIMNMX", "PRMT", "SHF", "VIADD", "LEA", "SEL", "ISETP", "PLOP3", "HSET2"))
     fma = sum(h[o] for o in ("IMAD", "HFMA2", "FFMA"))
+    hf = h["HFMA2"]
     out += ["", f"steady-state row loop without N in the reads [{lo:#x}, {hi:#x}]: {len(seq)} instructions per target row of {C} column "
-            f"pairs = {len(seq) / C:.2f} per packed cell pair ({alu / C:.2f} on the ALU-pipe opcode list, {fma / C:.2f} IMAD/FMA-pipe)"]
+            f"pairs = {len(seq) / C:.2f} per packed cell pair ({alu / C:.2f} on the ALU-pipe opcode list, {fma / C:.2f} on the FMA pipe: {(fma - hf) / C:.2f} IMAD + {hf / C:.2f} HFMA2)"]
     out += [f"  {n:5d} {op}  ({n / C:.2f}/column)" for op, n in h.most_common()]
     out += ["", "loop body:"] + [f"  {a:#06x}  {t}" for a, t in seq]
 dst = os.path.join(ROOT, "profiles", f"r2_sass_fast_dp_{L}_{C}.txt")
