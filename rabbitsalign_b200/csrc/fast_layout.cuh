@@ -6,10 +6,13 @@
 // every owned column is a real query base (no padding columns exist).
 //
 // Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
-//     uint32 index = (((r>>2)*W + w)*L + l)*4 + (r&3),   W = ceil(C/4)
-// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); for a fixed (row block, w) the L lanes'
-// chunks are contiguous (one 128-byte line), so the DP kernel stores full lines with one STG.128 per lane and
-// the traceback, which moves diagonally, finds ~2-3 consecutive path cells in the chunk it just fetched.
+//     uint32 index = (((r>>2)*L + l)*W + w)*4 + (r&3),   W = ceil(C/4) rounded up to an even number
+// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); the chunks of one lane and row block are
+// contiguous and two of them (4 rows x 8 columns) fill one 32-byte sector, which the DP kernel writes with ONE 256-bit
+// store per thread (never a partial sector: partial sectors are read-modify-written by the L2), and in which the
+// traceback, which moves diagonally, finds the next ~4 path cells of a row block.  (Round 1 ordered the chunks
+// [row block][word][lane]: a sector then held the same word of two neighbouring LANES, i.e. columns C apart, and every
+// 16-byte chunk the traceback touched cost a 32-64 byte HBM access of which half was useless: 6.2 KB read per pair.)
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
 //     bit3 F of the next column NOT opened from the diagonal (extended; = reference bit3)
 //     bit2 E of the next row NOT opened from the diagonal (= reference bit2)
@@ -24,13 +27,16 @@ namespace rsa {
 // 4 lanes up to 160 bases (C <= 40 columns per lane: the per-row overhead of a lane -- shuffles, profile loads, maximum
 // tracking, loop control -- is spread over twice the columns of an 8-lane group and the wavefront skew shrinks from 7 to 3
 // idle steps per window), 8 lanes up to 256 (C <= 32), 16 lanes beyond.
-__host__ __device__ inline int fast_lanes_for(int qlen) { return qlen <= 160 ? 4 : (qlen <= 256 ? 8 : 16); }
+#ifndef RSA_FAST_L4_MAXQ
+#define RSA_FAST_L4_MAXQ 160   // (A/B builds: 0 = no 4-lane groups)
+#endif
+__host__ __device__ inline int fast_lanes_for(int qlen) { return qlen <= RSA_FAST_L4_MAXQ ? 4 : (qlen <= 256 ? 8 : 16); }
 
 struct FastGeom {
     int L;    // lanes per group
     int C;    // columns of the widest lanes
     int rem;  // number of lanes owning C columns (1..8); the rest own C-1
-    int W;    // 32-bit direction words per lane and row
+    int W;    // 32-bit direction words per lane and row as STORED (even: the last one may be padding)
 };
 
 __host__ __device__ inline FastGeom fast_geom(int qlen) {
@@ -38,7 +44,7 @@ __host__ __device__ inline FastGeom fast_geom(int qlen) {
     g.L = fast_lanes_for(qlen);
     g.C = (qlen + g.L - 1) / g.L;
     g.rem = qlen - g.L * (g.C - 1);
-    g.W = (g.C + 3) / 4;
+    g.W = (((g.C + 3) / 4) + 1) & ~1;
     return g;
 }
 
@@ -58,7 +64,7 @@ __device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const ui
     const int wide = g.rem * g.C;
     if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
     else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
-    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.W + (cc >> 2)) * g.L + lane) << 2) + (i & 3)];
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.L + lane) * g.W + (cc >> 2)) << 2) + (i & 3)];
     const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
     return (h16 >> (4 * (cc & 3))) & 0xFu;
 }

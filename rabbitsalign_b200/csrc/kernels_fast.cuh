@@ -115,6 +115,7 @@ struct FastDp {
         uint32_t bestkey = 0;  // key of "no positive cell yet"
         firstrow[0] = firstrow[1] = 0;
         constexpr int NW = (C + 3) / 4;
+        constexpr int NW2 = (NW + 1) & ~1;      // stored words per lane and row (fast_layout.cuh)
         constexpr int RS = fast_ring_slots(L);
         constexpr int CB = fast_col_bits(L);
         constexpr uint32_t kColMask = (uint32_t)((1 << CB) - 1) * 0x00010001u;
@@ -192,20 +193,23 @@ struct FastDp {
             pr = prn;
             // De-skewed, row-blocked store: lane gl computed row r at step r+gl and parked its words in ring slot
             // (r+gl)&(RS-1).  When the group's LAST lane has finished the last row of a 4-row block (step = 4b+3+L-1),
-            // every lane stores ITS OWN words of rows 4b..4b+3 as one 16-byte chunk per word: L lanes x 16 B = one
-            // (two) full 128-byte line(s) per store instruction and group.
+            // every lane stores ITS OWN words of rows 4b..4b+3, two words (4 rows x 8 columns, both pairs) per 256-bit
+            // store = one full 32-byte sector; a lane's words of a row block are contiguous (fast_layout.cuh).
             const int rl = s - (L - 1);                   // row the last lane finished in this step
             if (rl >= 0 && (rl & 3) == 3 && rl - 3 < rows) {
                 const int rb = rl >> 2;
-                uint4* dblk = reinterpret_cast<uint4*>(dir) + (size_t)rb * (NW * L) + gl;
+                uint4* dblk = reinterpret_cast<uint4*>(dir) + ((size_t)rb * L + gl) * NW2;
+                const uint32_t* r0 = ring + ((((rl - 3 + gl) & (RS - 1)) * NW) << 5) + lane;
+                const uint32_t* r1 = ring + ((((rl - 2 + gl) & (RS - 1)) * NW) << 5) + lane;
+                const uint32_t* r2 = ring + ((((rl - 1 + gl) & (RS - 1)) * NW) << 5) + lane;
+                const uint32_t* r3 = ring + ((((rl + gl) & (RS - 1)) * NW) << 5) + lane;
 #pragma unroll
-                for (int wv = 0; wv < NW; ++wv) {
-                    uint4 v;
-                    v.x = ring[((((rl - 3 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
-                    v.y = ring[((((rl - 2 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
-                    v.z = ring[((((rl - 1 + gl) & (RS - 1)) * NW + wv) << 5) + lane];
-                    v.w = ring[((((rl + gl) & (RS - 1)) * NW + wv) << 5) + lane];
-                    dblk[wv * L] = v;
+                for (int wv = 0; wv < NW2; wv += 2) {
+                    uint4 v, w = make_uint4(0u, 0u, 0u, 0u);
+                    v.x = r0[wv << 5]; v.y = r1[wv << 5]; v.z = r2[wv << 5]; v.w = r3[wv << 5];
+                    if (wv + 1 < NW) { w.x = r0[(wv + 1) << 5]; w.y = r1[(wv + 1) << 5]; w.z = r2[(wv + 1) << 5]; w.w = r3[(wv + 1) << 5]; }
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                 :: "l"(dblk + wv), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 }
             }
         }
@@ -214,9 +218,15 @@ struct FastDp {
 };
 
 template <int L, int C>
-// (4-lane groups with C = 33..40 columns need ~250 registers: two blocks per SM.  Capping them at 168 registers for three
-// blocks spills ~55 words per thread and measured slower: DP phase 1737 vs 1811 GCUPS, value 1691 vs 1745.)
-__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : 2))))
+// (4-lane groups with C = 28..40 columns would take ~250 registers: two blocks per SM.  Capped at 168 registers for three
+// blocks they spill ~30 words per thread and measure slightly faster with the clamp-fact recipe: DP phase 1983 vs 1971
+// GCUPS, value 1914 vs 1891.  A/B builds that did not pay, numbers in DESIGN.md 4.1: row loop unrolled by two (1951 /
+// 1894); per-column selectors re-loaded from shared memory each row instead of held in C registers (168 registers, no
+// spills, DP phase 2037 -- but 74 KB of shared memory per block leave no room for the traceback kernel beside it: 1732).)
+#ifndef RSA_FAST_WIDE_BLOCKS
+#define RSA_FAST_WIDE_BLOCKS 3   // (A/B builds)
+#endif
+__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : RSA_FAST_WIDE_BLOCKS))))
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
@@ -550,6 +560,11 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
     }
     switch (C) {
 #define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+#if RSA_FAST_L4_MAXQ < 160   // (A/B builds without 4-lane groups)
+        RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6) RSA_FAST_CASE(7)
+        RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12) RSA_FAST_CASE(13) RSA_FAST_CASE(14)
+        RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18) RSA_FAST_CASE(19) RSA_FAST_CASE(20)
+#endif
         RSA_FAST_CASE(21) RSA_FAST_CASE(22) RSA_FAST_CASE(23) RSA_FAST_CASE(24) RSA_FAST_CASE(25) RSA_FAST_CASE(26)
         RSA_FAST_CASE(27) RSA_FAST_CASE(28) RSA_FAST_CASE(29) RSA_FAST_CASE(30) RSA_FAST_CASE(31) RSA_FAST_CASE(32)
 #undef RSA_FAST_CASE

@@ -21,7 +21,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsa_ext.so")
+# RSA_EXT_LIB: an A/B build of the same library (kernel experiments); the product is the in-tree librsa_ext.so
+LIB_PATH = os.environ.get("RSA_EXT_LIB") or os.path.join(_HERE, "librsa_ext.so")
 
 RLE_INLINE = 40
 FLAG_EXACT_ONLY = 1
