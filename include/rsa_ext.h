@@ -168,6 +168,22 @@ typedef struct {
  * end_bonus is strobealign's -L (src/cmdline.hpp:50, default 10). */
 int rsa_ext_request_alninfo(rsa_ext_t *h, rsa_ext_alninfo_t *out, int32_t end_bonus);
 
+/* ---- SURVEY 8(f) "next" row 3, first half: the Hamming shortcut of the seed extension, on the device -------
+ *
+ * What extend_seed_part (src/aln.cpp:374-431) does on the host for every candidate site whose projected window has the
+ * read's length, before deciding to run Smith-Waterman: hamming_distance (src/aligner.hpp:54-67), the test
+ * (float) distance / |query| < 0.05 (src/aln.cpp:395) and, if it holds, hamming_align (src/aligner.cpp:254-302, with
+ * highest_scoring_segment :219-252).  Blocking call, one warp per pair.
+ * hamming[i]: the distance, -1 for windows of another length than the read.
+ * out[i].status: 0 the shortcut applies and the record is hamming_align's AlignmentInfo (ref_start/ref_end relative to
+ * the window); 1 the pair needs the gapped path (submit it); 3 more than RSA_EXT_CIGAR_INLINE runs (host path).
+ * Scores are the handle's; end_bonus is strobealign's -L. */
+int rsa_ext_hamming_align(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff, const char *tbuf,
+                          const int64_t *toff, int32_t end_bonus, int32_t *hamming, rsa_ext_alninfo_t *out);
+/* The same with window i = [win_off[i], win_off[i] + |query i|) of the resident reference (rsa_ext_set_reference). */
+int rsa_ext_hamming_ref_windows(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff, const int64_t *win_off,
+                                int32_t end_bonus, int32_t *hamming, rsa_ext_alninfo_t *out);
+
 /* ---- device-resident legs (bench.py `value`, roofline): inputs already in HBM ---------------- */
 
 /* Upload + plan a batch once; afterwards rsa_ext_run_resident() re-runs only the GPU kernels on the

@@ -185,6 +185,53 @@ class SswReference:
         return out
 
 
+def hamming_restatement(qbuf, qoff, tbuf, toff, match=2, mismatch=8, end_bonus=10):
+    """The C restatement of the Hamming shortcut (sw_oracle.c: rsa_oracle_hamming; reference src/aln.cpp:391-404,
+    src/aligner.cpp:219-302).  Returns dict of arrays hamming/status/score/ed/start/end and the CIGAR texts."""
+    lib = restatement().lib
+    lib.rsa_oracle_hamming.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_char_p, C.c_int]
+    lib.rsa_oracle_hamming.restype = C.c_int
+    n = len(qoff) - 1
+    out = {k: np.zeros(n, np.int32) for k in ("hamming", "status", "score", "ed", "start", "end")}
+    out["cigar"] = []
+    buf = C.create_string_buffer(8192)
+    one = [C.c_int() for _ in range(5)]
+    for i in range(n):
+        ql, tl = int(qoff[i + 1] - qoff[i]), int(toff[i + 1] - toff[i])
+        hd = lib.rsa_oracle_hamming(qbuf.ctypes.data + int(qoff[i]), ql, tbuf.ctypes.data + int(toff[i]), tl, match, mismatch,
+                                    end_bonus, *[C.addressof(v) for v in one], buf, 8192)
+        out["hamming"][i] = hd
+        for k, v in zip(("status", "score", "ed", "start", "end"), one):
+            out[k][i] = v.value
+        out["cigar"].append(buf.value.decode())
+    return out
+
+
+def hamming_reference(qbuf, qoff, tbuf, toff, match=2, mismatch=8, end_bonus=10):
+    """The reference's own hamming_distance / hamming_align (compiled into oracle/_ref/libssw_ref_*.so), called as
+    extend_seed_part calls them; None when _ref/ was not built."""
+    ref = ssw_reference()
+    if ref is None or not hasattr(ref.lib, "ssw_ref_hamming_batch"):
+        return None
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    ref.lib.ssw_ref_hamming_batch.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32] + [vp] * 9 + [i32]
+    ref.lib.ssw_ref_hamming_batch.restype = i32
+    n = len(qoff) - 1
+    out = {k: np.zeros(n, np.int32) for k in ("hamming", "status", "score", "qs", "qe", "rs", "re", "ed")}
+    slot = 2048
+    pool = np.zeros(n * slot, np.uint8)
+    rc = ref.lib.ssw_ref_hamming_batch(n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data, toff.ctypes.data, match,
+                                       mismatch, end_bonus, out["hamming"].ctypes.data, out["status"].ctypes.data,
+                                       out["score"].ctypes.data, out["qs"].ctypes.data, out["qe"].ctypes.data,
+                                       out["rs"].ctypes.data, out["re"].ctypes.data, out["ed"].ctypes.data,
+                                       pool.ctypes.data, slot)
+    if rc != 0:
+        raise RuntimeError("ssw_ref_hamming_batch failed")
+    raw = pool.tobytes()
+    out["cigar"] = [raw[i * slot:(i + 1) * slot].split(b"\0", 1)[0].decode() for i in range(n)]
+    return out
+
+
 def ssw_reference() -> Optional[SswReference]:
     if "ssw" not in _cache:
         flags = ""

@@ -102,3 +102,27 @@ extern "C" int ssw_ref_align_gpu_batch(int64_t n, const char* qbuf, const int64_
     }
     return 0;
 }
+
+// The Hamming shortcut of extend_seed_part (src/aln.cpp:391-404): hamming_distance (src/aligner.hpp:54-67), the 5 % test
+// with the reference's own expression, hamming_align (src/aligner.cpp:254-302) -- the reference's functions, called as
+// the reference calls them.  status: 0 shortcut taken, 1 gapped path.
+extern "C" int ssw_ref_hamming_batch(int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
+                                     int match, int mismatch, int end_bonus, int32_t* hamming, int32_t* status,
+                                     int32_t* score, int32_t* qs, int32_t* qe, int32_t* rs, int32_t* re, int32_t* ed,
+                                     char* cigar_pool, int cigar_slot) {
+    Out o{score, qs, qe, rs, re, ed, cigar_pool, nullptr, cigar_slot};
+    for (int64_t i = 0; i < n; ++i) {
+        const std::string query(qbuf + qoff[i], qbuf + qoff[i + 1]);
+        const std::string ref_segm_ham(tbuf + toff[i], tbuf + toff[i + 1]);
+        auto hamming_dist = hamming_distance(query, ref_segm_ham);
+        hamming[i] = hamming_dist;
+        AlignmentInfo info;
+        status[i] = 1;
+        if (hamming_dist >= 0 && (((float) hamming_dist / query.size()) < 0.05)) {
+            info = hamming_align(query, ref_segm_ham, match, mismatch, end_bonus);
+            status[i] = 0;
+        }
+        store(o, i, info);
+    }
+    return 0;
+}

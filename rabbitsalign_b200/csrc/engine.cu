@@ -36,6 +36,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_tb.cuh"
 #include "kernels_finish.cuh"
+#include "kernels_hamming.cuh"
 #include "kernels_plan.cuh"
 
 using namespace rsa;
@@ -206,6 +207,8 @@ struct rsa_ext {
     // submit_ptrs staging
     PinBuf own_q, own_t;
     std::vector<int64_t> own_qoff, own_toff;
+
+    DevBuf ham_q, ham_t, ham_off, ham_out;  // rsa_ext_hamming_* staging
 
     // resident set
     std::vector<ResidentChunk> res_chunks;
@@ -1304,7 +1307,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
         if (s.ev_plan) cudaEventDestroy(s.ev_plan);
     }
     h->ref.reset();
-    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs})
+    for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs, &h->ham_q, &h->ham_t, &h->ham_off, &h->ham_out})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
     if (h->own_q.p) cudaFreeHost(h->own_q.p);
@@ -1393,6 +1396,68 @@ extern "C" int rsa_ext_share_reference(rsa_ext_t* h, const rsa_ext_t* donor) {
 extern "C" int rsa_ext_submit_ref_windows(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
                                           const int64_t* win_off, const int32_t* win_len, rsa_ext_result_t* results) {
     return submit_core_ex(h, n, qbuf, qoff, nullptr, nullptr, win_off, win_len, results);
+}
+
+// ---- the Hamming shortcut (src/aln.cpp:391-404, src/aligner.cpp:219-302) on the device ----------
+namespace {
+int hamming_core(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf, const int64_t* toff,
+                 const int64_t* win_off, int32_t end_bonus, int32_t* hamming, rsa_ext_alninfo_t* out) {
+    if (!h) return RSA_EXT_ERR_ARG;
+    if (h->pending) { h->err = "a batch is pending"; return RSA_EXT_ERR_STATE; }
+    if (n <= 0 || !qbuf || !qoff || !hamming || !out) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    if (win_off) {
+        if (!h->ref) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
+        for (int64_t i = 0; i < n; ++i) {
+            if (win_off[i] < 0 || win_off[i] + (qoff[i + 1] - qoff[i]) > h->ref->len) {
+                h->err = "window " + std::to_string(i) + " lies outside the resident reference";
+                return RSA_EXT_ERR_ARG;
+            }
+        }
+    } else if (!tbuf || !toff) { h->err = "bad argument"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t qbytes = (size_t)(qoff[n] - qoff[0]), tbytes = win_off ? 0 : (size_t)(toff[n] - toff[0]);
+    const size_t offb = sizeof(int64_t) * (size_t)(n + 1);
+    int rc;
+    if ((rc = ensure_dev(h, h->ham_q, qbytes + 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_t, tbytes + 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_off, 2 * offb + 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_out, (sizeof(rsa_ext_alninfo_t) + sizeof(int32_t)) * (size_t)n + 16))) return rc;
+    cudaStream_t st = h->s_comp;
+    int64_t* d_qoff = reinterpret_cast<int64_t*>(h->ham_off.p);
+    int64_t* d_toff = reinterpret_cast<int64_t*>(h->ham_off.p + offb);
+    rsa_ext_alninfo_t* d_out = reinterpret_cast<rsa_ext_alninfo_t*>(h->ham_out.p);
+    int32_t* d_ham = reinterpret_cast<int32_t*>(h->ham_out.p + sizeof(rsa_ext_alninfo_t) * (size_t)n);
+    CU_TRY(h, cudaMemcpyAsync(h->ham_q.p, qbuf + qoff[0], qbytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(d_qoff, qoff, offb, cudaMemcpyHostToDevice, st));
+    if (win_off) {
+        CU_TRY(h, cudaMemcpyAsync(d_toff, win_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(h->ham_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(d_toff, toff, offb, cudaMemcpyHostToDevice, st));
+    }
+    const int blocks = (int)std::min<int64_t>((n + kHamWarpsPerBlock - 1) / kHamWarpsPerBlock, (int64_t)h->n_sms * 16);
+    // the uploaded sequence slices start at the first pair's offset: rebase the pointers instead of the offsets
+    hamming_kernel<<<blocks, 32 * kHamWarpsPerBlock, 0, st>>>(
+        h->ham_q.p - qoff[0], d_qoff, win_off ? h->ref->d : h->ham_t.p - toff[0], win_off ? nullptr : d_toff,
+        win_off ? d_toff : nullptr, (long long)n, h->sc.match, h->sc.mismatch, end_bonus, d_ham, d_out);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(out, d_out, sizeof(rsa_ext_alninfo_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(hamming, d_ham, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    h->stats.kernel_launches = 1;
+    return RSA_EXT_OK;
+}
+}  // namespace
+
+extern "C" int rsa_ext_hamming_align(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff, const char* tbuf,
+                                     const int64_t* toff, int32_t end_bonus, int32_t* hamming, rsa_ext_alninfo_t* out) {
+    return hamming_core(h, n, qbuf, qoff, tbuf, toff, nullptr, end_bonus, hamming, out);
+}
+
+extern "C" int rsa_ext_hamming_ref_windows(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
+                                           const int64_t* win_off, int32_t end_bonus, int32_t* hamming,
+                                           rsa_ext_alninfo_t* out) {
+    return hamming_core(h, n, qbuf, qoff, nullptr, nullptr, win_off, end_bonus, hamming, out);
 }
 
 // Allocate, now, what a batch of n pairs of (qlen x tlen) needs from slot 0 and the submit_ptrs staging, so that the

@@ -66,6 +66,7 @@ ABI_SYMBOLS = [
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
     "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows", "rsa_ext_share_reference", "rsa_ext_scan_debug",
+    "rsa_ext_hamming_align", "rsa_ext_hamming_ref_windows",
 ]
 
 _lib = None
@@ -125,6 +126,10 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_share_reference.restype = C.c_int
     lib.rsa_ext_submit_ref_windows.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.rsa_ext_submit_ref_windows.restype = C.c_int
+    lib.rsa_ext_hamming_align.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp]
+    lib.rsa_ext_hamming_align.restype = C.c_int
+    lib.rsa_ext_hamming_ref_windows.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp]
+    lib.rsa_ext_hamming_ref_windows.restype = C.c_int
     _lib = lib
     return lib
 
@@ -237,6 +242,26 @@ class ExtensionEngine:
                                                         wl.ctypes.data, results.ctypes.data))
         self.wait()
         return results
+
+    def hamming_align(self, qbuf, qoff, tbuf, toff, end_bonus: int = 10):
+        """The Hamming shortcut of extend_seed_part (reference src/aln.cpp:391-404, src/aligner.cpp:219-302) for n
+        (read, equally long window) pairs: returns (hamming int32[n], ALNINFO records; status 0 = shortcut applies)."""
+        n = len(qoff) - 1
+        ham = np.zeros(n, np.int32)
+        out = np.zeros(n, dtype=ALNINFO_DTYPE)
+        self._check(self.lib.rsa_ext_hamming_align(self.h, n, qbuf.ctypes.data, qoff.ctypes.data, tbuf.ctypes.data,
+                                                   toff.ctypes.data, end_bonus, ham.ctypes.data, out.ctypes.data))
+        return ham, out
+
+    def hamming_ref_windows(self, qbuf, qoff, win_off, end_bonus: int = 10):
+        """hamming_align() with window i = |query i| bases of the resident reference starting at win_off[i]."""
+        n = len(qoff) - 1
+        ham = np.zeros(n, np.int32)
+        out = np.zeros(n, dtype=ALNINFO_DTYPE)
+        wo = np.ascontiguousarray(win_off, dtype=np.int64)
+        self._check(self.lib.rsa_ext_hamming_ref_windows(self.h, n, qbuf.ctypes.data, qoff.ctypes.data, wo.ctypes.data,
+                                                         end_bonus, ham.ctypes.data, out.ctypes.data))
+        return ham, out
 
     def align_ptrs(self, queries: Sequence[bytes], targets: Sequence[bytes]) -> np.ndarray:
         """Blocking rsa_ext_submit_ptrs: n separate strings, the shape of std::vector<std::string> (the veneer's path)."""
