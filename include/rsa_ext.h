@@ -57,6 +57,8 @@ typedef struct {
 } rsa_ext_config_t;
 
 #define RSA_EXT_FLAG_EXACT_ONLY 1 /* route every pair through the exact int32 kernel (testing) */
+#define RSA_EXT_FLAG_ASCII_WINDOWS 8 /* window form: stage the windows from the ASCII copy of the resident reference
+                                        instead of its packed planes (A/B tests; results are identical) */
 #define RSA_EXT_FLAG_HOST_PLAN 4  /* plan every chunk on the host (the round-1 planner); default: batches of >= 4096 pairs
                                      are planned by device kernels from the raw offset arrays (same records) */
 #define RSA_EXT_FLAG_SERIALIZE 2  /* one stream, no kernel overlap: per-kernel CUDA-event times (dp_ms, tb_ms) are then
@@ -126,6 +128,12 @@ int rsa_ext_set_reference(rsa_ext_t *h, const char *seq, int64_t len);
  * the pipeline's workers each own a handle but need the reference once per GPU (north_star: "index and reference
  * replicated per GPU"). */
 int rsa_ext_share_reference(rsa_ext_t *h, const rsa_ext_t *donor);
+/* The packed planes the upload built beside the ASCII copy and the packed DP kernel stages windows from (north_star:
+ * "2-bit-packed reads and reference windows are staged into shared memory with vectorised, coalesced HBM loads"; the
+ * reference packs to 4 bits on the device, GASAL2/src/kernels/pack_rc_seqs.h:13-53): per 64-base unit 16 bytes of
+ * 2-bit codes (A C G T = 0..3, first base in the low bits) and 8 bytes of "not ACGT" bits (then code 0 = N, 1 = any
+ * other symbol).  Copies `units` whole units out (diagnostics, tests). */
+int rsa_ext_packed_reference(rsa_ext_t *h, uint32_t *codes, uint32_t *flags, int64_t units);
 int rsa_ext_submit_ref_windows(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff,
                                const int64_t *win_off, const int32_t *win_len, rsa_ext_result_t *results);
 

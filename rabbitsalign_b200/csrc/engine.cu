@@ -149,8 +149,15 @@ struct RefBuf {
     uint8_t* d = nullptr;
     const char* host = nullptr;  // kept for the rare exact-only re-submission (status 4); the caller keeps it alive
     int64_t len = 0;
+    // packed form for the DP kernel's vectorised staging (pack_reference_kernel): 64-base units, 16 B of 2-bit codes and
+    // 8 B of "not ACGT" flags each
+    uint4* d_pack = nullptr;
+    uint2* d_flag = nullptr;
     ~RefBuf() {
-        if (d) { cudaSetDevice(device); cudaFree(d); }
+        cudaSetDevice(device);
+        if (d) cudaFree(d);
+        if (d_pack) cudaFree(d_pack);
+        if (d_flag) cudaFree(d_flag);
     }
 };
 
@@ -713,6 +720,8 @@ struct ChunkDev {
     uint8_t* arena;
     unsigned long long* arena_used;
     uint64_t arena_cap;
+    const uint4* tpack = nullptr;  // window form: the resident reference's packed planes (else null: ASCII targets)
+    const uint2* tflag = nullptr;
 };
 
 template <int C>
@@ -757,7 +766,7 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
         ++cls_i;
         int rc = launch_fast_class(cst, fc.L, fc.C, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
-                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen);
+                                   fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen, d.tpack, d.tflag);
         if (rc != 0) { h->err = "no packed-kernel instance for L=" + std::to_string(fc.L) + " C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
@@ -1010,6 +1019,7 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
     ChunkDev d{s.d_blob.p, s.d_q.p, d_targets, reinterpret_cast<DpEnd*>(s.d_ends.p),
                reinterpret_cast<rsa_ext_result_t*>(s.d_res.p), s.d_scratch.p, (uint64_t)s.d_scratch.cap, s.d_arena.p,
                s.d_arena_used, (uint64_t)s.d_arena.cap};
+    if (h->win_off && !(h->cfg.flags & RSA_EXT_FLAG_ASCII_WINDOWS)) { d.tpack = h->ref->d_pack; d.tflag = h->ref->d_flag; }
     cudaStream_t s_trace = serial ? s_dp : h->s_tb;
     if ((rc = enqueue_compute(h, s_dp, s_trace, s.ev_mid, d, p, nullptr))) return rc;
     if (h->alninfo) {
@@ -1377,10 +1387,29 @@ extern "C" int rsa_ext_set_reference(rsa_ext_t* h, const char* seq, int64_t len)
     CU_TRY(h, cudaMemcpy(rb->d, seq, (size_t)len, cudaMemcpyHostToDevice));
     // a pageable cudaMemcpy may return once the bytes are staged; the engine's streams are non-blocking, so nothing
     // would order their kernels behind the final DMA
+    {   // packed planes: whole 64-base units, one spare unit behind the end (the staging loads whole units)
+        const long long units = (len + 63) / 64 + 1;
+        CU_TRY(h, cudaMalloc(&rb->d_pack, sizeof(uint4) * (size_t)units));
+        CU_TRY(h, cudaMalloc(&rb->d_flag, sizeof(uint2) * (size_t)units));
+        const long long n32 = units * 2;
+        pack_reference_kernel<<<(unsigned)((n32 + 255) / 256), 256>>>(rb->d, (long long)len, n32, reinterpret_cast<uint32_t*>(rb->d_pack),
+                                                                       reinterpret_cast<uint32_t*>(rb->d_flag));
+        CU_TRY(h, cudaGetLastError());
+    }
     CU_TRY(h, cudaDeviceSynchronize());
     rb->host = seq;
     rb->len = len;
     h->ref = rb;
+    return RSA_EXT_OK;
+}
+
+extern "C" int rsa_ext_packed_reference(rsa_ext_t* h, uint32_t* codes, uint32_t* flags, int64_t units) {
+    if (!h || !codes || !flags) return RSA_EXT_ERR_ARG;
+    if (!h->ref) { h->err = "no resident reference (rsa_ext_set_reference)"; return RSA_EXT_ERR_STATE; }
+    if (units <= 0 || units > (h->ref->len + 63) / 64) { h->err = "bad unit count"; return RSA_EXT_ERR_ARG; }
+    CU_TRY(h, cudaSetDevice(h->cfg.device));
+    CU_TRY(h, cudaMemcpy(codes, h->ref->d_pack, sizeof(uint4) * (size_t)units, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(flags, h->ref->d_flag, sizeof(uint2) * (size_t)units, cudaMemcpyDeviceToHost));
     return RSA_EXT_OK;
 }
 

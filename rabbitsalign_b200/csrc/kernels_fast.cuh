@@ -38,6 +38,8 @@ constexpr int kFastMinQlen = 8;
 constexpr int kFastMaxC = 40;                 // 4-lane groups: C <= 40 (160 bases); 8- and 16-lane groups: C <= 32
 constexpr int kFastMaxQlen = 16 * 32;         // 512: 4 lanes x C<=40, 8 lanes x C<=32 up to 256 bases, 16 lanes x C<=32 beyond
 constexpr int kFastMaxTlen = 2047;
+constexpr int kFastStageUnits = 34;           // 64-base units of the longest window (2047 bases at any phase: 33) + 1
+constexpr int kFastStageBytes = 24 * kFastStageUnits + 16;   // per warp: 16 B of codes + 8 B of flags per unit, one status word
 constexpr int kFastLutBytes = 64;             // two 8-word profile tables (pair A, pair B) at the head of the shared memory
 // 8-lane groups: 4 groups per warp, 4 warps per block; 16-lane groups: 2 groups per warp, 2 warps per block
 // (their shared-memory ring is deeper and wider)
@@ -79,6 +81,37 @@ __device__ __forceinline__ uint32_t base_code(uint32_t nib) {
     c = (nib == 4u) ? 3u : c;
     c = (nib == 0xEu) ? 4u : c;
     return c;
+}
+
+// The resident reference in the packed form the staging above reads (north_star: 2-bit-packed windows, vectorised loads):
+// plane 1, 2 bits per base: A C G T -> 0..3; N -> 0 and every other symbol -> 1 with plane 2, 1 bit per base ("not ACGT"),
+// set.  One thread packs 32 bases (two 128-bit loads of ASCII -> two code words + one flag word).  The ASCII copy stays
+// resident beside it: the traceback, the exact kernel (symbols outside ACGTN compare by nibble) and explicit windows use it.
+__global__ void __launch_bounds__(256) pack_reference_kernel(const uint8_t* __restrict__ ref, long long len, long long n_words32,
+                                                             uint32_t* __restrict__ codes, uint32_t* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words32) return;
+    const long long base = i * 32;
+    uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (base + 32 <= len && (reinterpret_cast<uintptr_t>(ref) & 15u) == 0) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ref + base)), v1 = __ldg(reinterpret_cast<const uint4*>(ref + base) + 1);
+        bytes[0] = v0.x; bytes[1] = v0.y; bytes[2] = v0.z; bytes[3] = v0.w; bytes[4] = v1.x; bytes[5] = v1.y; bytes[6] = v1.z; bytes[7] = v1.w;
+    } else {
+        for (int j = 0; j < 32 && base + j < len; ++j) bytes[j >> 2] |= (uint32_t)ref[base + j] << (8 * (j & 3));
+    }
+    uint32_t c0 = 0, c1 = 0, f = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t code = base_code(nibble_of((uint8_t)(bytes[j >> 2] >> (8 * (j & 3)))));
+        const uint32_t two = code < 4u ? code : (code == 4u ? 0u : 1u);
+        if (base + j < len) {
+            if (j < 16) c0 |= two << (2 * j); else c1 |= two << (2 * (j - 16));
+            f |= (code >= 4u ? 1u : 0u) << j;
+        }
+    }
+    codes[2 * i] = c0;
+    codes[2 * i + 1] = c1;
+    flags[i] = f;
 }
 
 __device__ __forceinline__ int half_s(uint32_t v, int h) { return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFFu)); }
@@ -230,7 +263,8 @@ __global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <=
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
-               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad) {
+               uint32_t* __restrict__ redo_list, FastConsts k, int rows_pad, const uint4* __restrict__ tpack,
+               const uint2* __restrict__ tflag) {
     extern __shared__ uint8_t fast_smem[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(fast_smem);  // 8 profile words for pair A (low halves), 8 for pair B
     if (threadIdx.x < 16) lut[threadIdx.x] = profile_word(threadIdx.x & 7, k, threadIdx.x >> 3);
@@ -249,8 +283,14 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     uint32_t* ring = reinterpret_cast<uint32_t*>(fast_smem + kFastLutBytes + (size_t)WPB * GPW * rows_pad) + warp * kRingWords;
 
     // ---- staging: target profiles into shared memory, query selectors into registers ----------------
+    // Two forms of the targets.  (1) ASCII windows (explicit windows of a batch): every lane of a group converts the rows
+    // r = gl, gl + L, ... with byte loads.  (2) Windows of the resident reference in its packed form (2 bits per base +
+    // a "not ACGT" bit plane, pack_reference_kernel): the WARP stages one window after the other -- its 64-base units
+    // arrive with one 128-bit and one 64-bit load per lane, coalesced, land in a small per-warp buffer, and the 32 lanes
+    // unpack the rows of that window into the group's row codes.
     bool bad_a = false, bad_b = false;
     int rows = 0, tlen_a = 0, tlen_b = 0, qlen = 0;
+    uint32_t toff_a = 0, toff_b = 0;
     const uint8_t *qa = nullptr, *qb = nullptr;
     FastGeom geo = fast_geom(L * C);
     if (live) {
@@ -259,15 +299,57 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         geo = fast_geom(qlen);
         rows = grp.rows;
         tlen_a = ma.tlen; tlen_b = mb.tlen;
+        toff_a = ma.toff; toff_b = mb.toff;
         qa = qbuf + ma.qoff; qb = qbuf + mb.qoff;
-        const uint8_t* ta = tbuf + ma.toff;
-        const uint8_t* tb = tbuf + mb.toff;
-        for (int r = gl; r < rows; r += L) {
-            uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
-            if (r < tlen_a) { ca = base_code(nibble_of(ta[r])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
-            if (r < tlen_b) { cb = base_code(nibble_of(tb[r])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
-            tcodes[r] = (uint8_t)(ca | (cb << 4));
+        if (!tpack) {
+            const uint8_t* ta = tbuf + ma.toff;
+            const uint8_t* tb = tbuf + mb.toff;
+            for (int r = gl; r < rows; r += L) {
+                uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
+                if (r < tlen_a) { ca = base_code(nibble_of(ta[r])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
+                if (r < tlen_b) { cb = base_code(nibble_of(tb[r])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
+                tcodes[r] = (uint8_t)(ca | (cb << 4));
+            }
         }
+    }
+    if (tpack) {  // (uniform over the launch)
+        uint8_t* stage = fast_smem + kFastLutBytes + (size_t)WPB * GPW * rows_pad + (size_t)WPB * kRingWords * 4 + (size_t)warp * kFastStageBytes;
+        uint4* wcode = reinterpret_cast<uint4*>(stage);
+        uint2* wflag = reinterpret_cast<uint2*>(stage + 16 * kFastStageUnits);
+        uint32_t* wbad = reinterpret_cast<uint32_t*>(stage + 24 * kFastStageUnits);
+        if (lane == 0) *wbad = 0u;
+        for (int w = 0; w < 2 * GPW; ++w) {
+            const int src = (w >> 1) * L;  // first lane of the group
+            const uint32_t o = __shfl_sync(0xFFFFFFFFu, (w & 1) ? toff_b : toff_a, src);
+            const int tl = __shfl_sync(0xFFFFFFFFu, (w & 1) ? tlen_b : tlen_a, src);
+            const int rws = __shfl_sync(0xFFFFFFFFu, rows, src);
+            if (!__shfl_sync(0xFFFFFFFFu, live ? 1 : 0, src)) continue;
+            const uint32_t u0 = o >> 6;                                             // first 64-base unit of the window
+            const int nu = (int)(((o & 63u) + (uint32_t)tl + 63u) >> 6);           // units it touches (<= kFastStageUnits)
+            __syncwarp();
+            for (int u = lane; u < nu; u += 32) { wcode[u] = __ldg(tpack + u0 + u); wflag[u] = __ldg(tflag + u0 + u); }
+            __syncwarp();
+            uint8_t* tc = fast_smem + kFastLutBytes + (size_t)(warp * GPW + (w >> 1)) * rows_pad;
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(wcode);
+            const uint32_t* fw = reinterpret_cast<const uint32_t*>(wflag);
+            bool bad = false;
+            for (int r = lane; r < rws; r += 32) {
+                uint32_t c = 5u;  // rows past this pair's own window
+                if (r < tl) {
+                    const uint32_t pos = (o & 63u) + (uint32_t)r;
+                    const uint32_t code = (cw[pos >> 4] >> (2u * (pos & 15u))) & 3u;
+                    const bool other = (fw[pos >> 5] >> (pos & 31u)) & 1u;        // N (code 0) or a symbol outside ACGTN (code 1)
+                    c = other ? (code == 0u ? 4u : 5u) : code;
+                    bad |= other && code != 0u;
+                }
+                if (w & 1) tc[r] |= (uint8_t)(c << 4); else tc[r] = (uint8_t)c;    // (row r is this lane's in both passes)
+            }
+            if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) *wbad |= 1u << w;
+        }
+        __syncwarp();
+        const uint32_t wb = *wbad;
+        bad_a |= (wb >> (2 * gi)) & 1u;
+        bad_b |= (wb >> (2 * gi + 1)) & 1u;
     }
     const int ncols = live ? ((gl < geo.rem) ? geo.C : geo.C - 1) : 0;
     const bool wide = live && (ncols == C);
@@ -503,12 +585,13 @@ namespace rsa {
 template <int L, int C>
 inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                            uint32_t* redo_list, const FastConsts& k, int max_rows) {
+                            uint32_t* redo_list, const FastConsts& k, int max_rows, const uint4* tpack, const uint2* tflag) {
     const int rows_pad = (max_rows + 15) & ~15;
     constexpr int WPB = fast_warps_per_block(L);
     const int groups_per_block = WPB * fast_groups_per_warp(L);
     const int blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-    const size_t smem = kFastLutBytes + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4;
+    const size_t smem = kFastLutBytes + (size_t)groups_per_block * rows_pad + (size_t)WPB * fast_ring_slots(L) * ((C + 3) / 4) * 32 * 4 +
+                        (tpack ? (size_t)WPB * kFastStageBytes : 0);
     if (smem > 48 * 1024) {
         // Long windows / wide lanes need the opt-in shared-memory limit.  The attribute belongs to the FUNCTION (per
         // device), not to the launch: setting it to this launch's size raced with other workers launching the same
@@ -527,16 +610,17 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
         }
     }
     fast_dp_kernel<L, C><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
-                                                                     redo, redo_list, k, rows_pad);
+                                                                     redo, redo_list, k, rows_pad, tpack, tflag);
 }
 
 // returns 0, or -1 when C is outside the instantiated range
 inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                              const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
-                             uint32_t* redo_list, const FastConsts& k, int max_rows) {
+                             uint32_t* redo_list, const FastConsts& k, int max_rows, const uint4* tpack = nullptr,
+                             const uint2* tflag = nullptr) {
     if (L == 16) {
         switch (C) {
-#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
             RSA_FAST_CASE16(17) RSA_FAST_CASE16(18) RSA_FAST_CASE16(19) RSA_FAST_CASE16(20) RSA_FAST_CASE16(21) RSA_FAST_CASE16(22)
             RSA_FAST_CASE16(23) RSA_FAST_CASE16(24) RSA_FAST_CASE16(25) RSA_FAST_CASE16(26) RSA_FAST_CASE16(27) RSA_FAST_CASE16(28)
             RSA_FAST_CASE16(29) RSA_FAST_CASE16(30) RSA_FAST_CASE16(31) RSA_FAST_CASE16(32)
@@ -546,7 +630,7 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
     }
     if (L == 4) {
         switch (C) {
-#define RSA_FAST_CASE4(c) case c: launch_fast_one<4, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+#define RSA_FAST_CASE4(c) case c: launch_fast_one<4, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
             RSA_FAST_CASE4(2) RSA_FAST_CASE4(3) RSA_FAST_CASE4(4) RSA_FAST_CASE4(5) RSA_FAST_CASE4(6) RSA_FAST_CASE4(7) RSA_FAST_CASE4(8)
             RSA_FAST_CASE4(9) RSA_FAST_CASE4(10) RSA_FAST_CASE4(11) RSA_FAST_CASE4(12) RSA_FAST_CASE4(13) RSA_FAST_CASE4(14)
             RSA_FAST_CASE4(15) RSA_FAST_CASE4(16) RSA_FAST_CASE4(17) RSA_FAST_CASE4(18) RSA_FAST_CASE4(19) RSA_FAST_CASE4(20)
@@ -559,7 +643,7 @@ inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, co
         }
     }
     switch (C) {
-#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows); return 0;
+#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
 #if RSA_FAST_L4_MAXQ < 160   // (A/B builds without 4-lane groups)
         RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6) RSA_FAST_CASE(7)
         RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12) RSA_FAST_CASE(13) RSA_FAST_CASE(14)

@@ -28,6 +28,7 @@ RLE_INLINE = 40
 FLAG_EXACT_ONLY = 1
 FLAG_SERIALIZE = 2
 FLAG_HOST_PLAN = 4
+FLAG_ASCII_WINDOWS = 8
 
 RESULT_DTYPE = np.dtype([
     ("score", "<i4"), ("query_start", "<i4"), ("query_end", "<i4"), ("ref_start", "<i4"),
@@ -66,7 +67,7 @@ ABI_SYMBOLS = [
     "rsa_ext_stage_resident", "rsa_ext_run_resident", "rsa_ext_fetch_resident", "rsa_ext_stream",
     "rsa_ext_get_stats", "rsa_ext_version", "rsa_ext_device_count", "rsa_ext_request_alninfo", "rsa_ext_plan_debug",
     "rsa_ext_reserve", "rsa_ext_set_reference", "rsa_ext_submit_ref_windows", "rsa_ext_share_reference", "rsa_ext_scan_debug",
-    "rsa_ext_hamming_align", "rsa_ext_hamming_ref_windows",
+    "rsa_ext_hamming_align", "rsa_ext_hamming_ref_windows", "rsa_ext_packed_reference",
 ]
 
 _lib = None
@@ -126,6 +127,8 @@ def load_library() -> C.CDLL:
     lib.rsa_ext_share_reference.restype = C.c_int
     lib.rsa_ext_submit_ref_windows.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     lib.rsa_ext_submit_ref_windows.restype = C.c_int
+    lib.rsa_ext_packed_reference.argtypes = [vp, vp, vp, i64]
+    lib.rsa_ext_packed_reference.restype = C.c_int
     lib.rsa_ext_hamming_align.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp]
     lib.rsa_ext_hamming_align.restype = C.c_int
     lib.rsa_ext_hamming_ref_windows.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp]
@@ -172,11 +175,12 @@ class ExtensionEngine:
 
     def __init__(self, device: int = 0, match: int = 2, mismatch: int = 8, gap_open: int = 12,
                  gap_extend: int = 1, max_query_len: int = 500, max_target_len: int = 2000,
-                 exact_only: bool = False, scratch_bytes: int = 0, serialize: bool = False, host_plan: bool = False):
+                 exact_only: bool = False, scratch_bytes: int = 0, serialize: bool = False, host_plan: bool = False,
+                 ascii_windows: bool = False):
         self.lib = load_library()
         self.cfg = Config(device, max_query_len, max_target_len, match, mismatch, gap_open, gap_extend,
                           (FLAG_EXACT_ONLY if exact_only else 0) | (FLAG_SERIALIZE if serialize else 0) |
-                          (FLAG_HOST_PLAN if host_plan else 0), scratch_bytes)
+                          (FLAG_HOST_PLAN if host_plan else 0) | (FLAG_ASCII_WINDOWS if ascii_windows else 0), scratch_bytes)
         h = C.c_void_p()
         rc = self.lib.rsa_ext_create(C.byref(self.cfg), C.byref(h))
         if rc != 0:
@@ -225,6 +229,15 @@ class ExtensionEngine:
         assert seq.dtype == np.uint8
         self._ref_keep = np.ascontiguousarray(seq)
         self._check(self.lib.rsa_ext_set_reference(self.h, self._ref_keep.ctypes.data, len(self._ref_keep)))
+
+    def packed_reference(self, n_bases: int):
+        """The packed planes of the resident reference as the DP kernel's staging reads them: (codes uint32[], 16 bases
+        of 2 bits per word; flags uint32[], 32 "not ACGT" bits per word), whole 64-base units."""
+        units = (n_bases + 63) // 64
+        codes = np.zeros(units * 4, np.uint32)
+        flags = np.zeros(units * 2, np.uint32)
+        self._check(self.lib.rsa_ext_packed_reference(self.h, codes.ctypes.data, flags.ctypes.data, units))
+        return codes, flags
 
     def share_reference(self, donor: "ExtensionEngine"):
         """Use the resident reference another engine on the same device uploaded (one copy in HBM)."""

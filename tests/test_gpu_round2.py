@@ -229,3 +229,72 @@ def test_device_planner_many_chunks_and_exact_only():
     e.close()
     assert st["pairs_fast"] == 0
     assert got.tobytes() == want.tobytes()
+
+
+def test_packed_reference_planes_and_vectorised_window_staging(oracle_lib):
+    """north_star staging: the resident reference is packed to 2 bits per base + a "not ACGT" plane on
+    upload and the packed DP kernel stages windows from those planes with 128-bit loads.  (1) the planes equal a numpy
+    packing; (2) window batches staged from the planes give the byte-identical records of the same batches staged from
+    the ASCII copy (RSA_EXT_FLAG_ASCII_WINDOWS) and of explicit windows -- with N, IUPAC and lower-case symbols in the
+    reference, windows at both ends of it, every window phase mod 64, 2047-base windows and 250-bp reads; (3) a sample
+    equals the oracle."""
+    rng = np.random.default_rng(2024)
+    ref = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1_000_003)
+    ref[rng.integers(0, len(ref), size=400)] = ord("N")
+    ref[rng.integers(0, len(ref), size=60)] = ord("R")
+    ref[rng.integers(0, len(ref), size=60)] = ord("n")
+    low = rng.integers(0, len(ref) - 50, size=200)
+    for p in low:
+        ref[p:p + 20] |= 0x20  # soft-masked stretches
+    e = ExtensionEngine(max_target_len=2047)
+    e.set_reference(ref)
+    codes, flags = e.packed_reference(len(ref))
+    nib = ref & 0xF
+    code = np.full(len(ref), 0xF, np.uint8)
+    for k, v in ((1, 0), (3, 1), (7, 2), (4, 3), (0xE, 4)):
+        code[nib == k] = v
+    two = np.where(code < 4, code, np.where(code == 4, 0, 1)).astype(np.uint32)
+    pad = (-len(ref)) % 64
+    two = np.concatenate([two, np.zeros(pad, np.uint32)]).reshape(-1, 16)
+    want_codes = (two << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+    fl = np.concatenate([(code >= 4).astype(np.uint32), np.zeros(pad, np.uint32)]).reshape(-1, 32)
+    want_flags = (fl << np.arange(32, dtype=np.uint32)).sum(axis=1).astype(np.uint32)
+    assert (codes == want_codes).all() and (flags == want_flags).all()
+
+    n = 40_000
+    read_len = np.where(np.arange(n) % 5 == 0, 250, 150)
+    win_len = (read_len + rng.integers(0, 200, size=n)).astype(np.int32)
+    win_len[:64] = 2047
+    win_off = rng.integers(0, len(ref) - 2100, size=n).astype(np.int64)
+    win_off[:64] = 5000 + np.arange(64)            # every phase of a long window
+    win_off[64], win_len[64] = 0, 300              # first bases of the reference
+    win_off[65] = len(ref) - 300; win_len[65] = 300  # last bases
+    win_off[66] = len(ref) - 151; win_len[66] = 151
+    qs, ts = [], []
+    for i in range(n):
+        w = ref[win_off[i]:win_off[i] + win_len[i]]
+        lo = int(rng.integers(0, max(1, len(w) - read_len[i])))
+        q = w[lo:lo + read_len[i]].copy()
+        mut = rng.random(len(q)) < 0.02
+        q[mut] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(mut.sum()))
+        if i % 6 == 0 and len(q) > 60:
+            q = np.concatenate([q[:40], q[42:]])
+        qs.append(q.tobytes())
+        ts.append(w.tobytes())
+    b = W.from_lists(qs, ts)
+    packed = e.align_ref_windows(b.qbuf, b.qoff, win_off, win_len).copy()
+    explicit = e.align_packed(b.qbuf, b.qoff, b.tbuf, b.toff).copy()
+    e.close()
+    e2 = ExtensionEngine(ascii_windows=True, max_target_len=2047)
+    e2.set_reference(ref)
+    ascii_form = e2.align_ref_windows(b.qbuf, b.qoff, win_off, win_len).copy()
+    short = explicit["n_ops"] <= 40
+    for f in ["score", "query_start", "query_end", "ref_start", "ref_end", "n_ops", "status"]:
+        assert (packed[f] == explicit[f]).all(), f
+        assert (packed[f] == ascii_form[f]).all(), f
+    assert (packed["rle"][short] == explicit["rle"][short]).all() and (packed["rle"][short] == ascii_form["rle"][short]).all()
+    assert (packed["status"] == 0).all()
+    sub = b.slice(0, 2500)
+    bad = compare(e2, packed[:2500], oracle_arrays(oracle_lib, sub), sub)
+    e2.close()
+    assert not bad, "\n".join(bad)
