@@ -10,12 +10,14 @@ all: $(LIB) tools/dpx_microbench oracle
 tools/dpx_microbench: tools/dpx_microbench.cu $(CSRC)/fast_cell.cuh $(CSRC)/common.cuh
 	$(NVCC) -O3 -std=c++17 -lineinfo $(ARCH) -o $@ $<
 
-# two translation units (extension engine, seeding) compiled in parallel, one product library
+# three translation units (extension engine, seeding, SAM formatter), one product library
 $(CSRC)/engine.o: $(CSRC)/engine.cu $(wildcard $(CSRC)/*.cuh) include/rsa_ext.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 $(CSRC)/seed.o: $(CSRC)/seed.cu $(CSRC)/kernels_seed.cuh include/rsa_seed.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
-$(LIB): $(CSRC)/engine.o $(CSRC)/seed.o
+$(CSRC)/sam.o: $(CSRC)/sam.cu include/rsa_sam.h include/rsa_ext.h
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(LIB): $(CSRC)/engine.o $(CSRC)/seed.o $(CSRC)/sam.o
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
 ptxas-info:

@@ -232,6 +232,51 @@ def hamming_reference(qbuf, qoff, tbuf, toff, match=2, mismatch=8, end_bonus=10)
     return out
 
 
+SAM_CALL_DTYPE = np.dtype([
+    ("kind", "<i4"), ("is_primary", "<i4"), ("is_proper", "<i4"), ("mapq1", "<u4"), ("mapq2", "<u4"), ("unmapped_flags", "<u4"),
+    ("a1", [("ref_id", "<i4"), ("ref_start", "<i4"), ("edit_distance", "<i4"), ("score", "<i4"), ("length", "<i4"),
+            ("is_rc", "<i4"), ("is_unaligned", "<i4"), ("cigar_off", "<u4"), ("n_cigar", "<u4")]),
+    ("a2", [("ref_id", "<i4"), ("ref_start", "<i4"), ("edit_distance", "<i4"), ("score", "<i4"), ("length", "<i4"),
+            ("is_rc", "<i4"), ("is_unaligned", "<i4"), ("cigar_off", "<u4"), ("n_cigar", "<u4")]),
+    ("r1", np.dtype([("name_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u8"), ("name_len", "<u4"), ("seq_len", "<u4"),
+                     ("qual_len", "<u4")], align=True)),
+    ("r2", np.dtype([("name_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u8"), ("name_len", "<u4"), ("seq_len", "<u4"),
+                     ("qual_len", "<u4")], align=True)),
+    ("details1", "<u4", (5,)), ("details2", "<u4", (5,))], align=True)
+assert SAM_CALL_DTYPE.itemsize == 216
+
+
+def sam_reference_replay(ref_names, calls, text_pool, cigar_pool, cigar_m=False, read_group=b"", output_unmapped=True,
+                         show_details=False):
+    """The reference's own SAM writer (class Sam, src/sam.cpp, compiled into oracle/_ref/libsam_ref.so) replaying a list of
+    Sam::add / add_pair / add_unmapped / add_unmapped_pair calls (SAM_CALL_DTYPE); returns the text, or None when
+    _ref/ was not built."""
+    p = os.path.join(_HERE, "_ref", "libsam_ref.so")
+    if not os.path.exists(p):
+        return None
+    if "sam" not in _cache:
+        lib = C.CDLL(p)
+        vp, i64, i32 = C.c_void_p, C.c_longlong, C.c_int
+        lib.sam_ref_replay.argtypes = [i32, vp, vp, i32, C.c_char_p, i32, i32, i64, vp, vp, vp, vp, i64]
+        lib.sam_ref_replay.restype = i64
+        _cache["sam"] = lib
+    lib = _cache["sam"]
+    buf = b"".join(ref_names)
+    off = np.zeros(len(ref_names) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in ref_names])
+    nb = np.frombuffer(buf, np.uint8).copy() if buf else np.zeros(1, np.uint8)
+    calls = np.ascontiguousarray(calls, dtype=SAM_CALL_DTYPE)
+    cigar_pool = np.ascontiguousarray(cigar_pool, dtype=np.uint32)
+    cap = len(text_pool) * 2 + 400 * len(calls) + 16 * len(cigar_pool) + 1024
+    out = np.zeros(cap, np.uint8)
+    n = lib.sam_ref_replay(len(ref_names), nb.ctypes.data, off.ctypes.data, int(cigar_m), read_group, int(output_unmapped),
+                           int(show_details), len(calls), calls.ctypes.data, text_pool.ctypes.data,
+                           cigar_pool.ctypes.data if len(cigar_pool) else None, out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("sam_ref_replay: output buffer too small")
+    return out[:n].tobytes()
+
+
 def ssw_reference() -> Optional[SswReference]:
     if "ssw" not in _cache:
         flags = ""
