@@ -257,9 +257,13 @@ template <int L, int C>
 // 1894); per-column selectors re-loaded from shared memory each row instead of held in C registers (168 registers, no
 // spills, DP phase 2037 -- but 74 KB of shared memory per block leave no room for the traceback kernel beside it: 1732).)
 #ifndef RSA_FAST_WIDE_BLOCKS
-#define RSA_FAST_WIDE_BLOCKS 3   // (A/B builds)
+#define RSA_FAST_WIDE_BLOCKS 3   // (A/B builds) 4-lane groups, C > 27
 #endif
-__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : RSA_FAST_WIDE_BLOCKS))))
+#ifndef RSA_FAST_WIDE_BLOCKS8
+#define RSA_FAST_WIDE_BLOCKS8 2  // (A/B builds) 8-lane groups, C > 27: 255 registers; capped at 168 the 250-bp batch measured
+                                 // DP phase 1848 vs 1824 GCUPS but value 1784 vs 1859 (less room beside the traceback)
+#endif
+__global__ void __launch_bounds__(32 * fast_warps_per_block(L), (L == 16 ? (C <= 27 ? 6 : 4) : (C <= 20 ? 4 : (C <= 27 ? 3 : (L == 4 ? RSA_FAST_WIDE_BLOCKS : RSA_FAST_WIDE_BLOCKS8)))))
 fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbuf,
                const PairMeta* __restrict__ meta, const FastGroup* __restrict__ groups, int n_groups,
                uint8_t* __restrict__ scratch, DpEnd* __restrict__ ends, RedoHeader* __restrict__ redo,
