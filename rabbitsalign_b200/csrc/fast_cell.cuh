@@ -6,19 +6,25 @@
 // on the FMA pipe does.  Compared with the round-1 recipe (carry-trick flags: 3 IADD3 + 3 LOP3 + shift/insert per cell)
 //   * the four direction facts are CLEAN 0/1 values per half, one VIADDMNMX.S16x2.RELU each:
 //     clamp(a + (-b) + c, 0, 1); the negated operands are IMADs (FMA pipe);
-//   * clean 0/1 halves are fp16 denormals whose bit pattern IS their integer value, so the facts are merged into a
-//     nibble, and two nibbles into a byte, with HFMA2 (x*2^k + y is exact below 2048): FMA pipe again, no LOP3/SHF;
+//   * clean 0/1 halves need no masks: the facts are merged into a nibble, and two nibbles into a byte, with multiply-adds
+//     x * 2^k + y on the packed register (IMAD, FMA pipe again: no LOP3/SHF).  HFMA2 does the same on the fp16 view (0/1
+//     halves are denormals whose bit pattern is their integer value; exact below 2048) but measured slower: mixing fp16
+//     and integer work on the FMA pipe costs issue slots (bare recipe 2544 vs 2798 GCUPS, kernel 1901 vs 1970);
 //   * the substitution profile carries (score - gap_open_extend) as SIGNED bytes, so S = H(diag) + profile is already the
 //     "open a gap from the diagonal" value both E' and F' need (no separate add), and H takes its "+ gap_oe" inside the
 //     fused add+max.
 // ALU pipe per cell pair: PRMT, VIMNMX3, 3 VIADDMNMX, 4 VIADDMNMX.RELU, 1/2 VIMNMX3 (row key), 1/4 PRMT (word).
-// FMA pipe per cell pair: 5 IMAD (S, three negations, key) + 3.5 HFMA2.
+// FMA pipe per cell pair: 8.5 IMAD (S, three negations, key, 3.5 merges).
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace rsa {
+
+#ifndef RSA_CELL_IMAD_MERGE
+#define RSA_CELL_IMAD_MERGE 1   // 0: merge the direction facts with HFMA2 on denormal bit patterns instead (A/B builds)
+#endif
 
 constexpr int kBias = 64;  // every stored half = value + kBias; E,F >= -(mismatch+gap_oe) > -kBias
 
@@ -31,7 +37,8 @@ struct FastConsts {
     uint32_t c_b2;     // b2 = c_b2 - S  : per half  -S - gap_oe        (H != diagonal)
     uint32_t c_b3;     // b3 = c_b3 - F  : per half  -F                 (max(F,E,0) != F)
     uint32_t sub_n;    // S increment of a query N: (-gap_oe, -gap_oe - 1)
-    uint32_t h2, h4, h16;   // fp16 pairs 2.0, 4.0, 16.0
+    uint32_t i2, i4, i16;   // multipliers of the fact merges (in registers so that the products stay IMADs)
+    uint32_t h2, h4, h16;   // (A/B builds: the same as fp16 pairs 2.0, 4.0, 16.0)
     uint32_t k32, k64, minus1;  // multipliers kept in registers so that the products below stay IMADs (FMA pipe)
     int match, mismatch, gap_oe;
     int bias;
@@ -65,6 +72,7 @@ __host__ inline FastConsts make_fast_consts(const Scoring& sc) {
     k.h2 = 0x40004000u;
     k.h4 = 0x44004400u;
     k.h16 = 0x4C004C00u;
+    k.i2 = 2u; k.i4 = 4u; k.i16 = 16u;
     k.k32 = 32u;
     k.k64 = 64u;
     k.minus1 = 0xFFFFFFFFu;
@@ -164,14 +172,22 @@ __host__ __device__ __forceinline__ void fast_cell(const FastConsts& k, uint32_t
     const uint32_t xe = __viaddmin_s16x2_relu(e, b1, k.one16);
     const uint32_t nd = __viaddmin_s16x2_relu(u, b2, k.one16);   // clamp(u - (diag + sub), 0, 1)
     const uint32_t nf = __viaddmin_s16x2_relu(u, b3, k.one16);   // clamp(u - F, 0, 1)
-    nib = hfma2(hfma2(xf, k.h2, xe), k.h4, hfma2(nd, k.h2, nf)); // 8 xf + 4 xe + 2 nd + nf   (FMA pipe)
+#if RSA_CELL_IMAD_MERGE
+    nib = imad(imad(xf, k.i2, xe), k.i4, imad(nd, k.i2, nf));    // 8 xf + 4 xe + 2 nd + nf   (FMA pipe)
+#else
+    nib = hfma2(hfma2(xf, k.h2, xe), k.h4, hfma2(nd, k.h2, nf));
+#endif
     key = imad(h, kmul, colconst);                               // ((h-bias) << B) | (2^B - 1 - column), FMA pipe
 }
 
 // Gathering the direction nibbles of four columns into one word (nibble k of each half = column k of the word): two
-// nibbles make a byte with one HFMA2 (FMA pipe), one byte-permute puts the two bytes of each half in place.
+// nibbles make a byte with one multiply-add (FMA pipe), one byte-permute puts the two bytes of each half in place.
 __host__ __device__ __forceinline__ uint32_t dir_pair(const FastConsts& k, uint32_t nib_even, uint32_t nib_odd) {   // bits 7..0 of each half
+#if RSA_CELL_IMAD_MERGE
+    return imad(nib_odd, k.i16, nib_even);
+#else
     return hfma2(nib_odd, k.h16, nib_even);
+#endif
 }
 __host__ __device__ __forceinline__ uint32_t dir_word(uint32_t p01, uint32_t p23) { return prmt(p01, p23, 0x6240u); }
 
