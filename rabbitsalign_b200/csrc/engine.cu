@@ -88,7 +88,7 @@ struct ChunkPlan {
     int n_exact[3] = {0, 0, 0};     // tasks per exact class (C = 4, 8, 16), consecutive in `list`
     int max_tlen_exact[3] = {0, 0, 0};
     int n_fast_classes = 0;
-    struct FastClass { int L; int C; int group_begin; int n_groups; int max_tlen; };
+    struct FastClass { int L; int C; int group_begin; int n_groups; int max_tlen; bool flex = false; };
     std::vector<FastClass> fast;
     int64_t n_fast_pairs = 0;
     int64_t n_failed = 0;
@@ -169,6 +169,10 @@ struct ResidentChunk {
 
 }  // namespace
 
+// A chunk of variable-length reads has one launch per column class; classes are independent, so each gets its own stream
+// (small classes are latency-bound single waves: back to back on few streams they cost ~0.3 ms each)
+constexpr int kClsStreams = 7;
+
 struct rsa_ext {
     rsa_ext_config_t cfg{};
     Scoring sc{};
@@ -176,8 +180,8 @@ struct rsa_ext {
     bool fast_ok = false;
     int n_sms = 148;
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_comp2 = nullptr, s_tb = nullptr, s_d2h = nullptr, s_plan = nullptr;
-    cudaStream_t s_cls[2] = {nullptr, nullptr};  // side streams for the column classes of one chunk
-    cudaEvent_t ev_cls_fork = nullptr, ev_cls_join[2] = {nullptr, nullptr};
+    cudaStream_t s_cls[kClsStreams] = {};  // side streams for the column classes of one chunk
+    cudaEvent_t ev_cls_fork = nullptr, ev_cls_join[kClsStreams] = {};
     cudaEvent_t ev_fork = nullptr;  // orders the second DP stream behind what the caller put on the first
     int dp_toggle = 0;              // consecutive chunks alternate between the two DP streams so that the next
                                     // chunk's blocks fill the SMs while the previous kernel's last wave drains
@@ -359,6 +363,44 @@ size_t blob_layout(ChunkPlan& plan, int64_t n) {
     return off;
 }
 
+// Variable-length batches: one launch per column class means many small launches, each a partly filled, latency-bound
+// wave (a 131 k-pair chunk of indel-rich 250-bp reads has ten classes).  Neighbouring classes of one lane count whose widths
+// fall into the same four-column bucket can share a "flex" launch of the bucket's width (FastDp<.., FLEX>), at the price of
+// the idle column slots of the narrower groups.  Merge a bucket when those idle columns cost less than the partial waves
+// the separate launches would leave (about half a wave each).  Classes are contiguous runs of the group array, so a merged
+// class is just the union of the runs.
+void merge_small_classes(std::vector<ChunkPlan::FastClass>& fast) {
+    if (fast.size() < 3 || getenv("RSA_EXT_NO_FLEX")) return;
+    std::vector<ChunkPlan::FastClass> out;
+    size_t i = 0;
+    while (i < fast.size()) {
+        const int L = fast[i].L, b = fast_flex_width(L, fast[i].C);
+        size_t j = i;
+        double idle = 0, groups = 0;
+        while (j < fast.size() && fast[j].L == L && fast_flex_width(L, fast[j].C) == b && b - fast[j].C <= kFlexSlack) {
+            idle += (double)fast[j].n_groups * (b - fast[j].C) / b;
+            groups += fast[j].n_groups;
+            ++j;
+        }
+        const int members = (int)(j - i);
+        const int gpb = fast_warps_per_block(L) * fast_groups_per_warp(L);
+        const int blocks_per_sm = L == 16 ? (b <= 27 ? 6 : 4) : (b <= 20 ? 4 : (b <= 27 ? 3 : (L == 4 ? RSA_FAST_WIDE_BLOCKS : RSA_FAST_WIDE_BLOCKS8)));
+        const double wave = 148.0 * blocks_per_sm * gpb;   // groups in flight in one full wave
+        if (members >= 2 && idle < 0.5 * wave * (members - 1)) {
+            ChunkPlan::FastClass m = fast[i];
+            m.C = b;
+            m.flex = true;
+            m.n_groups = fast[j - 1].group_begin + fast[j - 1].n_groups - fast[i].group_begin;
+            for (size_t k = i; k < j; ++k) m.max_tlen = std::max(m.max_tlen, fast[k].max_tlen);
+            out.push_back(m);
+        } else {
+            for (size_t k = i; k < j; ++k) out.push_back(fast[k]);
+        }
+        i = j > i ? j : i + 1;
+    }
+    fast.swap(out);
+}
+
 int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std::vector<uint8_t>* vec_blob,
                PinBuf* pin_blob) {
     const LenTables& LT = len_tables();
@@ -515,6 +557,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         while (n_groups % kGroupPad) groups[n_groups++] = empty;
         plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
     }
+    merge_small_classes(plan.fast);
     plan.n_fast_classes = (int)plan.fast.size();
 
     // 5) exact-kernel lists (statically routed pairs); pairs the packed kernel flags at run time get their
@@ -699,6 +742,7 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
     }
     while (n_groups % kGroupPad) ++n_groups;
     if (!plan.fast.empty()) plan.fast.back().n_groups = n_groups - plan.fast.back().group_begin;
+    merge_small_classes(plan.fast);
     plan.n_fast_classes = (int)plan.fast.size();
     plan.list_base[0] = 0;
     plan.list_base[1] = (unsigned)plan.n_exact[0];
@@ -756,21 +800,27 @@ int enqueue_compute(rsa_ext* h, cudaStream_t st, cudaStream_t st_tb, cudaEvent_t
     const bool spread = p.fast.size() > 1 && (h->cfg.flags & RSA_EXT_FLAG_SERIALIZE) == 0;
     if (spread) {
         CU_TRY(h, cudaEventRecord(h->ev_cls_fork, st));
-        for (int k = 0; k < 2; ++k) CU_TRY(h, cudaStreamWaitEvent(h->s_cls[k], h->ev_cls_fork, 0));
+        for (int k = 0; k < kClsStreams; ++k) CU_TRY(h, cudaStreamWaitEvent(h->s_cls[k], h->ev_cls_fork, 0));
     }
+    // largest classes first: their waves fill the SMs, the small (single-wave, latency-bound) classes run beside them
+    std::vector<int> order(p.fast.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    if (spread) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.fast[a].n_groups * p.fast[a].L > p.fast[b].n_groups * p.fast[b].L; });
     int cls_i = 0;
-    bool used_side[2] = {false, false};
-    for (const auto& fc : p.fast) {
+    bool used_side[kClsStreams] = {};
+    for (int oi : order) {
+        const auto& fc = p.fast[oi];
         cudaStream_t cst = st;
-        if (spread && cls_i % 3 != 0) { cst = h->s_cls[cls_i % 3 - 1]; used_side[cls_i % 3 - 1] = true; }
+        const int slot = cls_i % (kClsStreams + 1);
+        if (spread && slot != 0) { cst = h->s_cls[slot - 1]; used_side[slot - 1] = true; }
         ++cls_i;
-        int rc = launch_fast_class(cst, fc.L, fc.C, d.q, d.t, meta,
+        int rc = launch_fast_class(cst, fc.L, fc.C, fc.flex, d.q, d.t, meta,
                                    reinterpret_cast<const FastGroup*>(d.blob + p.off_groups) + fc.group_begin,
                                    fc.n_groups, d.scratch, d.ends, redo, redo_list, h->fk, fc.max_tlen, d.tpack, d.tflag);
         if (rc != 0) { h->err = "no packed-kernel instance for L=" + std::to_string(fc.L) + " C=" + std::to_string(fc.C); return RSA_EXT_ERR_STATE; }
         h->stats.kernel_launches++;
     }
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < kClsStreams; ++k)
         if (used_side[k]) {
             CU_TRY(h, cudaEventRecord(h->ev_cls_join[k], h->s_cls[k]));
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_cls_join[k], 0));
@@ -831,6 +881,16 @@ PlanInput pending_plan_input(const rsa_ext* h) {
 // Chunk-size ramp of a batch: the first chunks are small so that the GPU starts while the host still plans.
 // Inline planning shares the caller's thread with enqueue/retire (16k, 32k, 64k); the plan-ahead thread runs
 // continuously, so its ramp only has to keep (plan + H2D) of chunk k+1 below the GPU time of chunk k.
+// Balanced tail: when the greedy cut of a chunk leaves less than half a chunk behind it, the batch ends with a small
+// chunk whose launches are single, partly filled waves (latency-bound: ~0.3 ms per column class for almost no work).
+// Cutting the last two chunks evenly instead costs one more planning pass over this chunk's pairs.  Returns the pair cap
+// for a second pass, or 0 to keep the cut.
+inline int64_t balanced_tail_cap(int64_t n, int64_t lo, int64_t hi) {
+    const int64_t tail = n - hi, got = hi - lo;
+    if (tail <= 0 || got < 8192 || 2 * tail >= got) return 0;
+    return (n - lo + 1) / 2;
+}
+
 int64_t ramp_pairs(bool plan_ahead, long chunk_index) {
     static const std::vector<int64_t> knob = [] {  // RSA_EXT_RAMP="16384,65536": experiment knob
         std::vector<int64_t> v;
@@ -958,6 +1018,12 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
         in.max_pairs = ramp_pairs(false, h->chunks_enqueued);
         if ((rc = ensure_pin(h, s.h_blob, sizeof(PlanQlen) * kPlanQ))) return rc;
         rc = scan_chunk(h, in, h->next_pair, s.plan, reinterpret_cast<PlanQlen*>(s.h_blob.p));
+        if (!rc) {
+            if (const int64_t cap = balanced_tail_cap(in.n, h->next_pair, s.plan.hi)) {
+                in.max_pairs = cap;
+                rc = scan_chunk(h, in, h->next_pair, s.plan, reinterpret_cast<PlanQlen*>(s.h_blob.p));
+            }
+        }
         h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
         if (rc) return rc;
         h_blob = s.h_blob.p;
@@ -965,6 +1031,12 @@ int enqueue_chunk(rsa_ext* h, Slot& s) {
         PlanInput in = pending_plan_input(h);
         in.max_pairs = ramp_pairs(false, h->chunks_enqueued);
         rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
+        if (!rc) {
+            if (const int64_t cap = balanced_tail_cap(in.n, h->next_pair, s.plan.hi)) {
+                in.max_pairs = cap;
+                rc = plan_chunk(h, in, h->next_pair, s.plan, nullptr, &s.h_blob);
+            }
+        }
         h->stats.host_plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
         if (rc) return rc;
         h_blob = s.h_blob.p;
@@ -1244,7 +1316,7 @@ extern "C" int rsa_ext_create(const rsa_ext_config_t* cfg_in, rsa_ext_t** out) {
     if ((e = cudaStreamCreateWithFlags(&h->s_comp2, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     if ((e = cudaEventCreateWithFlags(&h->ev_cls_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kClsStreams; ++k) {
         if ((e = cudaStreamCreateWithFlags(&h->s_cls[k], cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
         if ((e = cudaEventCreateWithFlags(&h->ev_cls_join[k], cudaEventDisableTiming)) != cudaSuccess) return fail("event", e);
     }
@@ -1327,7 +1399,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     if (h->s_comp2) cudaStreamDestroy(h->s_comp2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_cls_fork) cudaEventDestroy(h->ev_cls_fork);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kClsStreams; ++k) {
         if (h->s_cls[k]) { cudaStreamSynchronize(h->s_cls[k]); cudaStreamDestroy(h->s_cls[k]); }
         if (h->ev_cls_join[k]) cudaEventDestroy(h->ev_cls_join[k]);
     }
@@ -1735,6 +1807,12 @@ extern "C" int rsa_ext_stage_resident(rsa_ext_t* h, int64_t n, const char* qbuf,
         blobs.emplace_back();
         int rc = plan_chunk(h, in, lo, rc_.plan, &blobs.back(), nullptr);
         if (rc) return rc;
+        if (const int64_t cap = balanced_tail_cap(n, lo, rc_.plan.hi)) {
+            PlanInput in2 = in;
+            in2.max_pairs = cap;
+            blobs.back().clear();
+            if ((rc = plan_chunk(h, in2, lo, rc_.plan, &blobs.back(), nullptr))) return rc;
+        }
         rc_.q_base = (size_t)(qoff[lo] - qoff[0]);
         rc_.t_base = (size_t)(toff[lo] - toff[0]);
         blob_total += align_up(rc_.plan.blob_bytes, 256);

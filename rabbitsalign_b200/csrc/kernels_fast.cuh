@@ -126,7 +126,12 @@ __host__ __device__ inline bool fast_key_ok(int qlen, int match) {
     return match * qlen <= (fast_lanes_for(qlen) == 4 ? 511 : 1023);
 }
 
-template <int L, int C, bool HASN>
+// FLEX = false: every group of the launch has exactly C = ceil(|q|/L) columns per lane (the widest lanes; the others C - 1).
+// FLEX = true ("merged classes", variable-length batches): groups with ceil(|q|/L) in C-3 .. C share one launch; a lane
+// owns C-4 .. C columns, the last four column slots are conditional and a group's tile keeps its own (narrower) geometry.
+constexpr int kFlexSlack = 3;   // a flex launch of width C takes groups of width C - kFlexSlack .. C
+
+template <int L, int C, bool HASN, bool FLEX>
 struct FastDp {
     // One group's sweep.  All 32 lanes of the warp call this together (shuffles inside).
     //
@@ -138,7 +143,7 @@ struct FastDp {
     //   phase 2  the F-dependent chain left-to-right (H, E', F', direction flags, keys).
     __device__ static __forceinline__ void run(const FastConsts& k, const uint8_t* __restrict__ tcodes,
                                                const uint32_t* __restrict__ lut, int rows, int nsteps, int gl,
-                                               bool wide, const uint32_t (&qsel)[C], uint32_t* __restrict__ dir,
+                                               int ncols, int nw2g, const uint32_t (&qsel)[C], uint32_t* __restrict__ dir,
                                                uint32_t* __restrict__ ring, int lane, uint32_t& bestkey_out,
                                                int (&firstrow)[2]) {
         uint32_t S[C], E[C];
@@ -148,7 +153,10 @@ struct FastDp {
         uint32_t bestkey = 0;  // key of "no positive cell yet"
         firstrow[0] = firstrow[1] = 0;
         constexpr int NW = (C + 3) / 4;
-        constexpr int NW2 = (NW + 1) & ~1;      // stored words per lane and row (fast_layout.cuh)
+        constexpr int NW2 = (NW + 1) & ~1;      // stored words per lane and row (fast_layout.cuh); FLEX: the group's own, nw2g
+        constexpr int D = FLEX ? kFlexSlack + 1 : 1;   // a lane owns C - D .. C columns
+        const bool wide = ncols == C;
+        if (!FLEX) nw2g = NW2;
         constexpr int RS = fast_ring_slots(L);
         constexpr int CB = fast_col_bits(L);
         constexpr uint32_t kColMask = (uint32_t)((1 << CB) - 1) * 0x00010001u;
@@ -182,9 +190,9 @@ struct FastDp {
                 uint32_t rowkey = 0, nib_even = 0, p_lo = 0, Fsave = F, key_prev = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    if (c == C - 1) Fsave = F;  // F entering the last (conditional) column
-                    uint32_t nib = 0;           // (absent last column of a narrow lane: zero nibble)
-                    if (c < C - 1 || wide) {
+                    if (!FLEX && c == C - 1) Fsave = F;  // F entering the last (conditional) column
+                    uint32_t nib = 0;           // (absent column of a narrow lane: zero nibble)
+                    if (c < C - D || c < ncols) {
                         uint32_t h, fn, en, key;
                         fast_cell(k, S[c], F, E[c], key_colconst<CB>(c), kmul, h, fn, en, nib, key);
                         if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
@@ -193,6 +201,7 @@ struct FastDp {
                         S[c] = h;
                         E[c] = en;
                         F = fn;
+                        if (FLEX && c >= C - D - 1 && c == ncols - 1) { Hlast = h; Fout = fn; }   // the lane's last real column
                     } else if (c & 1) {
                         rowkey = __vmaxs2(rowkey, key_prev);  // (an even last column has no pending key)
                     }
@@ -205,8 +214,10 @@ struct FastDp {
                     else if ((c & 3) == 2) { nib_even = nib; if (c == C - 1) *slot = dir_word(p_lo, nib); }
                     else *slot = dir_word(p_lo, dir_pair(k, nib_even, nib));
                 }
-                Hlast = wide ? S[C - 1] : S[(C >= 2) ? C - 2 : 0];
-                Fout = wide ? F : Fsave;
+                if (!FLEX) {
+                    Hlast = wide ? S[C - 1] : S[(C >= 2) ? C - 2 : 0];
+                    Fout = wide ? F : Fsave;
+                }
                 // Running maximum of this lane, per half, kept as the FIRST cell in the reference's visiting order
                 // (8-row block, column, row in block) among the cells seen so far with the largest H:
                 //   row H > best H                      -> this row's key wins;
@@ -231,13 +242,14 @@ struct FastDp {
             const int rl = s - (L - 1);                   // row the last lane finished in this step
             if (rl >= 0 && (rl & 3) == 3 && rl - 3 < rows) {
                 const int rb = rl >> 2;
-                uint4* dblk = reinterpret_cast<uint4*>(dir) + ((size_t)rb * L + gl) * NW2;
+                uint4* dblk = reinterpret_cast<uint4*>(dir) + ((size_t)rb * L + gl) * nw2g;
                 const uint32_t* r0 = ring + ((((rl - 3 + gl) & (RS - 1)) * NW) << 5) + lane;
                 const uint32_t* r1 = ring + ((((rl - 2 + gl) & (RS - 1)) * NW) << 5) + lane;
                 const uint32_t* r2 = ring + ((((rl - 1 + gl) & (RS - 1)) * NW) << 5) + lane;
                 const uint32_t* r3 = ring + ((((rl + gl) & (RS - 1)) * NW) << 5) + lane;
 #pragma unroll
                 for (int wv = 0; wv < NW2; wv += 2) {
+                    if (FLEX && wv >= nw2g) break;   // a narrower group's tile has fewer words per lane and row
                     uint4 v, w = make_uint4(0u, 0u, 0u, 0u);
                     v.x = r0[wv << 5]; v.y = r1[wv << 5]; v.z = r2[wv << 5]; v.w = r3[wv << 5];
                     if (wv + 1 < NW) { w.x = r0[(wv + 1) << 5]; w.y = r1[(wv + 1) << 5]; w.z = r2[(wv + 1) << 5]; w.w = r3[(wv + 1) << 5]; }
@@ -250,7 +262,7 @@ struct FastDp {
     }
 };
 
-template <int L, int C>
+template <int L, int C, bool FLEX>
 // (4-lane groups with C = 28..40 columns would take ~250 registers: two blocks per SM.  Capped at 168 registers for three
 // blocks they spill ~30 words per thread and measure slightly faster with the clamp-fact recipe: DP phase 1983 vs 1971
 // GCUPS, value 1914 vs 1891.  A/B builds that did not pay, numbers in DESIGN.md 4.1: row loop unrolled by two (1951 /
@@ -356,7 +368,6 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         bad_b |= (wb >> (2 * gi + 1)) & 1u;
     }
     const int ncols = live ? ((gl < geo.rem) ? geo.C : geo.C - 1) : 0;
-    const bool wide = live && (ncols == C);
     const int col0 = live ? fast_lane_col0(geo, gl) : 0;
     uint32_t qsel[C];
     bool has_n = false;
@@ -389,8 +400,8 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
     uint32_t* dir = reinterpret_cast<uint32_t*>(scratch + grp.dir_off);
     uint32_t bestkey;
     int firstrow[2];
-    if (warp_has_n) FastDp<L, C, true>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
-    else FastDp<L, C, false>::run(k, tcodes, lut, rows, nsteps, gl, wide, qsel, dir, ring, lane, bestkey, firstrow);
+    if (warp_has_n) FastDp<L, C, true, FLEX>::run(k, tcodes, lut, rows, nsteps, gl, ncols, geo.W, qsel, dir, ring, lane, bestkey, firstrow);
+    else FastDp<L, C, false, FLEX>::run(k, tcodes, lut, rows, nsteps, gl, ncols, geo.W, qsel, dir, ring, lane, bestkey, firstrow);
 
     // ---- end cell per pair (half 0 = a, half 1 = b) --------------------------------------------------
     // Every lane holds its first-in-reference-order maximum cell; lanes own increasing column ranges, so among
@@ -586,7 +597,7 @@ exact_redo_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ 
 // ---- host-side launchers ------------------------------------------------------------------------------
 namespace rsa {
 
-template <int L, int C>
+template <int L, int C, bool FLEX = false>
 inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                             const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
                             uint32_t* redo_list, const FastConsts& k, int max_rows, const uint4* tpack, const uint2* tflag) {
@@ -609,55 +620,78 @@ inline void launch_fast_one(cudaStream_t st, const uint8_t* q, const uint8_t* t,
         if (dev >= 0 && dev < 64 && !done[dev]) {
             int optin = 0;
             cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            cudaFuncSetAttribute(fast_dp_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+            cudaFuncSetAttribute(fast_dp_kernel<L, C, FLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             done[dev] = true;
         }
     }
-    fast_dp_kernel<L, C><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
+    fast_dp_kernel<L, C, FLEX><<<blocks, 32 * WPB, smem, st>>>(q, t, meta, groups, n_groups, scratch, ends,
                                                                      redo, redo_list, k, rows_pad, tpack, tflag);
 }
 
+// Widths a merged ("flex") launch exists for: multiples of four columns per lane; a flex launch of width C takes groups of
+// width C - kFlexSlack .. C (FastDp<.., FLEX = true>).
+__host__ inline int fast_flex_width(int L, int C) {
+    const int b = (C + 3) / 4 * 4;
+    const int hi = L == 4 ? kFastMaxC : 32;
+    return b > hi ? hi : b;
+}
+
 // returns 0, or -1 when C is outside the instantiated range
-inline int launch_fast_class(cudaStream_t st, int L, int C, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
+inline int launch_fast_class(cudaStream_t st, int L, int C, bool flex, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
                              const FastGroup* groups, int n_groups, uint8_t* scratch, DpEnd* ends, RedoHeader* redo,
                              uint32_t* redo_list, const FastConsts& k, int max_rows, const uint4* tpack = nullptr,
                              const uint2* tflag = nullptr) {
+#define RSA_FAST_ARGS st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag
+#define RSA_FAST_CASE(l, c) case c: launch_fast_one<l, c, false>(RSA_FAST_ARGS); return 0;
+#define RSA_FLEX_CASE(l, c) case c: launch_fast_one<l, c, true>(RSA_FAST_ARGS); return 0;
+    if (flex) {
+        if (L == 16) {
+            switch (C) { RSA_FLEX_CASE(16, 20) RSA_FLEX_CASE(16, 24) RSA_FLEX_CASE(16, 28) RSA_FLEX_CASE(16, 32) default: return -1; }
+        }
+        if (L == 4) {
+            switch (C) {
+                RSA_FLEX_CASE(4, 4) RSA_FLEX_CASE(4, 8) RSA_FLEX_CASE(4, 12) RSA_FLEX_CASE(4, 16) RSA_FLEX_CASE(4, 20)
+                RSA_FLEX_CASE(4, 24) RSA_FLEX_CASE(4, 28) RSA_FLEX_CASE(4, 32) RSA_FLEX_CASE(4, 36) RSA_FLEX_CASE(4, 40)
+                default: return -1;
+            }
+        }
+        switch (C) { RSA_FLEX_CASE(8, 24) RSA_FLEX_CASE(8, 28) RSA_FLEX_CASE(8, 32) default: return -1; }
+    }
     if (L == 16) {
         switch (C) {
-#define RSA_FAST_CASE16(c) case c: launch_fast_one<16, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
-            RSA_FAST_CASE16(17) RSA_FAST_CASE16(18) RSA_FAST_CASE16(19) RSA_FAST_CASE16(20) RSA_FAST_CASE16(21) RSA_FAST_CASE16(22)
-            RSA_FAST_CASE16(23) RSA_FAST_CASE16(24) RSA_FAST_CASE16(25) RSA_FAST_CASE16(26) RSA_FAST_CASE16(27) RSA_FAST_CASE16(28)
-            RSA_FAST_CASE16(29) RSA_FAST_CASE16(30) RSA_FAST_CASE16(31) RSA_FAST_CASE16(32)
-#undef RSA_FAST_CASE16
+            RSA_FAST_CASE(16, 17) RSA_FAST_CASE(16, 18) RSA_FAST_CASE(16, 19) RSA_FAST_CASE(16, 20) RSA_FAST_CASE(16, 21)
+            RSA_FAST_CASE(16, 22) RSA_FAST_CASE(16, 23) RSA_FAST_CASE(16, 24) RSA_FAST_CASE(16, 25) RSA_FAST_CASE(16, 26)
+            RSA_FAST_CASE(16, 27) RSA_FAST_CASE(16, 28) RSA_FAST_CASE(16, 29) RSA_FAST_CASE(16, 30) RSA_FAST_CASE(16, 31)
+            RSA_FAST_CASE(16, 32)
             default: return -1;
         }
     }
     if (L == 4) {
         switch (C) {
-#define RSA_FAST_CASE4(c) case c: launch_fast_one<4, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
-            RSA_FAST_CASE4(2) RSA_FAST_CASE4(3) RSA_FAST_CASE4(4) RSA_FAST_CASE4(5) RSA_FAST_CASE4(6) RSA_FAST_CASE4(7) RSA_FAST_CASE4(8)
-            RSA_FAST_CASE4(9) RSA_FAST_CASE4(10) RSA_FAST_CASE4(11) RSA_FAST_CASE4(12) RSA_FAST_CASE4(13) RSA_FAST_CASE4(14)
-            RSA_FAST_CASE4(15) RSA_FAST_CASE4(16) RSA_FAST_CASE4(17) RSA_FAST_CASE4(18) RSA_FAST_CASE4(19) RSA_FAST_CASE4(20)
-            RSA_FAST_CASE4(21) RSA_FAST_CASE4(22) RSA_FAST_CASE4(23) RSA_FAST_CASE4(24) RSA_FAST_CASE4(25) RSA_FAST_CASE4(26)
-            RSA_FAST_CASE4(27) RSA_FAST_CASE4(28) RSA_FAST_CASE4(29) RSA_FAST_CASE4(30) RSA_FAST_CASE4(31) RSA_FAST_CASE4(32)
-            RSA_FAST_CASE4(33) RSA_FAST_CASE4(34) RSA_FAST_CASE4(35) RSA_FAST_CASE4(36) RSA_FAST_CASE4(37) RSA_FAST_CASE4(38)
-            RSA_FAST_CASE4(39) RSA_FAST_CASE4(40)
-#undef RSA_FAST_CASE4
+            RSA_FAST_CASE(4, 2) RSA_FAST_CASE(4, 3) RSA_FAST_CASE(4, 4) RSA_FAST_CASE(4, 5) RSA_FAST_CASE(4, 6) RSA_FAST_CASE(4, 7)
+            RSA_FAST_CASE(4, 8) RSA_FAST_CASE(4, 9) RSA_FAST_CASE(4, 10) RSA_FAST_CASE(4, 11) RSA_FAST_CASE(4, 12) RSA_FAST_CASE(4, 13)
+            RSA_FAST_CASE(4, 14) RSA_FAST_CASE(4, 15) RSA_FAST_CASE(4, 16) RSA_FAST_CASE(4, 17) RSA_FAST_CASE(4, 18) RSA_FAST_CASE(4, 19)
+            RSA_FAST_CASE(4, 20) RSA_FAST_CASE(4, 21) RSA_FAST_CASE(4, 22) RSA_FAST_CASE(4, 23) RSA_FAST_CASE(4, 24) RSA_FAST_CASE(4, 25)
+            RSA_FAST_CASE(4, 26) RSA_FAST_CASE(4, 27) RSA_FAST_CASE(4, 28) RSA_FAST_CASE(4, 29) RSA_FAST_CASE(4, 30) RSA_FAST_CASE(4, 31)
+            RSA_FAST_CASE(4, 32) RSA_FAST_CASE(4, 33) RSA_FAST_CASE(4, 34) RSA_FAST_CASE(4, 35) RSA_FAST_CASE(4, 36) RSA_FAST_CASE(4, 37)
+            RSA_FAST_CASE(4, 38) RSA_FAST_CASE(4, 39) RSA_FAST_CASE(4, 40)
             default: return -1;
         }
     }
     switch (C) {
-#define RSA_FAST_CASE(c) case c: launch_fast_one<8, c>(st, q, t, meta, groups, n_groups, scratch, ends, redo, redo_list, k, max_rows, tpack, tflag); return 0;
 #if RSA_FAST_L4_MAXQ < 160   // (A/B builds without 4-lane groups)
-        RSA_FAST_CASE(1) RSA_FAST_CASE(2) RSA_FAST_CASE(3) RSA_FAST_CASE(4) RSA_FAST_CASE(5) RSA_FAST_CASE(6) RSA_FAST_CASE(7)
-        RSA_FAST_CASE(8) RSA_FAST_CASE(9) RSA_FAST_CASE(10) RSA_FAST_CASE(11) RSA_FAST_CASE(12) RSA_FAST_CASE(13) RSA_FAST_CASE(14)
-        RSA_FAST_CASE(15) RSA_FAST_CASE(16) RSA_FAST_CASE(17) RSA_FAST_CASE(18) RSA_FAST_CASE(19) RSA_FAST_CASE(20)
+        RSA_FAST_CASE(8, 1) RSA_FAST_CASE(8, 2) RSA_FAST_CASE(8, 3) RSA_FAST_CASE(8, 4) RSA_FAST_CASE(8, 5) RSA_FAST_CASE(8, 6)
+        RSA_FAST_CASE(8, 7) RSA_FAST_CASE(8, 8) RSA_FAST_CASE(8, 9) RSA_FAST_CASE(8, 10) RSA_FAST_CASE(8, 11) RSA_FAST_CASE(8, 12)
+        RSA_FAST_CASE(8, 13) RSA_FAST_CASE(8, 14) RSA_FAST_CASE(8, 15) RSA_FAST_CASE(8, 16) RSA_FAST_CASE(8, 17) RSA_FAST_CASE(8, 18)
+        RSA_FAST_CASE(8, 19) RSA_FAST_CASE(8, 20)
 #endif
-        RSA_FAST_CASE(21) RSA_FAST_CASE(22) RSA_FAST_CASE(23) RSA_FAST_CASE(24) RSA_FAST_CASE(25) RSA_FAST_CASE(26)
-        RSA_FAST_CASE(27) RSA_FAST_CASE(28) RSA_FAST_CASE(29) RSA_FAST_CASE(30) RSA_FAST_CASE(31) RSA_FAST_CASE(32)
-#undef RSA_FAST_CASE
+        RSA_FAST_CASE(8, 21) RSA_FAST_CASE(8, 22) RSA_FAST_CASE(8, 23) RSA_FAST_CASE(8, 24) RSA_FAST_CASE(8, 25) RSA_FAST_CASE(8, 26)
+        RSA_FAST_CASE(8, 27) RSA_FAST_CASE(8, 28) RSA_FAST_CASE(8, 29) RSA_FAST_CASE(8, 30) RSA_FAST_CASE(8, 31) RSA_FAST_CASE(8, 32)
         default: return -1;
     }
+#undef RSA_FAST_CASE
+#undef RSA_FLEX_CASE
+#undef RSA_FAST_ARGS
 }
 
 inline void launch_exact_redo(cudaStream_t st, const uint8_t* q, const uint8_t* t, const PairMeta* meta,
