@@ -20,6 +20,7 @@
 #include <memory>
 #include <atomic>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -47,6 +48,19 @@ struct Worker {
 };
 
 Worker g_workers[THREAD_NUM_MAX];
+
+// RSA_EXT_STATS=1: where the time of the calls went, summed over the workers, printed at exit (diagnostics)
+struct VeneerStats {
+    std::atomic<long long> calls{0}, pairs{0}, ns_gather{0}, ns_submit{0}, ns_wait{0}, ns_unpack{0}, ns_max_call{0};
+    const bool on = getenv("RSA_EXT_STATS") != nullptr;
+    ~VeneerStats() {
+        if (!on || !calls.load()) return;
+        fprintf(stderr, "[rsa_ext veneer] %lld calls, %lld pairs; summed over workers: gather %.1f ms, submit %.1f ms, wait %.1f ms, "
+                        "unpack %.1f ms; longest call %.1f ms\n", calls.load(), pairs.load(), ns_gather.load() / 1e6, ns_submit.load() / 1e6,
+                ns_wait.load() / 1e6, ns_unpack.load() / 1e6, ns_max_call.load() / 1e6);
+    }
+} g_vstats;
+inline long long now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 std::mutex g_create_mutex;
 
 [[noreturn]] void die(const char *what, rsa_ext_t *h) {
@@ -81,7 +95,10 @@ int usable_devices() {
 // creates its handle the ordinary way.  A failure here is not reported -- the first real call reports it.
 constexpr int kDefaultScores[4] = {2, 8, 12, 1};  // src/cmdline.hpp:46-50 / the prototype's default arguments
 constexpr int kPoolReadLen = 250, kPoolWindowLen = 500;  // shapes the pooled handles are pre-sized for
-constexpr int kPoolPairs = STREAM_BATCH_SIZE < 8192 ? STREAM_BATCH_SIZE : 8192;  // (whole-chunk builds raise the macro)
+// (whole-chunk builds raise the macro: a chunk of 10 000 reads sends 5-20 k pairs; a pool sized for 8192 made every worker
+// regrow its pinned staging and device buffers inside its first calls -- cudaHostAlloc / cudaMalloc under the driver lock,
+// 0.1-0.2 s each with 16 workers, tools/r2_call30.sh)
+constexpr int kPoolPairs = STREAM_BATCH_SIZE < 8192 ? STREAM_BATCH_SIZE : 24576;
 
 struct Warmup {
     std::thread t;
@@ -246,6 +263,7 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
     gasal_results.resize(n);
     if (n == 0) return;
 
+    const long long t0 = now_ns();
     w.qp.resize(n); w.tp.resize(n); w.ql.resize(n); w.tl.resize(n); w.res.resize(n);
     for (size_t i = 0; i < n; ++i) {
         w.qp[i] = query_seqs[i].data(); w.ql[i] = (int32_t)query_seqs[i].size();
@@ -260,13 +278,23 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
     w.aln.resize(n);
     if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
 #endif
+    const long long t1 = now_ns();
     int rc = rsa_ext_submit_ptrs(w.h, (int64_t)n, w.qp.data(), w.ql.data(), w.tp.data(), w.tl.data(), w.res.data());
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
     if (rc != RSA_EXT_OK) die("rsa_ext_submit_ptrs", w.h);
+    const long long t2 = now_ns();
     rc = rsa_ext_wait(w.h);
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);  // (large batches are validated chunk by chunk)
     if (rc != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    const long long t3 = now_ns();
     unpack_results(w, n, gasal_results, text_free, end_bonus);
+    if (g_vstats.on) {
+        const long long t4 = now_ns();
+        g_vstats.calls++; g_vstats.pairs += (long long)n;
+        g_vstats.ns_gather += t1 - t0; g_vstats.ns_submit += t2 - t1; g_vstats.ns_wait += t3 - t2; g_vstats.ns_unpack += t4 - t3;
+        long long mx = g_vstats.ns_max_call.load();
+        while (t4 - t0 > mx && !g_vstats.ns_max_call.compare_exchange_weak(mx, t4 - t0)) {}
+    }
 }
 
 #ifdef RSA_EXT_WINDOWS

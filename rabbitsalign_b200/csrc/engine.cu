@@ -421,7 +421,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
         if (ql > 0 && tl > 0 && tl <= in.max_tlen) {
             need = (uint64_t)tl * LT.exact_row_bytes_[ql] + 16;
             if (fast_shape_ok((int)ql, (int)tl, in.match))  // a lone pair owns a whole group
-                need = std::max<uint64_t>(need, (uint64_t)((tl + 3) & ~3) * LT.fast_row_bytes[ql]);
+                need = std::max<uint64_t>(need, (uint64_t)fast_tile_rows((int)tl) * LT.fast_row_bytes[ql]);
         }
         if (hi > lo && (scratch + need > in.scratch_cap || in.qoff[hi + 1] - q0 > kMaxChunkSeqBytes ||
                         (!in.win_off && in.toff[hi + 1] - t0 > kMaxChunkSeqBytes)))
@@ -550,7 +550,7 @@ int plan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, std
             groups[n_groups++] = fg;
             diroff[a] = sc_off;
             if (b != a) { diroff[b] = sc_off; info[b] |= 1u; }
-            sc_off += (uint64_t)((rows + 3) & ~3u) * LT.fast_row_bytes[ql];
+            sc_off += (uint64_t)fast_tile_rows((int)rows) * LT.fast_row_bytes[ql];
             plan.fast.back().max_tlen = std::max<int>(plan.fast.back().max_tlen, (int)rows);
             plan.n_fast_pairs += (b != a) ? 2 : 1;
         }
@@ -687,6 +687,9 @@ int scan_chunk(rsa_ext* h, const PlanInput& in, int64_t lo, ChunkPlan& plan, Pla
                 nmx = std::max(c_mx, t4);
                 add2 = (uint64_t)c_rowb * (t4 + 3ull * (nmx - c_mx) + (c_mn - nmn));
             }
+            // tiles are whole 8-row units: up to 4 rows more than ceil4 per GROUP, i.e. per two pairs (a lone pair owns a
+            // group): 4 per pair in these doubled units, 8 for the first pair of a length
+            add2 += (uint64_t)c_rowb * (c_cnt == 0 ? 8u : 4u);
             if (scratch2 + add2 > cap2 && hi > lo) break;
             scratch2 += add2;
             ++c_cnt; c_mn = nmn; c_mx = nmx;
@@ -1575,7 +1578,7 @@ extern "C" int rsa_ext_reserve(rsa_ext_t* h, int64_t n, int32_t qlen, int32_t tl
     std::lock_guard<std::mutex> cold(g_cold_mutex);
     const LenTables& LT = len_tables();
     uint64_t per_pair = (uint64_t)tlen * LT.exact_row_bytes_[qlen] + 16;  // same rule as the chunk budget (plan_chunk)
-    if (fast_shape_ok(qlen, tlen, h->sc.match)) per_pair = std::max<uint64_t>(per_pair, (uint64_t)((tlen + 3) & ~3) * LT.fast_row_bytes[qlen]);
+    if (fast_shape_ok(qlen, tlen, h->sc.match)) per_pair = std::max<uint64_t>(per_pair, (uint64_t)fast_tile_rows(tlen) * LT.fast_row_bytes[qlen]);
     ChunkPlan p;
     const size_t blob = blob_layout(p, n);
     const SlotNeed need{blob, (size_t)n * qlen + 16, (size_t)n * tlen + 16, sizeof(DpEnd) * (size_t)n,

@@ -5,14 +5,17 @@
 // with C = ceil(qlen/L), the first `rem` lanes own C columns and the remaining lanes own C-1, so that
 // every owned column is a real query base (no padding columns exist).
 //
-// Direction scratch of a group: for target row r, lane l, word w (w = column-in-lane / 4):
-//     uint32 index = (((r>>2)*L + l)*W + w)*4 + (r&3),   W = ceil(C/4) rounded up to an even number
-// i.e. 16-byte chunks holding a 4-row x 4-column cell tile (both pairs); the chunks of one lane and row block are
-// contiguous and two of them (4 rows x 8 columns) fill one 32-byte sector, which the DP kernel writes with ONE 256-bit
-// store per thread (never a partial sector: partial sectors are read-modify-written by the L2), and in which the
-// traceback, which moves diagonally, finds the next ~4 path cells of a row block.  (Round 1 ordered the chunks
-// [row block][word][lane]: a sector then held the same word of two neighbouring LANES, i.e. columns C apart, and every
-// 16-byte chunk the traceback touched cost a 32-64 byte HBM access of which half was useless: 6.2 KB read per pair.)
+// Direction scratch of a group: 16-byte chunks holding a 4-row x 4-column cell tile (both pairs).  Two chunks of one lane
+// side by side (4 rows x 8 columns) fill one 32-byte SECTOR, which the DP kernel writes with ONE 256-bit store per thread
+// (never a partial sector: partial sectors are read-modify-written by the L2); the sectors of two consecutive row blocks
+// sit side by side in one 64-byte UNIT (8 rows x 8 columns of one lane), the granularity of an HBM access, in which the
+// traceback, which moves diagonally, finds the next ~8 path cells.  For target row r, lane l, word w (w = column-in-lane / 4),
+// with W = ceil(C/4) rounded up to an even number and rows padded to a multiple of 8:
+//     unit   = ((r>>3)*L + l)*(W/2) + (w>>1)
+//     uint32 index = ((unit*2 + ((r>>2)&1))*2 + (w&1))*4 + (r&3)
+// (Round 1 ordered the chunks [row block][word][lane]: a sector then held the same word of two neighbouring LANES, i.e.
+// columns C apart, and every 16-byte chunk the traceback touched cost a 64-byte HBM access of which three quarters were
+// useless: 6.2 KB read per pair; [row block][lane][word] brought 3.7 KB.)
 // low half = pair A, high half = pair B; nibble k = (column-in-lane & 3) sits at bits [4k,4k+4) of its half:
 //     bit3 F of the next column NOT opened from the diagonal (extended; = reference bit3)
 //     bit2 E of the next row NOT opened from the diagonal (= reference bit2)
@@ -48,9 +51,12 @@ __host__ __device__ inline FastGeom fast_geom(int qlen) {
     return g;
 }
 
+// rows of a group's tile: whole 8-row units
+__host__ __device__ inline int fast_tile_rows(int rows) { return (rows + 7) & ~7; }
+
 // bytes of direction scratch of one group (two pairs) with `rows` target rows
 __host__ __device__ inline uint64_t fast_dir_bytes(const FastGeom& g, int rows) {
-    return (uint64_t)((rows + 3) & ~3) * g.L * g.W * 4u;
+    return (uint64_t)fast_tile_rows(rows) * g.L * g.W * 4u;
 }
 
 // first column owned by lane l
@@ -64,7 +70,7 @@ __device__ __forceinline__ uint32_t fast_fetch_flags(const FastGeom& g, const ui
     const int wide = g.rem * g.C;
     if (j < wide) { lane = j / g.C; cc = j - lane * g.C; }
     else { const int jj = j - wide; const int k = jj / (g.C - 1); lane = g.rem + k; cc = jj - k * (g.C - 1); }
-    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((size_t)(i >> 2) * g.L + lane) * g.W + (cc >> 2)) << 2) + (i & 3)];
+    const uint32_t word = reinterpret_cast<const uint32_t*>(dir)[((((((size_t)(i >> 3) * g.L + lane) * (g.W >> 1) + (cc >> 3)) * 2 + ((i >> 2) & 1)) * 2 + ((cc >> 2) & 1)) << 2) + (i & 3)];
     const uint32_t h16 = half ? (word >> 16) : (word & 0xFFFFu);
     return (h16 >> (4 * (cc & 3))) & 0xFu;
 }

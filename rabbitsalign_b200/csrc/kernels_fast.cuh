@@ -238,11 +238,13 @@ struct FastDp {
             // De-skewed, row-blocked store: lane gl computed row r at step r+gl and parked its words in ring slot
             // (r+gl)&(RS-1).  When the group's LAST lane has finished the last row of a 4-row block (step = 4b+3+L-1),
             // every lane stores ITS OWN words of rows 4b..4b+3, two words (4 rows x 8 columns, both pairs) per 256-bit
-            // store = one full 32-byte sector; a lane's words of a row block are contiguous (fast_layout.cuh).
+            // store = one full 32-byte sector; the sectors of row blocks 2u and 2u+1 alternate in memory (64-byte units of
+            // 8 rows x 8 columns, fast_layout.cuh).
             const int rl = s - (L - 1);                   // row the last lane finished in this step
             if (rl >= 0 && (rl & 3) == 3 && rl - 3 < rows) {
                 const int rb = rl >> 2;
-                uint4* dblk = reinterpret_cast<uint4*>(dir) + ((size_t)rb * L + gl) * nw2g;
+                // sector of words (wv, wv + 1) of this lane and row block: unit ((rb >> 1) * L + gl) * (W / 2) + wv / 2, half rb & 1
+                uint4* dblk = reinterpret_cast<uint4*>(dir) + (((size_t)(rb >> 1) * L + gl) * nw2g + (rb & 1)) * 2;
                 const uint32_t* r0 = ring + ((((rl - 3 + gl) & (RS - 1)) * NW) << 5) + lane;
                 const uint32_t* r1 = ring + ((((rl - 2 + gl) & (RS - 1)) * NW) << 5) + lane;
                 const uint32_t* r2 = ring + ((((rl - 1 + gl) & (RS - 1)) * NW) << 5) + lane;
@@ -254,7 +256,7 @@ struct FastDp {
                     v.x = r0[wv << 5]; v.y = r1[wv << 5]; v.z = r2[wv << 5]; v.w = r3[wv << 5];
                     if (wv + 1 < NW) { w.x = r0[(wv + 1) << 5]; w.y = r1[(wv + 1) << 5]; w.z = r2[(wv + 1) << 5]; w.w = r3[(wv + 1) << 5]; }
                     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                                 :: "l"(dblk + wv), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+                                 :: "l"(dblk + 2 * wv), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 }
             }
         }
