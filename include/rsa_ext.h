@@ -182,7 +182,8 @@ int rsa_ext_request_alninfo(rsa_ext_t *h, rsa_ext_alninfo_t *out, int32_t end_bo
  * read's length, before deciding to run Smith-Waterman: hamming_distance (src/aligner.hpp:54-67), the test
  * (float) distance / |query| < 0.05 (src/aln.cpp:395) and, if it holds, hamming_align (src/aligner.cpp:254-302, with
  * highest_scoring_segment :219-252).  Blocking call, one warp per pair.
- * hamming[i]: the distance, -1 for windows of another length than the read.
+ * hamming[i]: the distance, -1 for windows of another length than the read (and for reads longer than 512 bases, which
+ * the engine does not extend either: status 1).
  * out[i].status: 0 the shortcut applies and the record is hamming_align's AlignmentInfo (ref_start/ref_end relative to
  * the window); 1 the pair needs the gapped path (submit it); 3 more than RSA_EXT_CIGAR_INLINE runs (host path).
  * Scores are the handle's; end_bonus is strobealign's -L. */

@@ -79,6 +79,9 @@ int rsa_sam_format(rsa_sam_t *h, int64_t n, const rsa_sam_record_t *records, con
                    const uint32_t *cigar_pool, int64_t n_cigar_ops, char *out, int64_t out_cap, int64_t *out_len,
                    int64_t *line_off);
 
+/* Device time of the kernels of the last rsa_sam_format (CUDA events: length + scan kernels, writer). */
+double rsa_sam_kernel_ms(const rsa_sam_t *h);
+
 /* Sam::add (src/sam.cpp:117-139): one aligned single-end record. */
 void rsa_sam_single(const rsa_sam_alignment_t *a, const rsa_sam_read_t *read, uint32_t mapq, int32_t is_primary,
                     const uint32_t details[5], rsa_sam_record_t *out);

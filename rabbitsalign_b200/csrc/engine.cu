@@ -220,6 +220,7 @@ struct rsa_ext {
     std::vector<int64_t> own_qoff, own_toff;
 
     DevBuf ham_q, ham_t, ham_off, ham_out;  // rsa_ext_hamming_* staging
+    cudaEvent_t ham_ev[2] = {nullptr, nullptr};
 
     // resident set
     std::vector<ResidentChunk> res_chunks;
@@ -1394,6 +1395,7 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     h->ref.reset();
     for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs, &h->ham_q, &h->ham_t, &h->ham_off, &h->ham_out})
         if (b->p) cudaFree(b->p);
+    for (cudaEvent_t ev : h->ham_ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
     if (h->own_q.p) cudaFreeHost(h->own_q.p);
     if (h->own_t.p) cudaFreeHost(h->own_t.p);
@@ -1539,16 +1541,26 @@ int hamming_core(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
         CU_TRY(h, cudaMemcpyAsync(h->ham_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(d_toff, toff, offb, cudaMemcpyHostToDevice, st));
     }
-    const int blocks = (int)std::min<int64_t>((n + kHamWarpsPerBlock - 1) / kHamWarpsPerBlock, (int64_t)h->n_sms * 16);
+    const int64_t ham_rounds = (n + 31) / 32;   // a warp takes 32 pairs per round
+    const int blocks = (int)std::min<int64_t>((ham_rounds + kHamWarpsPerBlock - 1) / kHamWarpsPerBlock, (int64_t)h->n_sms * 16);
+    for (cudaEvent_t& ev : h->ham_ev)
+        if (!ev) CU_TRY(h, cudaEventCreate(&ev));
+    CU_TRY(h, cudaEventRecord(h->ham_ev[0], st));
     // the uploaded sequence slices start at the first pair's offset: rebase the pointers instead of the offsets
     hamming_kernel<<<blocks, 32 * kHamWarpsPerBlock, 0, st>>>(
         h->ham_q.p - qoff[0], d_qoff, win_off ? h->ref->d : h->ham_t.p - toff[0], win_off ? nullptr : d_toff,
         win_off ? d_toff : nullptr, (long long)n, h->sc.match, h->sc.mismatch, end_bonus, d_ham, d_out);
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ham_ev[1], st));
     CU_TRY(h, cudaMemcpyAsync(out, d_out, sizeof(rsa_ext_alninfo_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaMemcpyAsync(hamming, d_ham, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaStreamSynchronize(st));
+    h->stats = rsa_ext_stats_t{};
     h->stats.kernel_launches = 1;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ham_ev[0], h->ham_ev[1]) == cudaSuccess) h->stats.dp_ms = ms;   // the Hamming kernel
+    h->stats.h2d_bytes = (int64_t)(qbytes + tbytes + (win_off ? sizeof(int64_t) * (size_t)n + offb : 2 * offb));
+    h->stats.d2h_bytes = (int64_t)((sizeof(rsa_ext_alninfo_t) + sizeof(int32_t)) * (size_t)n);
     return RSA_EXT_OK;
 }
 }  // namespace

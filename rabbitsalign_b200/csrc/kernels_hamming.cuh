@@ -6,10 +6,10 @@
 //   (float) distance / |query| < 0.05  ?                   src/aln.cpp:395
 //   hamming_align(query, window, match, mismatch, bonus)   src/aligner.cpp:254-302
 //     highest_scoring_segment                              src/aligner.cpp:219-252  (Kadane scan, end bonus at both ends)
-// and the pair never reaches the GPU.  Here: one warp per pair.  The 32 lanes compare 32 bases per step with coalesced
-// byte loads and a ballot turns every step into one word of a mismatch bit mask; the distance is a popcount; the
-// sequential segment scan and the '=' / 'X' run encoding then run over the bit mask in registers (lane 0), which is
-// where the reference's tie rules live (strict '>' keeps the FIRST best segment, a negative running score restarts the
+// and the pair never reaches the GPU.  Here: a warp takes 32 pairs per round.  For each pair in turn the 32 lanes compare 32
+// bases per step with coalesced byte loads and a ballot turns every step into one word of that pair's mismatch bit mask
+// (shared memory); then every lane takes one pair: the distance is a popcount, the sequential segment scan and the
+// '=' / 'X' run encoding run over the lane's own bit mask, which is where the reference's tie rules live (strict '>' keeps the FIRST best segment, a negative running score restarts the
 // segment behind the current base, the end bonus counts once per reached read end).
 // Output: rsa_ext_alninfo_t (= AlignmentInfo, BAM-style ops) with status 0 when the shortcut applies, 1 when the pair
 // needs the gapped path (distance too high, unequal lengths, empty read), 3 when the run list does not fit
@@ -21,44 +21,59 @@
 namespace rsa {
 
 constexpr int kHamWarpsPerBlock = 4;
-constexpr int kHamMaxWords = 64;   // reads up to 2048 bases
+constexpr int kHamMaxWords = 16;   // reads up to 512 bases (the engine's packed limit; longer reads take the gapped path)
 
+// A warp takes 32 pairs per round.  Stage A, cooperative: for each of the 32 pairs in turn the lanes compare 32 bases per
+// step (coalesced byte loads) and a ballot makes one word of that pair's mismatch bit mask (shared memory, [pair][word]).
+// Stage B, one lane per pair: distance test, segment scan and run encoding over the lane's own bit mask.
 __global__ void __launch_bounds__(32 * kHamWarpsPerBlock)
 hamming_kernel(const uint8_t* __restrict__ qbuf, const int64_t* __restrict__ qoff, const uint8_t* __restrict__ tbuf,
                const int64_t* __restrict__ toff, const int64_t* __restrict__ win_off, long long n, int match, int mismatch,
                int end_bonus, int32_t* __restrict__ hamming, rsa_ext_alninfo_t* __restrict__ out) {
-    __shared__ uint32_t s_mask[kHamWarpsPerBlock][kHamMaxWords];
+    __shared__ uint32_t s_mask[kHamWarpsPerBlock][32][kHamMaxWords + 1];   // (+1: lanes walk their own rows, no bank conflicts)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* mask = s_mask[warp];
-    for (long long pi = (long long)blockIdx.x * kHamWarpsPerBlock + warp; pi < n; pi += (long long)gridDim.x * kHamWarpsPerBlock) {
-        const long long q0 = qoff[pi];
-        const int len = (int)(qoff[pi + 1] - q0);
-        long long t0;
-        int tlen;
-        if (win_off) { t0 = win_off[pi]; tlen = len; }
-        else { t0 = toff[pi]; tlen = (int)(toff[pi + 1] - t0); }
+    const long long rounds = (n + 31) / 32;
+    for (long long rd = (long long)blockIdx.x * kHamWarpsPerBlock + warp; rd < rounds; rd += (long long)gridDim.x * kHamWarpsPerBlock) {
+        const long long pi = rd * 32 + lane;     // this lane's pair in stage B
+        long long q0 = 0, t0 = 0;
+        int len = 0, tlen = -1;
+        if (pi < n) {
+            q0 = qoff[pi];
+            len = (int)(qoff[pi + 1] - q0);
+            if (win_off) { t0 = win_off[pi]; tlen = len; }
+            else { t0 = toff[pi]; tlen = (int)(toff[pi + 1] - t0); }
+        }
+        const bool comparable = pi < n && tlen == len && len <= kHamMaxWords * 32;
+        __syncwarp();
+        // ---- stage A
+        for (int p = 0; p < 32; ++p) {
+            const int plen = __shfl_sync(0xFFFFFFFFu, comparable ? len : 0, p);
+            if (plen == 0) continue;   // (uniform)
+            const uint8_t* q = qbuf + __shfl_sync(0xFFFFFFFFu, q0, p);
+            const uint8_t* t = tbuf + __shfl_sync(0xFFFFFFFFu, t0, p);
+            for (int b = 0; b < plen; b += 32) {
+                const int i = b + lane;
+                const bool mis = i < plen && q[i] != t[i];
+                const uint32_t w = __ballot_sync(0xFFFFFFFFu, mis);
+                if (lane == 0) s_mask[warp][p][b >> 5] = w;
+            }
+        }
+        __syncwarp();
+        // ---- stage B
+        if (pi >= n) continue;
+        const uint32_t* mask = s_mask[warp][lane];
         rsa_ext_alninfo_t a;
         a.sw_score = 0; a.edit_distance = 0; a.ref_start = 0; a.ref_end = 0; a.query_start = 0; a.query_end = 0;
         a.n_cigar = 0; a.status = 1;
 #pragma unroll
         for (int k = 0; k < RSA_EXT_CIGAR_INLINE; ++k) a.cigar[k] = 0;
         int hd = -1;
-        if (tlen == len && len <= kHamMaxWords * 32) {
-            const uint8_t* q = qbuf + q0;
-            const uint8_t* t = tbuf + t0;
+        if (comparable) {
             hd = 0;
-            __syncwarp();
-            for (int b = 0; b < len; b += 32) {
-                const int i = b + lane;
-                const bool mis = i < len && q[i] != t[i];
-                const uint32_t w = __ballot_sync(0xFFFFFFFFu, mis);
-                hd += __popc(w);
-                if (lane == 0) mask[b >> 5] = w;
-            }
-            __syncwarp();
+            for (int w = 0; w < (len + 31) >> 5; ++w) hd += __popc(mask[w]);
             // (float) hamming_dist / query.size() < 0.05 : float division, compared as double (src/aln.cpp:395)
             const bool pass = len > 0 && (double)((float)hd / (float)len) < 0.05;
-            if (pass && lane == 0) {
+            if (pass) {
                 // highest_scoring_segment (src/aligner.cpp:219-252)
                 int start = 0, score = end_bonus, best_start = 0, best_end = 0, best = 0;
                 for (int i = 0; i < len; ++i) {
@@ -95,10 +110,8 @@ hamming_kernel(const uint8_t* __restrict__ qbuf, const int64_t* __restrict__ qof
                 }
             }
         }
-        if (lane == 0) {
-            hamming[pi] = hd;
-            out[pi] = a;
-        }
+        hamming[pi] = hd;
+        out[pi] = a;
     }
 }
 

@@ -266,6 +266,8 @@ struct rsa_sam {
     char* d_names = nullptr;
     long long* d_names_off = nullptr;
     cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // around the length + scan kernels, around the writer
+    double kernel_ms = 0;
     Buf rec, text, cig, len, off, sums, out;
     std::string err;
 };
@@ -287,6 +289,8 @@ static int grow(rsa_sam* h, Buf& b, size_t need) {
     b.cap = cap;
     return RSA_EXT_OK;
 }
+
+extern "C" double rsa_sam_kernel_ms(const rsa_sam_t* h) { return h ? h->kernel_ms : 0.0; }
 
 extern "C" const char* rsa_sam_last_error(const rsa_sam_t* h) { return h ? h->err.c_str() : g_sam_create_error.c_str(); }
 
@@ -310,6 +314,8 @@ extern "C" int rsa_sam_create(int32_t device, int32_t n_refs, const char* names_
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (cudaEvent_t* ev : {&h->ev0, &h->ev1, &h->ev2, &h->ev3})
+        if ((e = cudaEventCreate(ev)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t nb = n_refs ? (size_t)names_off[n_refs] : 0;
     if ((e = cudaMalloc(&h->d_names, nb + 16)) != cudaSuccess) return fail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_names_off, sizeof(long long) * (size_t)(n_refs + 1))) != cudaSuccess) return fail("cudaMalloc", e);
@@ -327,6 +333,7 @@ extern "C" void rsa_sam_destroy(rsa_sam_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
+    for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev2, h->ev3}) if (ev) cudaEventDestroy(ev);
     for (Buf* b : {&h->rec, &h->text, &h->cig, &h->len, &h->off, &h->sums, &h->out}) if (b->p) cudaFree(b->p);
     if (h->d_names) cudaFree(h->d_names);
     if (h->d_names_off) cudaFree(h->d_names_off);
@@ -366,11 +373,14 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
     unsigned long long* d_len = (unsigned long long*)h->len.p;
     unsigned long long* d_off = (unsigned long long*)h->off.p;
     unsigned long long* d_sums = (unsigned long long*)h->sums.p;
+    h->kernel_ms = 0;
+    SAM_TRY(h, cudaEventRecord(h->ev0, st));
     sam_length_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)h->text.p, (const uint32_t*)h->cig.p, d_len);
     scan_block_sums<<<nb, kScanThreads, 0, st>>>(d_len, (long long)n, d_sums);
     scan_of_sums<<<1, 1, 0, st>>>(d_sums, nb, d_sums + nb);
     scan_apply<<<nb, kScanThreads, 0, st>>>(d_len, (long long)n, d_sums, d_off);
     SAM_TRY(h, cudaGetLastError());
+    SAM_TRY(h, cudaEventRecord(h->ev1, st));
     unsigned long long total = 0;
     SAM_TRY(h, cudaMemcpyAsync(&total, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, st));
     SAM_TRY(h, cudaStreamSynchronize(st));
@@ -390,11 +400,17 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const long long want = (n + kSamWarps - 1) / kSamWarps;
         const int blocks = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+        SAM_TRY(h, cudaEventRecord(h->ev2, st));
         sam_write_kernel<<<blocks, 32 * kSamWarps, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)h->text.p, (const uint32_t*)h->cig.p, d_off, (char*)h->out.p);
         SAM_TRY(h, cudaGetLastError());
+        SAM_TRY(h, cudaEventRecord(h->ev3, st));
         SAM_TRY(h, cudaMemcpyAsync(out, h->out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     }
     SAM_TRY(h, cudaStreamSynchronize(st));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, h->ev0, h->ev1);                 // length + scan kernels
+    if (total) cudaEventElapsedTime(&b, h->ev2, h->ev3);      // writer
+    h->kernel_ms = (double)a + (double)b;
     return RSA_EXT_OK;
 }
 

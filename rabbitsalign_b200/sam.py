@@ -21,7 +21,7 @@ READ_DTYPE = np.dtype([("name_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u
                        ("seq_len", "<u4"), ("qual_len", "<u4")], align=True)
 assert READ_DTYPE.itemsize == 40
 
-SAM_ABI_SYMBOLS = ["rsa_sam_create", "rsa_sam_destroy", "rsa_sam_last_error", "rsa_sam_format", "rsa_sam_single",
+SAM_ABI_SYMBOLS = ["rsa_sam_create", "rsa_sam_destroy", "rsa_sam_last_error", "rsa_sam_format", "rsa_sam_kernel_ms", "rsa_sam_single",
                    "rsa_sam_pair", "rsa_sam_unmapped"]
 
 KIND_ALIGNED, KIND_UNMAPPED, KIND_UNMAPPED_MATE = 0, 1, 2
@@ -42,6 +42,8 @@ def _lib():
         lib.rsa_sam_last_error.restype = C.c_char_p
         lib.rsa_sam_format.argtypes = [vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp]
         lib.rsa_sam_format.restype = C.c_int
+        lib.rsa_sam_kernel_ms.argtypes = [vp]
+        lib.rsa_sam_kernel_ms.restype = C.c_double
         lib.rsa_sam_single.argtypes = [vp, vp, u32, i32, vp, vp]
         lib.rsa_sam_single.restype = None
         lib.rsa_sam_pair.argtypes = [vp, vp, vp, vp, u32, u32, i32, i32, vp, vp, vp]
@@ -70,6 +72,9 @@ class SamFormatter:
             raise ExtensionError(rc, self.lib.rsa_sam_last_error(None).decode())
         self.h = h
 
+    def kernel_ms(self) -> float:
+        return float(self.lib.rsa_sam_kernel_ms(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.rsa_sam_destroy(self.h)
@@ -81,21 +86,26 @@ class SamFormatter:
         except Exception:
             pass
 
-    def format(self, records: np.ndarray, text_pool: np.ndarray, cigar_pool: np.ndarray, want_offsets: bool = False):
-        """Returns the SAM text of the records (bytes), optionally with the n + 1 line offsets."""
+    def format(self, records: np.ndarray, text_pool: np.ndarray, cigar_pool: np.ndarray, want_offsets: bool = False,
+               out: Optional[np.ndarray] = None):
+        """Returns the SAM text of the records (bytes), optionally with the n + 1 line offsets.  `out`: a caller-owned
+        uint8 buffer (e.g. pinned) to receive the text; the return value is then a view of it instead of a copy."""
         n = len(records)
         records = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
         cigar_pool = np.ascontiguousarray(cigar_pool, dtype=np.uint32)
-        cap = int(records["name_len"].sum() + records["seq_len"].sum() + records["qual_len"].sum()) + 160 * n + 12 * len(cigar_pool) + 64
-        out = np.zeros(cap, np.uint8)
+        if out is None:
+            cap = int(records["name_len"].sum() + records["seq_len"].sum() + records["qual_len"].sum()) + 160 * n + 12 * len(cigar_pool) + 64
+            buf = np.empty(cap, np.uint8)
+        else:
+            buf, cap = out, len(out)
         out_len = C.c_int64(0)
         offs = np.zeros(n + 1, np.int64) if want_offsets else None
         rc = self.lib.rsa_sam_format(self.h, n, records.ctypes.data, text_pool.ctypes.data, len(text_pool),
-                                     cigar_pool.ctypes.data if len(cigar_pool) else None, len(cigar_pool), out.ctypes.data, cap,
+                                     cigar_pool.ctypes.data if len(cigar_pool) else None, len(cigar_pool), buf.ctypes.data, cap,
                                      C.byref(out_len), offs.ctypes.data if want_offsets else None)
         if rc != 0:
             raise ExtensionError(rc, self.lib.rsa_sam_last_error(self.h).decode())
-        text = out[:out_len.value].tobytes()
+        text = buf[:out_len.value] if out is not None else buf[:out_len.value].tobytes()
         return (text, offs) if want_offsets else text
 
 
