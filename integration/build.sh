@@ -167,6 +167,40 @@ $CXX -o "$OUT/rabbitsalign_b200_gpuseed" $SEEDOBJS "$OUT/obj_seed/seed_glue.o" "
 SEEDFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_seed/pc_fx.o";; aln) echo "$OUT/obj_seed/aln.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
 $CXX -o "$OUT/rabbitsalign_fx_b200_gpuseed" $SEEDFXOBJS $FXIO "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
      -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# ---- Hamming-on-device build (caller half): the GPU seeding build + patch_hamming.py: the
+#      Hamming shortcut of extend_seed_part is decided for a whole chunk in one rsa_ext_hamming_ref_windows call (windows read
+#      from the genome resident in HBM); candidates that fail the 5 % test join the chunk's Smith-Waterman batch as before.
+mkdir -p "$OUT/ham" "$OUT/obj_ham"
+python3 "$HERE/patch_hamming.py" "$OUT/seed/aln.cpp" "$OUT/ham/aln.cpp" "$OUT/seed/pc.cpp" "$OUT/ham/pc.cpp"
+pids=()
+( $CXX $WINFLAGS -c "$OUT/ham/aln.cpp" -o "$OUT/obj_ham/aln.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$OUT/ham/pc.cpp" -o "$OUT/obj_ham/pc.o" ) & pids+=($!)
+( $CXX $WINFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$OUT/ham/pc.cpp" -o "$OUT/obj_ham/pc_fx.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$HERE/hamming_glue.cpp" -o "$OUT/obj_ham/hamming_glue.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+HAMOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_ham/pc.o";; aln) echo "$OUT/obj_ham/aln.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_gpuham" $HAMOBJS "$OUT/obj_ham/hamming_glue.o" "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+HAMFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_ham/pc_fx.o";; aln) echo "$OUT/obj_ham/aln.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_gpuham" $HAMFXOBJS $FXIO "$OUT/obj_ham/hamming_glue.o" "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+# ---- SAM-from-the-device build (caller half): the Hamming build + patch_sam.py: the three
+#      text-appending members of class Sam hand their arguments to a per-chunk collector, one rsa_sam_format call per chunk
+#      writes the text.  With this build every step between FASTQ parsing and SAM bytes that touches bases runs on the GPU.
+mkdir -p "$OUT/sam" "$OUT/obj_sam"
+python3 "$HERE/patch_sam.py" "$REF_ROOT/src/sam.cpp" "$OUT/sam/sam.cpp" "$OUT/ham/pc.cpp" "$OUT/sam/pc.cpp"
+pids=()
+( $CXX $WINFLAGS -c "$OUT/sam/sam.cpp" -o "$OUT/obj_sam/sam.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$OUT/sam/pc.cpp" -o "$OUT/obj_sam/pc.o" ) & pids+=($!)
+( $CXX $WINFLAGS -DRABBIT_FX -DOPT_NUMA_CLOSE -DVERB -include cstdint -I"$REF_ROOT/RabbitFX/io" -c "$OUT/sam/pc.cpp" -o "$OUT/obj_sam/pc_fx.o" ) & pids+=($!)
+( $CXX $WINFLAGS -c "$HERE/sam_glue.cpp" -o "$OUT/obj_sam/sam_glue.o" ) & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+SAMOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_sam/pc.o";; sam) echo "$OUT/obj_sam/sam.o";; aln) echo "$OUT/obj_ham/aln.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_b200_gpusam" $SAMOBJS "$OUT/obj_sam/sam_glue.o" "$OUT/obj_ham/hamming_glue.o" "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
+SAMFXOBJS=$(for s in $SRCS ssw_cpp ssw xxhash; do case $s in pc) echo "$OUT/obj_sam/pc_fx.o";; sam) echo "$OUT/obj_sam/sam.o";; aln) echo "$OUT/obj_ham/aln.o";; main) echo "$OUT/obj_fx/main.o";; aligner|ssw_cpp) echo "$OUT/obj_aln/$s.o";; *) echo "$OUT/obj/$s.o";; esac; done)
+$CXX -o "$OUT/rabbitsalign_fx_b200_gpusam" $SAMFXOBJS $FXIO "$OUT/obj_sam/sam_glue.o" "$OUT/obj_ham/hamming_glue.o" "$OUT/obj_seed/seed_glue.o" "$OUT/obj_win/veneer.o" -L"$ROOT/rabbitsalign_b200" -lrsa_ext \
+     -Wl,-rpath,'$ORIGIN/../../rabbitsalign_b200' -lz -lpthread
 # ---- profiling builds: the reference's own per-phase timers (time1 seeding loop, time2_1..4 extension phases, time3_1..2
 #      SAM + output; their summary fprintf is commented out in src/pc.cpp:806-809 and siblings) switched back on
 mkdir -p "$OUT/timed"

@@ -52,12 +52,19 @@ Worker g_workers[THREAD_NUM_MAX];
 // RSA_EXT_STATS=1: where the time of the calls went, summed over the workers, printed at exit (diagnostics)
 struct VeneerStats {
     std::atomic<long long> calls{0}, pairs{0}, ns_gather{0}, ns_submit{0}, ns_wait{0}, ns_unpack{0}, ns_max_call{0};
+    std::atomic<long long> ham_calls{0}, ham_pairs{0}, ns_hamming{0}, ns_max_ham{0}, ns_attach{0}, ns_acquire{0};
     const bool on = getenv("RSA_EXT_STATS") != nullptr;
     ~VeneerStats() {
         if (!on || !calls.load()) return;
         fprintf(stderr, "[rsa_ext veneer] %lld calls, %lld pairs; summed over workers: gather %.1f ms, submit %.1f ms, wait %.1f ms, "
                         "unpack %.1f ms; longest call %.1f ms\n", calls.load(), pairs.load(), ns_gather.load() / 1e6, ns_submit.load() / 1e6,
                 ns_wait.load() / 1e6, ns_unpack.load() / 1e6, ns_max_call.load() / 1e6);
+        if (ham_calls.load())
+            fprintf(stderr, "[rsa_ext veneer] Hamming shortcut: %lld calls, %lld pairs, %.1f ms summed over workers, longest call %.1f ms\n",
+                    ham_calls.load(), ham_pairs.load(), ns_hamming.load() / 1e6, ns_max_ham.load() / 1e6);
+        fprintf(stderr, "[rsa_ext veneer] first calls waiting for a pooled handle: %.1f ms summed over workers\n", ns_acquire.load() / 1e6);
+        if (ns_attach.load())
+            fprintf(stderr, "[rsa_ext veneer] waiting for / uploading the resident genome: %.1f ms summed over workers\n", ns_attach.load() / 1e6);
     }
 } g_vstats;
 inline long long now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -145,6 +152,12 @@ struct Warmup {
                     const int32_t ql = (int32_t)q.size(), tl = (int32_t)w.size();
                     rsa_ext_result_t r;
                     if (rsa_ext_submit_ptrs(h, 1, &qp, &ql, &tp, &tl, &r) == RSA_EXT_OK) rsa_ext_wait(h);
+#ifdef RSA_EXT_WINDOWS
+                    const int64_t off2[2] = {0, ql};   // ... and the Hamming kernel (gpuham builds)
+                    int32_t dist;
+                    rsa_ext_alninfo_t info;
+                    rsa_ext_hamming_align(h, 1, qp, off2, qp, off2, 10, &dist, &info);
+#endif
                 }
                 std::lock_guard<std::mutex> lk(m);
                 pool.emplace_back(cfg.device, h);
@@ -191,6 +204,7 @@ Worker &acquire_worker(int thread_id, size_t n_queries, size_t n_targets, int ma
     }
     Worker &w = g_workers[thread_id];
     if (!w.h) {
+        const long long t_acq = now_ns();
         std::lock_guard<std::mutex> lock(g_create_mutex);
         const int ndev = usable_devices();
         rsa_ext_config_t cfg;
@@ -205,6 +219,7 @@ Worker &acquire_worker(int thread_id, size_t n_queries, size_t n_targets, int ma
         w.device = cfg.device;
         w.h = g_warmup.take(cfg.device, match_score, mismatch_score, gap_open_score, gap_extend_score);
         if (!w.h && rsa_ext_create(&cfg, &w.h) != RSA_EXT_OK) die("rsa_ext_create", nullptr);
+        if (g_vstats.on) g_vstats.ns_acquire += now_ns() - t_acq;
     }
     return w;
 }
@@ -253,6 +268,11 @@ void unpack_results(Worker &w, size_t n, std::vector<gasal_tmp_res> &gasal_resul
 }
 
 }  // namespace
+
+int rsa_ext_veneer_device(int thread_id) {
+    const int ndev = usable_devices();
+    return ndev > 0 && thread_id >= 0 ? thread_id % ndev : 0;
+}
 
 void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &query_seqs,
                       std::vector<std::string> &target_seqs, int match_score, int mismatch_score, int gap_open_score,
@@ -343,7 +363,9 @@ void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_r
     const size_t n = query_seqs.size();
     gasal_results.resize(n);
     if (n == 0) return;
+    const long long t0 = now_ns();
     if (!w.has_reference) attach_reference(w, sequences);
+    const long long t_attach = now_ns();
 
     // queries back to back (the engine copies them to the GPU from here); windows as (offset, length) in the genome
     w.qoff.resize(n + 1); w.woff.resize(n); w.wlen.resize(n); w.res.resize(n);
@@ -361,13 +383,43 @@ void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_r
     const bool text_free = (bonus_state & kBonusConfirmed) != 0;
     w.aln.resize(n);
     if (rsa_ext_request_alninfo(w.h, w.aln.data(), end_bonus) != RSA_EXT_OK) die("rsa_ext_request_alninfo", w.h);
+    const long long t1 = now_ns();
     int rc = rsa_ext_submit_ref_windows(w.h, (int64_t)n, w.qcat.data(), w.qoff.data(), w.woff.data(), w.wlen.data(), w.res.data());
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
     if (rc != RSA_EXT_OK) die("rsa_ext_submit_ref_windows", w.h);
+    const long long t2 = now_ns();
     rc = rsa_ext_wait(w.h);
     if (rc == RSA_EXT_ERR_QUERY_LEN) die_query_too_long(query_seqs);
     if (rc != RSA_EXT_OK) die("rsa_ext_wait", w.h);
+    const long long t3 = now_ns();
     unpack_results(w, n, gasal_results, text_free, end_bonus);
+    if (g_vstats.on) {
+        const long long t4 = now_ns();
+        g_vstats.calls++; g_vstats.pairs += (long long)n; g_vstats.ns_attach += t_attach - t0;
+        g_vstats.ns_gather += t1 - t_attach; g_vstats.ns_submit += t2 - t1; g_vstats.ns_wait += t3 - t2; g_vstats.ns_unpack += t4 - t3;
+        long long mx = g_vstats.ns_max_call.load();
+        while (t4 - t0 > mx && !g_vstats.ns_max_call.compare_exchange_weak(mx, t4 - t0)) {}
+    }
+}
+void solve_hamming_on_gpu_windows(int thread_id, size_t n, const char *qcat, const int64_t *qoff, const uint32_t *ref_id,
+                                  const uint32_t *start, const std::vector<std::string> &sequences, int match_score,
+                                  int mismatch_score, int gap_open_score, int gap_extend_score, int end_bonus,
+                                  int32_t *hamming, rsa_ext_alninfo_t *out) {
+    Worker &w = acquire_worker(thread_id, n, n, match_score, mismatch_score, gap_open_score, gap_extend_score);
+    if (n == 0) return;
+    const long long t0 = now_ns();
+    if (!w.has_reference) attach_reference(w, sequences);
+    const long long t_attach = now_ns();
+    w.woff.resize(n);
+    for (size_t i = 0; i < n; ++i) w.woff[i] = g_genome.contig_off[ref_id[i]] + (int64_t)start[i];
+    if (rsa_ext_hamming_ref_windows(w.h, (int64_t)n, qcat, qoff, w.woff.data(), end_bonus, hamming, out) != RSA_EXT_OK)
+        die("rsa_ext_hamming_ref_windows", w.h);
+    if (g_vstats.on) {
+        const long long t1 = now_ns();
+        g_vstats.ham_calls++; g_vstats.ham_pairs += (long long)n; g_vstats.ns_hamming += t1 - t_attach; g_vstats.ns_attach += t_attach - t0;
+        long long mx = g_vstats.ns_max_ham.load();
+        while (t1 - t_attach > mx && !g_vstats.ns_max_ham.compare_exchange_weak(mx, t1 - t_attach)) {}
+    }
 }
 #endif  // RSA_EXT_WINDOWS
 

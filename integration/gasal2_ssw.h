@@ -54,6 +54,10 @@ void solve_ssw_on_gpu(int thread_id, std::vector<gasal_tmp_res> &gasal_results, 
                       std::vector<std::string> &todo_refs, int match_score = 2, int mismatch_score = 8,
                       int gap_open_score = 12, int gap_extend_score = 1);
 
+// The GPU worker `thread_id` is placed on (thread_id % visible devices, RSA_EXT_DEVICES caps the count): the other glue
+// layers (integration/seed_glue.cpp, sam_glue.cpp) keep a worker's state on the same device.
+int rsa_ext_veneer_device(int thread_id);
+
 #ifdef RSA_EXT_WINDOWS
 // SURVEY 8(f) rank 1, caller half: a reference window named by (contig, start, length) instead of a std::string built
 // with substr (src/pc.cpp:214-242, 333-368).  The todo list of a chunk becomes std::vector<RsaWindow>; the whole list
@@ -82,6 +86,16 @@ struct RsaWindow {
 void solve_ssw_on_gpu_windows(int thread_id, std::vector<gasal_tmp_res> &gasal_results, std::vector<std::string> &todo_querys,
                               std::vector<RsaWindow> &todo_refs, const std::vector<std::string> &sequences,
                               int match_score = 2, int mismatch_score = 8, int gap_open_score = 12, int gap_extend_score = 1);
+
+// SURVEY 8(f) rank 3, caller half: the Hamming shortcut of extend_seed_part (src/aln.cpp:391-404) for a whole chunk in
+// ONE blocking call.  Pair i = query i (qcat[qoff[i] .. qoff[i+1])) against the |query i| bases of contig ref_id[i] that
+// start at start[i]; the engine reads them from the genome resident in HBM (rsa_ext_hamming_ref_windows).  On return
+// out[i].status == 0: hamming_align's AlignmentInfo (src/aligner.cpp:254-302); 1: the pair needs the gapped path;
+// 3: more CIGAR runs than the record holds (host path).  Called from integration/hamming_glue.cpp.
+void solve_hamming_on_gpu_windows(int thread_id, size_t n, const char *qcat, const int64_t *qoff, const uint32_t *ref_id,
+                                  const uint32_t *start, const std::vector<std::string> &sequences, int match_score,
+                                  int mismatch_score, int gap_open_score, int gap_extend_score, int end_bonus,
+                                  int32_t *hamming, rsa_ext_alninfo_t *out);
 #endif
 
 #ifdef RSA_EXT_ALNINFO

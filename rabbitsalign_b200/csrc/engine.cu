@@ -1601,6 +1601,11 @@ extern "C" int rsa_ext_reserve(rsa_ext_t* h, int64_t n, int32_t qlen, int32_t tl
     if ((rc = ensure_pin(h, h->slots[0].h_blob, blob))) return rc;
     if ((rc = ensure_pin(h, h->own_q, (size_t)n * qlen + 16))) return rc;
     if ((rc = ensure_pin(h, h->own_t, (size_t)n * tlen + 16))) return rc;
+    // the Hamming shortcut of the same batch shape (windows named by offset: no target bytes travel)
+    if ((rc = ensure_dev(h, h->ham_q, (size_t)n * qlen + 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_t, 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_off, 2 * sizeof(int64_t) * (size_t)(n + 1) + 16))) return rc;
+    if ((rc = ensure_dev(h, h->ham_out, (sizeof(rsa_ext_alninfo_t) + sizeof(int32_t)) * (size_t)n + 16))) return rc;
     return RSA_EXT_OK;
 }
 

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sam_golden.json")))
 
 
-SUFFIX = {"record": "", "alninfo": "_alninfo", "big": "_big", "windows": "_win", "gpuseed": "_gpuseed", "two-gpus": "_gpuseed"}
+SUFFIX = {"record": "", "alninfo": "_alninfo", "big": "_big", "windows": "_win", "gpuseed": "_gpuseed", "gpuham": "_gpuham", "gpusam": "_gpusam", "two-gpus": "_gpusam"}
 
 
 def _gpu_count():
@@ -27,14 +27,16 @@ def _gpu_count():
     return ext.load_library().rsa_ext_device_count()
 
 
-@pytest.mark.parametrize("variant", ["record", "alninfo", "big", "windows", "gpuseed", "two-gpus", "reference-gpu"])
+@pytest.mark.parametrize("variant", ["record", "alninfo", "big", "windows", "gpuseed", "gpuham", "gpusam", "two-gpus", "reference-gpu"])
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_sam_is_byte_identical(name, variant, tmp_path):
     """record: unmodified caller, 512-pair slices.  alninfo: AlignmentInfo from the device.  big: unmodified caller
     compiled with -DSTREAM_BATCH_SIZE=1048576 (one call per chunk).  windows: the caller edit of SURVEY 8f rank 1
     (windows as offsets into the genome resident in HBM, one call per chunk).  gpuseed: the windows build plus seeding on
-    the GPU (randstrobes, index lookup, NAM merge, rescue; integration/patch_seed.py).  two-gpus: the
-    gpuseed build with its workers spread over two GPUs (genome and index replicated per GPU); skipped on a one-GPU box."""
+    the GPU (randstrobes, index lookup, NAM merge, rescue; integration/patch_seed.py).  gpuham: the gpuseed build plus the Hamming shortcut of
+    extend_seed_part decided on the GPU for a whole chunk (integration/patch_hamming.py).  gpusam: the gpuham build plus the SAM text of
+    every record written by the device formatter, one call per chunk (integration/patch_sam.py).  two-gpus: the
+    gpusam build with its workers spread over two GPUs (genome and index replicated per GPU); skipped on a one-GPU box."""
     g = GOLD[name]
     BIN = os.path.join(B, ("rabbitsalign_fx_b200" if g.get("fx") else "rabbitsalign_b200") + SUFFIX.get(variant, ""))
     env = dict(os.environ)

@@ -65,6 +65,9 @@ def main():
                 return {"error": r.stderr[-500:]}
             mapping = [ln for ln in r.stderr.splitlines() if "Total time" in ln or "indexing" in ln.lower()]
             res = {"wall_s": round(dt, 2), "sam_md5": md5_nopg(sam), "stderr_times": mapping[-8:]}
+            veneer = [ln for ln in r.stderr.splitlines() if ln.startswith("[rsa_ext veneer]")]   # RSA_EXT_STATS=1
+            if veneer:
+                res["veneer_stats"] = veneer
             cost = [ln for ln in r.stderr.splitlines() if ln.startswith("cost time1")]  # the *_timed builds: per-worker phase timers
             if cost:
                 res["worker_phase_timers"] = cost[:32]
