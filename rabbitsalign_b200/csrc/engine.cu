@@ -220,6 +220,7 @@ struct rsa_ext {
     std::vector<int64_t> own_qoff, own_toff;
 
     DevBuf ham_q, ham_t, ham_off, ham_out;  // rsa_ext_hamming_* staging
+    PinBuf ham_pin_in, ham_pin_out;         // pinned bounce buffers for callers that pass pageable memory
     cudaEvent_t ham_ev[2] = {nullptr, nullptr};
 
     // resident set
@@ -288,6 +289,13 @@ int ensure_slot(rsa_ext* h, Slot& s, const SlotNeed& n) {
         s.d_scratch.cap = cap;
     }
     return RSA_EXT_OK;
+}
+
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Pageable memory reports cudaMemoryTypeUnregistered.
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 int ensure_pin(rsa_ext* h, PinBuf& b, size_t need) {
@@ -1396,6 +1404,8 @@ extern "C" void rsa_ext_destroy(rsa_ext_t* h) {
     for (DevBuf* b : {&h->r_q, &h->r_t, &h->r_res, &h->r_blobs, &h->ham_q, &h->ham_t, &h->ham_off, &h->ham_out})
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t ev : h->ham_ev) if (ev) cudaEventDestroy(ev);
+    if (h->ham_pin_in.p) cudaFreeHost(h->ham_pin_in.p);
+    if (h->ham_pin_out.p) cudaFreeHost(h->ham_pin_out.p);
     for (cudaEvent_t ev : h->r_events) cudaEventDestroy(ev);
     if (h->own_q.p) cudaFreeHost(h->own_q.p);
     if (h->own_t.p) cudaFreeHost(h->own_t.p);
@@ -1533,13 +1543,36 @@ int hamming_core(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
     int64_t* d_toff = reinterpret_cast<int64_t*>(h->ham_off.p + offb);
     rsa_ext_alninfo_t* d_out = reinterpret_cast<rsa_ext_alninfo_t*>(h->ham_out.p);
     int32_t* d_ham = reinterpret_cast<int32_t*>(h->ham_out.p + sizeof(rsa_ext_alninfo_t) * (size_t)n);
-    CU_TRY(h, cudaMemcpyAsync(h->ham_q.p, qbuf + qoff[0], qbytes, cudaMemcpyHostToDevice, st));
-    CU_TRY(h, cudaMemcpyAsync(d_qoff, qoff, offb, cudaMemcpyHostToDevice, st));
+    // Pageable caller memory goes through the handle's pinned bounce buffers.  A pageable cudaMemcpyAsync is a synchronous,
+    // driver-staged copy; with 16 pipeline workers calling at once (integration/hamming_glue.cpp, sam_glue.cpp) those copies
+    // made every GPU call of the process slow: BASELINE configs[1] at scale took 14.8 s instead of 6.7 s
+    // (profiles/r2_e2e_reads_pe_5m_pairs_100mb_pageable_copies.json vs ..._full_device_path.json).  Pinned callers
+    // (bench.py) are copied from / to directly.
+    const size_t outb = sizeof(rsa_ext_alninfo_t) * (size_t)n, hamb = sizeof(int32_t) * (size_t)n;
+    const size_t woffb = sizeof(int64_t) * (size_t)n;
+    const bool in_pinned = host_is_pinned(qbuf + qoff[0]) && host_is_pinned(qoff) && host_is_pinned(win_off ? (const void*)win_off : (const void*)toff) &&
+                           (win_off || host_is_pinned(tbuf + toff[0]));
+    const bool out_pinned = host_is_pinned(out) && host_is_pinned(hamming);
+    const uint8_t *src_q = reinterpret_cast<const uint8_t*>(qbuf + qoff[0]), *src_t = win_off ? nullptr : reinterpret_cast<const uint8_t*>(tbuf + toff[0]);
+    const void *src_qoff = qoff, *src_toff = win_off ? (const void*)win_off : (const void*)toff;
+    if (!in_pinned) {
+        const size_t a_q = 0, a_qoff = align_up(qbytes, 16), a_toff = a_qoff + align_up(offb, 16), a_t = a_toff + align_up(offb, 16);
+        if ((rc = ensure_pin(h, h->ham_pin_in, a_t + tbytes + 16))) return rc;
+        uint8_t* pin = h->ham_pin_in.p;
+        memcpy(pin + a_q, src_q, qbytes);
+        memcpy(pin + a_qoff, qoff, offb);
+        memcpy(pin + a_toff, src_toff, win_off ? woffb : offb);
+        if (!win_off) memcpy(pin + a_t, src_t, tbytes);
+        src_q = pin + a_q; src_qoff = pin + a_qoff; src_toff = pin + a_toff; src_t = pin + a_t;
+    }
+    if (!out_pinned && (rc = ensure_pin(h, h->ham_pin_out, outb + hamb + 16))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->ham_q.p, src_q, qbytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync(d_qoff, src_qoff, offb, cudaMemcpyHostToDevice, st));
     if (win_off) {
-        CU_TRY(h, cudaMemcpyAsync(d_toff, win_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(d_toff, src_toff, woffb, cudaMemcpyHostToDevice, st));
     } else {
-        CU_TRY(h, cudaMemcpyAsync(h->ham_t.p, tbuf + toff[0], tbytes, cudaMemcpyHostToDevice, st));
-        CU_TRY(h, cudaMemcpyAsync(d_toff, toff, offb, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(h->ham_t.p, src_t, tbytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(d_toff, src_toff, offb, cudaMemcpyHostToDevice, st));
     }
     const int64_t ham_rounds = (n + 31) / 32;   // a warp takes 32 pairs per round
     const int blocks = (int)std::min<int64_t>((ham_rounds + kHamWarpsPerBlock - 1) / kHamWarpsPerBlock, (int64_t)h->n_sms * 16);
@@ -1552,9 +1585,17 @@ int hamming_core(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
         win_off ? d_toff : nullptr, (long long)n, h->sc.match, h->sc.mismatch, end_bonus, d_ham, d_out);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ham_ev[1], st));
-    CU_TRY(h, cudaMemcpyAsync(out, d_out, sizeof(rsa_ext_alninfo_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaMemcpyAsync(hamming, d_ham, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
+    // (d_out and d_ham are adjacent on the device: one copy when the destination is the bounce buffer)
+    if (out_pinned) {
+        CU_TRY(h, cudaMemcpyAsync(out, d_out, outb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(hamming, d_ham, hamb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(h->ham_pin_out.p, d_out, outb + hamb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+        memcpy(out, h->ham_pin_out.p, outb);
+        memcpy(hamming, h->ham_pin_out.p + outb, hamb);
+    }
     h->stats = rsa_ext_stats_t{};
     h->stats.kernel_launches = 1;
     float ms = 0;
@@ -1606,6 +1647,8 @@ extern "C" int rsa_ext_reserve(rsa_ext_t* h, int64_t n, int32_t qlen, int32_t tl
     if ((rc = ensure_dev(h, h->ham_t, 16))) return rc;
     if ((rc = ensure_dev(h, h->ham_off, 2 * sizeof(int64_t) * (size_t)(n + 1) + 16))) return rc;
     if ((rc = ensure_dev(h, h->ham_out, (sizeof(rsa_ext_alninfo_t) + sizeof(int32_t)) * (size_t)n + 16))) return rc;
+    if ((rc = ensure_pin(h, h->ham_pin_in, (size_t)n * qlen + 2 * sizeof(int64_t) * (size_t)(n + 1) + 128))) return rc;
+    if ((rc = ensure_pin(h, h->ham_pin_out, (sizeof(rsa_ext_alninfo_t) + sizeof(int32_t)) * (size_t)n + 16))) return rc;
     return RSA_EXT_OK;
 }
 

@@ -73,14 +73,14 @@ __host__ inline bool fast_scoring_ok(const Scoring& sc) {
 }
 
 // nibble (ascii & 0xF) -> code: A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4, everything else 0xF
-__device__ __forceinline__ uint32_t base_code(uint32_t nib) {
-    uint32_t c = 0xFu;
-    c = (nib == 1u) ? 0u : c;
-    c = (nib == 3u) ? 1u : c;
-    c = (nib == 7u) ? 2u : c;
-    c = (nib == 4u) ? 3u : c;
-    c = (nib == 0xEu) ? 4u : c;
-    return c;
+// (a 16 x 4-bit table in one 64-bit constant: shift + mask instead of five compare/select pairs -- the staging of a group
+// converts ~200 bytes per lane, and staging was 12 % of the kernel's warp time, profiles/r2_kernels.md)
+__host__ __device__ __forceinline__ uint32_t base_code(uint32_t nib) {
+    constexpr unsigned long long kTable = 0xF4FFFFFF2FF31F0Full;   // entry n = bits 4n .. 4n+3
+    static_assert(((kTable >> 4) & 0xF) == 0 && ((kTable >> 12) & 0xF) == 1 && ((kTable >> 28) & 0xF) == 2 && ((kTable >> 16) & 0xF) == 3 &&
+                  ((kTable >> 56) & 0xF) == 4 && (kTable & 0xF) == 0xF && ((kTable >> 8) & 0xF) == 0xF && ((kTable >> 60) & 0xF) == 0xF,
+                  "A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4");
+    return (uint32_t)(kTable >> (4u * (nib & 0xFu))) & 0xFu;
 }
 
 // The resident reference in the packed form the staging above reads (north_star: 2-bit-packed windows, vectorised loads):
@@ -322,11 +322,28 @@ fast_dp_kernel(const uint8_t* __restrict__ qbuf, const uint8_t* __restrict__ tbu
         if (!tpack) {
             const uint8_t* ta = tbuf + ma.toff;
             const uint8_t* tb = tbuf + mb.toff;
-            for (int r = gl; r < rows; r += L) {
-                uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
-                if (r < tlen_a) { ca = base_code(nibble_of(ta[r])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
-                if (r < tlen_b) { cb = base_code(nibble_of(tb[r])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
-                tcodes[r] = (uint8_t)(ca | (cb << 4));
+            // kStageBatch rows of both windows are loaded before the first one is used: the loads of a batch overlap
+            // (one exposed memory latency per batch instead of one per row -- the profile showed the staging warps
+            // waiting on the long scoreboard for half of their time)
+            constexpr int kStageBatch = 8;
+            for (int r0 = gl; r0 < rows; r0 += L * kStageBatch) {
+                uint32_t xa[kStageBatch], xb[kStageBatch];
+#pragma unroll
+                for (int j = 0; j < kStageBatch; ++j) {
+                    const int r = r0 + j * L;
+                    xa[j] = (r < tlen_a) ? (uint32_t)ta[r] : 0u;
+                    xb[j] = (r < tlen_b) ? (uint32_t)tb[r] : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < kStageBatch; ++j) {
+                    const int r = r0 + j * L;
+                    if (r < rows) {
+                        uint32_t ca = 5u, cb = 5u;  // rows past a pair's own window
+                        if (r < tlen_a) { ca = base_code(nibble_of((uint8_t)xa[j])); bad_a |= (ca == 0xFu); ca = min(ca, 5u); }
+                        if (r < tlen_b) { cb = base_code(nibble_of((uint8_t)xb[j])); bad_b |= (cb == 0xFu); cb = min(cb, 5u); }
+                        tcodes[r] = (uint8_t)(ca | (cb << 4));
+                    }
+                }
             }
         }
     }

@@ -269,6 +269,7 @@ struct rsa_sam {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // around the length + scan kernels, around the writer
     double kernel_ms = 0;
     Buf rec, text, cig, len, off, sums, out;
+    Buf pin_in, pin_out;   // pinned bounce buffers for callers that pass pageable memory
     std::string err;
 };
 
@@ -288,6 +289,23 @@ static int grow(rsa_sam* h, Buf& b, size_t need) {
     SAM_TRY(h, cudaMalloc(&b.p, cap));
     b.cap = cap;
     return RSA_EXT_OK;
+}
+
+static int grow_pinned(rsa_sam* h, Buf& b, size_t need) {
+    if (need <= b.cap) return RSA_EXT_OK;
+    if (b.p) SAM_TRY(h, cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    const size_t cap = ((need + need / 2) + 1048575) & ~(size_t)1048575;
+    SAM_TRY(h, cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+    b.cap = cap;
+    return RSA_EXT_OK;
+}
+
+// page-locked host memory?  (pageable memory reports cudaMemoryTypeUnregistered)
+static bool sam_host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 extern "C" double rsa_sam_kernel_ms(const rsa_sam_t* h) { return h ? h->kernel_ms : 0.0; }
@@ -335,6 +353,7 @@ extern "C" void rsa_sam_destroy(rsa_sam_t* h) {
     if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
     for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev2, h->ev3}) if (ev) cudaEventDestroy(ev);
     for (Buf* b : {&h->rec, &h->text, &h->cig, &h->len, &h->off, &h->sums, &h->out}) if (b->p) cudaFree(b->p);
+    for (Buf* b : {&h->pin_in, &h->pin_out}) if (b->p) cudaFreeHost(b->p);
     if (h->d_names) cudaFree(h->d_names);
     if (h->d_names_off) cudaFree(h->d_names_off);
     delete h;
@@ -366,9 +385,24 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
     if ((rc = grow(h, h->off, sizeof(unsigned long long) * (size_t)(n + 1)))) return rc;
     if ((rc = grow(h, h->sums, sizeof(unsigned long long) * (size_t)(nb + 1)))) return rc;
     cudaStream_t st = h->st;
-    SAM_TRY(h, cudaMemcpyAsync(h->rec.p, records, sizeof(rsa_sam_record_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-    if (text_bytes) SAM_TRY(h, cudaMemcpyAsync(h->text.p, text_pool, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
-    if (n_cigar_ops) SAM_TRY(h, cudaMemcpyAsync(h->cig.p, cigar_pool, sizeof(uint32_t) * (size_t)n_cigar_ops, cudaMemcpyHostToDevice, st));
+    // Pageable caller memory (the pipeline's per-chunk collector, integration/sam_glue.cpp) goes through pinned bounce
+    // buffers: pageable cudaMemcpyAsync calls are synchronous driver-staged copies, and sixteen workers formatting their
+    // chunks through them slowed every GPU call of the process (see hamming_core in engine.cu for the measurement).
+    // Pinned callers are copied from / to directly.
+    const size_t recb = sizeof(rsa_sam_record_t) * (size_t)n, cigb = sizeof(uint32_t) * (size_t)n_cigar_ops;
+    const void *src_rec = records, *src_text = text_pool, *src_cig = cigar_pool;
+    if (!(sam_host_is_pinned(records) && sam_host_is_pinned(text_pool) && (!n_cigar_ops || sam_host_is_pinned(cigar_pool)))) {
+        const size_t a_text = (recb + 15) & ~(size_t)15, a_cig = a_text + (((size_t)text_bytes + 15) & ~(size_t)15);
+        if ((rc = grow_pinned(h, h->pin_in, a_cig + cigb + 16))) return rc;
+        char* pin = (char*)h->pin_in.p;
+        memcpy(pin, records, recb);
+        if (text_bytes) memcpy(pin + a_text, text_pool, (size_t)text_bytes);
+        if (n_cigar_ops) memcpy(pin + a_cig, cigar_pool, cigb);
+        src_rec = pin; src_text = pin + a_text; src_cig = pin + a_cig;
+    }
+    SAM_TRY(h, cudaMemcpyAsync(h->rec.p, src_rec, recb, cudaMemcpyHostToDevice, st));
+    if (text_bytes) SAM_TRY(h, cudaMemcpyAsync(h->text.p, src_text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
+    if (n_cigar_ops) SAM_TRY(h, cudaMemcpyAsync(h->cig.p, src_cig, cigb, cudaMemcpyHostToDevice, st));
     const rsa_sam_record_t* d_rec = (const rsa_sam_record_t*)h->rec.p;
     unsigned long long* d_len = (unsigned long long*)h->len.p;
     unsigned long long* d_off = (unsigned long long*)h->off.p;
@@ -381,9 +415,11 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
     scan_apply<<<nb, kScanThreads, 0, st>>>(d_len, (long long)n, d_sums, d_off);
     SAM_TRY(h, cudaGetLastError());
     SAM_TRY(h, cudaEventRecord(h->ev1, st));
+    if ((rc = grow_pinned(h, h->pin_out, 64))) return rc;   // (at least the total; grown below for a pageable destination)
     unsigned long long total = 0;
-    SAM_TRY(h, cudaMemcpyAsync(&total, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, st));
+    SAM_TRY(h, cudaMemcpyAsync(h->pin_out.p, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, st));
     SAM_TRY(h, cudaStreamSynchronize(st));
+    total = *(const unsigned long long*)h->pin_out.p;
     *out_len = (int64_t)total;
     if (line_off) {
         static_assert(sizeof(int64_t) == sizeof(unsigned long long), "offsets are copied as they are");
@@ -404,7 +440,15 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
         sam_write_kernel<<<blocks, 32 * kSamWarps, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)h->text.p, (const uint32_t*)h->cig.p, d_off, (char*)h->out.p);
         SAM_TRY(h, cudaGetLastError());
         SAM_TRY(h, cudaEventRecord(h->ev3, st));
-        SAM_TRY(h, cudaMemcpyAsync(out, h->out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+        if (sam_host_is_pinned(out)) {
+            SAM_TRY(h, cudaMemcpyAsync(out, h->out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            SAM_TRY(h, cudaStreamSynchronize(st));
+        } else {
+            if ((rc = grow_pinned(h, h->pin_out, (size_t)total))) return rc;
+            SAM_TRY(h, cudaMemcpyAsync(h->pin_out.p, h->out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            SAM_TRY(h, cudaStreamSynchronize(st));
+            memcpy(out, h->pin_out.p, (size_t)total);
+        }
     }
     SAM_TRY(h, cudaStreamSynchronize(st));
     float a = 0, b = 0;

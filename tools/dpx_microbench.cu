@@ -140,6 +140,73 @@ __global__ void bench_cell(uint32_t* out, const rsa::FastConsts k, const uint32_
     if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; cycles[gridDim.x + blockIdx.x] = n1 - n0; }
 }
 
+// ---- the same bare recipe at the KERNEL'S shape: NC columns per lane (38 for the 4-lane groups of 150-bp reads) and the
+// kernel's occupancy (168 registers -> 3 blocks of 128 threads per SM = 3 warps per scheduler; forced here with dynamic
+// shared memory).  Separates "what the recipe can do at this occupancy" from "what the rest of the kernel costs".
+template <int NC>
+__global__ void __launch_bounds__(128, NC >= 32 ? 3 : 4) bench_cell_n(uint32_t* out, const rsa::FastConsts k, const uint32_t* in, int ITERS) {
+    extern __shared__ uint32_t occupancy_pad[];
+    uint32_t S[NC], E[NC], qsel[NC];
+    uint32_t px = in[8] + threadIdx.x, py = in[9];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { S[c] = k.zero; E[c] = k.zero; qsel[c] = in[10 + (c & 31)] + (c >> 5); }
+    uint32_t F = k.zero, Hl = k.zero, rowkey = 0, sink = 0;
+    if (ITERS < 0) occupancy_pad[threadIdx.x] = px;   // never: keeps the allocation referenced
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = NC - 1; c >= 0; --c) S[c] = (c == 0 ? Hl : S[c - 1]) + rsa::prmt(px, py, qsel[c]);
+        uint32_t nib_even = 0, p_lo = 0, key_prev = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            uint32_t h, fn, en, nib, key;
+            rsa::fast_cell(k, S[c], F, E[c], rsa::key_colconst<6>(c), k.k64, h, fn, en, nib, key);
+            if (c & 1) rowkey = __vimax3_s16x2(rowkey, key_prev, key);
+            key_prev = key;
+            S[c] = h;
+            E[c] = en;
+            F = fn;
+            if ((c & 3) == 0 || (c & 3) == 2) nib_even = nib;
+            else if ((c & 3) == 1) p_lo = rsa::dir_pair(k, nib_even, nib);
+            else sink ^= rsa::dir_word(p_lo, rsa::dir_pair(k, nib_even, nib));
+        }
+        Hl = F;
+        px += py;
+    }
+    uint32_t s = sink + rowkey + F;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s += S[c] + E[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int NC>
+void run_cell_at_occupancy(int n_sms, int blocks_per_sm, uint32_t* d_out, uint32_t* d_in) {
+    const int threads = 128;
+    const int smem = blocks_per_sm >= 16 ? 0 : (220 * 1024 / blocks_per_sm - 2048) & ~1023;   // caps resident blocks per SM
+    CHECK(cudaFuncSetAttribute(bench_cell_n<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int resident = 0;
+    CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, bench_cell_n<NC>, threads, smem));
+    cudaFuncAttributes fa;
+    CHECK(cudaFuncGetAttributes(&fa, bench_cell_n<NC>));
+    const int iters = g_iters * 8 / NC;
+    const int blocks = n_sms * resident * 4;   // four full waves
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0));
+    CHECK(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 3; ++rep) {
+        CHECK(cudaEventRecord(e0));
+        bench_cell_n<NC><<<blocks, threads, smem>>>(d_out, g_consts, d_in, iters);
+        CHECK(cudaEventRecord(e1));
+        CHECK(cudaEventSynchronize(e1));
+    }
+    CHECK(cudaGetLastError());
+    float ms = 0;
+    CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double gcups = 2.0 * (double)iters * NC * (double)blocks * threads / (ms * 1e-3) / 1e9;
+    printf("{\"test\": \"bare cell recipe at a fixed occupancy\", \"columns_per_lane\": %d, \"registers\": %d, \"blocks_per_sm\": %d, "
+           "\"warps_per_scheduler\": %.1f, \"chip_gcups\": %.1f, \"ms\": %.3f}\n", NC, fa.numRegs, resident, resident * threads / 128.0, gcups, ms);
+}
+
 // ---- the previous recipe (rounds 1-2a), kept for comparison ------------------------------------------------------
 // s = diag + sub + mismatch (biased, unsigned profile); the four direction facts are carries of ring subtractions into
 // bits 15..12 (3 IADD3 + 2 IMAD), merged with three bit-selects, shifted into the word per cell.
@@ -324,6 +391,11 @@ int main(int argc, char** argv) {
             run<IMAD_RR>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
             run<MIX_DPX2_HFMA2_IMAD>(n_sms, bps, threads, d_out, d_in, d_cyc, prop.clockRate);
         }
+    }
+    if (!quick) {   // the recipe at the product kernel's shape and occupancy, and what more resident warps would buy
+        for (int bps : {3, 4, 6, 8}) run_cell_at_occupancy<38>(n_sms, bps, d_out, d_in);
+        for (int bps : {3, 4, 6, 8}) run_cell_at_occupancy<19>(n_sms, bps, d_out, d_in);
+        for (int bps : {3, 6}) run_cell_at_occupancy<8>(n_sms, bps, d_out, d_in);
     }
     {
         unsigned int* d_bad;
