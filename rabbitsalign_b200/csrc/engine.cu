@@ -1550,21 +1550,22 @@ int hamming_core(rsa_ext_t* h, int64_t n, const char* qbuf, const int64_t* qoff,
     // (bench.py) are copied from / to directly.
     const size_t outb = sizeof(rsa_ext_alninfo_t) * (size_t)n, hamb = sizeof(int32_t) * (size_t)n;
     const size_t woffb = sizeof(int64_t) * (size_t)n;
-    const bool in_pinned = host_is_pinned(qbuf + qoff[0]) && host_is_pinned(qoff) && host_is_pinned(win_off ? (const void*)win_off : (const void*)toff) &&
-                           (win_off || host_is_pinned(tbuf + toff[0]));
     const bool out_pinned = host_is_pinned(out) && host_is_pinned(hamming);
-    const uint8_t *src_q = reinterpret_cast<const uint8_t*>(qbuf + qoff[0]), *src_t = win_off ? nullptr : reinterpret_cast<const uint8_t*>(tbuf + toff[0]);
-    const void *src_qoff = qoff, *src_toff = win_off ? (const void*)win_off : (const void*)toff;
-    if (!in_pinned) {
-        const size_t a_q = 0, a_qoff = align_up(qbytes, 16), a_toff = a_qoff + align_up(offb, 16), a_t = a_toff + align_up(offb, 16);
-        if ((rc = ensure_pin(h, h->ham_pin_in, a_t + tbytes + 16))) return rc;
-        uint8_t* pin = h->ham_pin_in.p;
-        memcpy(pin + a_q, src_q, qbytes);
-        memcpy(pin + a_qoff, qoff, offb);
-        memcpy(pin + a_toff, src_toff, win_off ? woffb : offb);
-        if (!win_off) memcpy(pin + a_t, src_t, tbytes);
-        src_q = pin + a_q; src_qoff = pin + a_qoff; src_toff = pin + a_toff; src_t = pin + a_t;
+    // every input array on its own: pinned ones are read in place, pageable ones take a slot of the bounce buffer
+    struct In { const void* p; size_t bytes; bool pinned; size_t at; };
+    In ins[4] = {{qbuf + qoff[0], qbytes, false, 0}, {qoff, offb, false, 0},
+                 {win_off ? (const void*)win_off : (const void*)toff, win_off ? woffb : offb, false, 0},
+                 {win_off ? nullptr : (const void*)(tbuf + toff[0]), tbytes, false, 0}};
+    size_t bounce = 0;
+    for (In& a : ins) {
+        a.pinned = !a.p || !a.bytes || host_is_pinned(a.p);
+        if (!a.pinned) { a.at = bounce; bounce += align_up(a.bytes, 16); }
     }
+    if (bounce && (rc = ensure_pin(h, h->ham_pin_in, bounce + 16))) return rc;
+    for (In& a : ins)
+        if (!a.pinned) { memcpy(h->ham_pin_in.p + a.at, a.p, a.bytes); a.p = h->ham_pin_in.p + a.at; }
+    const uint8_t *src_q = reinterpret_cast<const uint8_t*>(ins[0].p), *src_t = reinterpret_cast<const uint8_t*>(ins[3].p);
+    const void *src_qoff = ins[1].p, *src_toff = ins[2].p;
     if (!out_pinned && (rc = ensure_pin(h, h->ham_pin_out, outb + hamb + 16))) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->ham_q.p, src_q, qbytes, cudaMemcpyHostToDevice, st));
     CU_TRY(h, cudaMemcpyAsync(d_qoff, src_qoff, offb, cudaMemcpyHostToDevice, st));
