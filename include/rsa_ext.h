@@ -186,7 +186,8 @@ int rsa_ext_request_alninfo(rsa_ext_t *h, rsa_ext_alninfo_t *out, int32_t end_bo
  * the engine does not extend either: status 1).
  * out[i].status: 0 the shortcut applies and the record is hamming_align's AlignmentInfo (ref_start/ref_end relative to
  * the window); 1 the pair needs the gapped path (submit it); 3 more than RSA_EXT_CIGAR_INLINE runs (host path).
- * Scores are the handle's; end_bonus is strobealign's -L. */
+ * Scores are the handle's; end_bonus is strobealign's -L.  Host arrays may be pinned or pageable: pinned ones are copied from / to
+ * directly, pageable ones go through pinned bounce buffers of the handle (sized ahead by rsa_ext_reserve). */
 int rsa_ext_hamming_align(rsa_ext_t *h, int64_t n, const char *qbuf, const int64_t *qoff, const char *tbuf,
                           const int64_t *toff, int32_t end_bonus, int32_t *hamming, rsa_ext_alninfo_t *out);
 /* The same with window i = [win_off[i], win_off[i] + |query i|) of the resident reference (rsa_ext_set_reference). */

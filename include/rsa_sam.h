@@ -74,7 +74,8 @@ const char *rsa_sam_last_error(const rsa_sam_t *h);
 
 /* Format n records.  text_pool: names, sequences, qualities; cigar_pool: all CIGAR ops.  The lines are written back to
  * back into out[0..out_cap); line_off (n + 1 entries, may be NULL) receives every line's start.  *out_len = total bytes;
- * if it exceeds out_cap nothing is copied and RSA_EXT_ERR_ARG is returned (call again with a larger buffer). Blocking. */
+ * if it exceeds out_cap nothing is copied and RSA_EXT_ERR_ARG is returned (call again with a larger buffer). Blocking.
+ * Host arrays may be pinned or pageable (pageable input pools and a pageable `out` go through pinned bounce buffers of the handle). */
 int rsa_sam_format(rsa_sam_t *h, int64_t n, const rsa_sam_record_t *records, const char *text_pool, int64_t text_bytes,
                    const uint32_t *cigar_pool, int64_t n_cigar_ops, char *out, int64_t out_cap, int64_t *out_len,
                    int64_t *line_off);

@@ -9,6 +9,7 @@
 //                       as coalesced byte copies, reverse-complemented (src/revcomp.hpp:10-41) or reversed for
 //                       reverse-strand records.
 // HBM-bound byte work: ~350 B read and ~400 B written per 150-bp record.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -268,7 +269,8 @@ struct rsa_sam {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // around the length + scan kernels, around the writer
     double kernel_ms = 0;
-    Buf rec, text, cig, len, off, sums, out;
+    Buf arena, out;        // arena: records, text pool, CIGAR pool, line lengths, offsets, scan sums -- ONE allocation (a cudaMalloc
+                           // issued while other pipeline workers are enqueueing stalls all of them)
     Buf pin_in, pin_out;   // pinned bounce buffers for callers that pass pageable memory
     std::string err;
 };
@@ -352,7 +354,7 @@ extern "C" void rsa_sam_destroy(rsa_sam_t* h) {
     cudaSetDevice(h->device);
     if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
     for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev2, h->ev3}) if (ev) cudaEventDestroy(ev);
-    for (Buf* b : {&h->rec, &h->text, &h->cig, &h->len, &h->off, &h->sums, &h->out}) if (b->p) cudaFree(b->p);
+    for (Buf* b : {&h->arena, &h->out}) if (b->p) cudaFree(b->p);
     for (Buf* b : {&h->pin_in, &h->pin_out}) if (b->p) cudaFreeHost(b->p);
     if (h->d_names) cudaFree(h->d_names);
     if (h->d_names_off) cudaFree(h->d_names_off);
@@ -378,12 +380,17 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
     SAM_TRY(h, cudaSetDevice(h->device));
     const int nb = (int)((n + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
     int rc;
-    if ((rc = grow(h, h->rec, sizeof(rsa_sam_record_t) * (size_t)n))) return rc;
-    if ((rc = grow(h, h->text, (size_t)text_bytes + 16))) return rc;
-    if ((rc = grow(h, h->cig, sizeof(uint32_t) * (size_t)n_cigar_ops + 16))) return rc;
-    if ((rc = grow(h, h->len, sizeof(unsigned long long) * (size_t)n))) return rc;
-    if ((rc = grow(h, h->off, sizeof(unsigned long long) * (size_t)(n + 1)))) return rc;
-    if ((rc = grow(h, h->sums, sizeof(unsigned long long) * (size_t)(nb + 1)))) return rc;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_text = al(sizeof(rsa_sam_record_t) * (size_t)n), o_cig = o_text + al((size_t)text_bytes + 16),
+                 o_len = o_cig + al(sizeof(uint32_t) * (size_t)n_cigar_ops + 16), o_off = o_len + al(sizeof(unsigned long long) * (size_t)n),
+                 o_sums = o_off + al(sizeof(unsigned long long) * (size_t)(n + 1)), arena_need = o_sums + al(sizeof(unsigned long long) * (size_t)(nb + 1));
+    if ((rc = grow(h, h->arena, arena_need))) return rc;
+    // the text buffer is sized before the lengths are known (so that a first call allocates everything at once): the caller's
+    // capacity, capped by a generous estimate; grown below in the rare case the estimate was short
+    const size_t est_out = std::min<size_t>((size_t)(out_cap > 0 ? out_cap : 0), (size_t)text_bytes + (size_t)n * 256 + 12 * (size_t)n_cigar_ops + 64);
+    if ((rc = grow(h, h->out, est_out))) return rc;
+    char* const a_base = (char*)h->arena.p;
+    void* const d_recs = a_base; void* const d_text = a_base + o_text; void* const d_cig = a_base + o_cig;
     cudaStream_t st = h->st;
     // Pageable caller memory (the pipeline's per-chunk collector, integration/sam_glue.cpp) goes through pinned bounce
     // buffers: pageable cudaMemcpyAsync calls are synchronous driver-staged copies, and sixteen workers formatting their
@@ -400,22 +407,24 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
         if (n_cigar_ops) memcpy(pin + a_cig, cigar_pool, cigb);
         src_rec = pin; src_text = pin + a_text; src_cig = pin + a_cig;
     }
-    SAM_TRY(h, cudaMemcpyAsync(h->rec.p, src_rec, recb, cudaMemcpyHostToDevice, st));
-    if (text_bytes) SAM_TRY(h, cudaMemcpyAsync(h->text.p, src_text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
-    if (n_cigar_ops) SAM_TRY(h, cudaMemcpyAsync(h->cig.p, src_cig, cigb, cudaMemcpyHostToDevice, st));
-    const rsa_sam_record_t* d_rec = (const rsa_sam_record_t*)h->rec.p;
-    unsigned long long* d_len = (unsigned long long*)h->len.p;
-    unsigned long long* d_off = (unsigned long long*)h->off.p;
-    unsigned long long* d_sums = (unsigned long long*)h->sums.p;
+    SAM_TRY(h, cudaMemcpyAsync(d_recs, src_rec, recb, cudaMemcpyHostToDevice, st));
+    if (text_bytes) SAM_TRY(h, cudaMemcpyAsync(d_text, src_text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
+    if (n_cigar_ops) SAM_TRY(h, cudaMemcpyAsync(d_cig, src_cig, cigb, cudaMemcpyHostToDevice, st));
+    const rsa_sam_record_t* d_rec = (const rsa_sam_record_t*)d_recs;
+    unsigned long long* d_len = (unsigned long long*)(a_base + o_len);
+    unsigned long long* d_off = (unsigned long long*)(a_base + o_off);
+    unsigned long long* d_sums = (unsigned long long*)(a_base + o_sums);
     h->kernel_ms = 0;
     SAM_TRY(h, cudaEventRecord(h->ev0, st));
-    sam_length_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)h->text.p, (const uint32_t*)h->cig.p, d_len);
+    sam_length_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)d_text, (const uint32_t*)d_cig, d_len);
     scan_block_sums<<<nb, kScanThreads, 0, st>>>(d_len, (long long)n, d_sums);
     scan_of_sums<<<1, 1, 0, st>>>(d_sums, nb, d_sums + nb);
     scan_apply<<<nb, kScanThreads, 0, st>>>(d_len, (long long)n, d_sums, d_off);
     SAM_TRY(h, cudaGetLastError());
     SAM_TRY(h, cudaEventRecord(h->ev1, st));
-    if ((rc = grow_pinned(h, h->pin_out, 64))) return rc;   // (at least the total; grown below for a pageable destination)
+    // (holds the total; sized for the text right away when the destination is pageable: one allocation on a first call)
+    const bool out_is_pinned = out && sam_host_is_pinned(out);
+    if ((rc = grow_pinned(h, h->pin_out, out_is_pinned ? 64 : est_out + 64))) return rc;
     unsigned long long total = 0;
     SAM_TRY(h, cudaMemcpyAsync(h->pin_out.p, d_sums + nb, sizeof total, cudaMemcpyDeviceToHost, st));
     SAM_TRY(h, cudaStreamSynchronize(st));
@@ -437,10 +446,10 @@ extern "C" int rsa_sam_format(rsa_sam_t* h, int64_t n, const rsa_sam_record_t* r
         const long long want = (n + kSamWarps - 1) / kSamWarps;
         const int blocks = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
         SAM_TRY(h, cudaEventRecord(h->ev2, st));
-        sam_write_kernel<<<blocks, 32 * kSamWarps, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)h->text.p, (const uint32_t*)h->cig.p, d_off, (char*)h->out.p);
+        sam_write_kernel<<<blocks, 32 * kSamWarps, 0, st>>>(h->cfg, d_rec, (long long)n, (const char*)d_text, (const uint32_t*)d_cig, d_off, (char*)h->out.p);
         SAM_TRY(h, cudaGetLastError());
         SAM_TRY(h, cudaEventRecord(h->ev3, st));
-        if (sam_host_is_pinned(out)) {
+        if (out_is_pinned) {
             SAM_TRY(h, cudaMemcpyAsync(out, h->out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
             SAM_TRY(h, cudaStreamSynchronize(st));
         } else {

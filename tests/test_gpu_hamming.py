@@ -74,3 +74,24 @@ def test_hamming_windows_in_the_resident_reference():
     ok = exp["status"] == 0
     assert (aln_w["sw_score"][ok] == exp["score"][ok]).all() and (aln_w["edit_distance"][ok] == exp["ed"][ok]).all()
     assert 0.3 < ok.mean() < 0.8
+
+
+def test_pinned_and_pageable_callers_get_the_same_records():
+    """Pinned host arrays are copied from directly, pageable ones go through the handle's bounce buffers (and a mix of the
+    two is decided per array): the records must not depend on it."""
+    import torch
+
+    def pinned(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return t, v
+    qbuf, qoff, tbuf, toff = make_pairs(5000, 21, 150)
+    e = ExtensionEngine()
+    ham0, aln0 = e.hamming_align(qbuf, qoff, tbuf, toff)                      # all pageable
+    keep = [pinned(x) for x in (qbuf, qoff, tbuf, toff)]
+    ham1, aln1 = e.hamming_align(*[v for _, v in keep])                        # inputs pinned, outputs pageable
+    ham2, aln2 = e.hamming_align(keep[0][1], qoff, keep[2][1], toff)           # sequences pinned, offsets pageable
+    e.close()
+    assert (ham0 == ham1).all() and (ham0 == ham2).all()
+    assert aln0.tobytes() == aln1.tobytes() == aln2.tobytes()

@@ -45,3 +45,24 @@ def test_output_buffer_too_small_is_reported():
     assert rc == -1 and n.value > 16
     assert len(f.format(recs, text, cig)) == n.value   # the handle stays usable
     f.close()
+
+
+def test_pinned_and_pageable_callers_get_the_same_text():
+    """rsa_sam_format reads pinned pools in place and bounces pageable ones; the same for the output buffer."""
+    import torch
+    ref_names, calls, text, cig = make_calls(3000, seed=77)
+    recs = records_from_calls(calls)
+    f = S.SamFormatter(ref_names)
+    want = f.format(recs, text, cig)                                             # all pageable
+
+    def pinned(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return t, v
+    keep = [pinned(np.ascontiguousarray(x)) for x in (recs, text, np.ascontiguousarray(cig, dtype=np.uint32))]
+    tout = torch.empty(len(want) + 64, dtype=torch.uint8).pin_memory()
+    got = f.format(keep[0][1], keep[1][1], keep[2][1], out=tout.numpy())         # all pinned
+    assert bytes(got) == want
+    assert f.format(keep[0][1], text, cig) == want                               # mixed
+    f.close()
