@@ -423,7 +423,7 @@ def leg_sam_format(device, peaks):
 def pipeline_block(threads):
     """BASELINE metric (i), end-to-end reads/s: the reference's host pipeline (integration/_build, compiled from the
     reference by integration/build.sh) with the reference's own GPU path vs this engine, same synthetic FASTQ/FASTA,
-    same threads.  A small job (600 k single-end reads, 20 Mb): process start-up weighs in (CUDA initialisation inside a
+    same threads.  A small job (1.5 M single-end reads, 50 Mb): process start-up weighs in (CUDA initialisation inside a
     busy process varies by seconds), so every binary runs twice, the better run counts, and the pipeline's own
     "Total time mapping" is reported next to the wall clock.  Runs at BASELINE scale: profiles/r2_e2e_*.json."""
     exe = os.path.join(ROOT, "tools", "e2e_reads_bench.py")
@@ -437,7 +437,7 @@ def pipeline_block(threads):
     if not all(os.path.exists(os.path.join(ROOT, "integration", "_build", b)) for b in bins[:2]):
         return None
     try:
-        r = subprocess.run([sys.executable, exe, "--ref-len", "20000000", "--reads", "600000", "--threads", str(threads),
+        r = subprocess.run([sys.executable, exe, "--ref-len", "50000000", "--reads", "1500000", "--threads", str(threads),
                             "--binaries", ",".join(bins), "--repeat", "2"], capture_output=True, text=True, timeout=420)
         d = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception as ex:  # noqa: BLE001
