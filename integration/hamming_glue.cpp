@@ -27,7 +27,10 @@ struct Scratch {
 thread_local Scratch t_scratch;
 }  // namespace
 
-HammingDefer::HammingDefer(bool on) : prev(t_defer) { t_defer = on && getenv("RSA_EXT_HOST_HAMMING") == nullptr; }
+HammingDefer::HammingDefer(bool on) : prev(t_defer) {
+    static const bool host_only = getenv("RSA_EXT_HOST_HAMMING") != nullptr;   // (once per process: this runs per read)
+    t_defer = on && !host_only;
+}
 HammingDefer::~HammingDefer() { t_defer = prev; }
 bool hamming_deferred() { return t_defer; }
 
