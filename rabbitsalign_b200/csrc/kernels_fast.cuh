@@ -77,9 +77,10 @@ __host__ inline bool fast_scoring_ok(const Scoring& sc) {
 // converts ~200 bytes per lane, and staging was 12 % of the kernel's warp time, profiles/r2_kernels.md)
 __host__ __device__ __forceinline__ uint32_t base_code(uint32_t nib) {
     constexpr unsigned long long kTable = 0xF4FFFFFF2FF31F0Full;   // entry n = bits 4n .. 4n+3
-    static_assert(((kTable >> 4) & 0xF) == 0 && ((kTable >> 12) & 0xF) == 1 && ((kTable >> 28) & 0xF) == 2 && ((kTable >> 16) & 0xF) == 3 &&
-                  ((kTable >> 56) & 0xF) == 4 && (kTable & 0xF) == 0xF && ((kTable >> 8) & 0xF) == 0xF && ((kTable >> 60) & 0xF) == 0xF,
-                  "A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4");
+    // A(1)->0 C(3)->1 G(7)->2 T(4)->3 N(0xE)->4, every other nibble 0xF
+    static_assert(kTable == ((0xFull << 0) | (0x0ull << 4) | (0xFull << 8) | (0x1ull << 12) | (0x3ull << 16) | (0xFull << 20) | (0xFull << 24) |
+                             (0x2ull << 28) | (0xFull << 32) | (0xFull << 36) | (0xFull << 40) | (0xFull << 44) | (0xFull << 48) |
+                             (0xFull << 52) | (0x4ull << 56) | (0xFull << 60)), "nibble -> base code table");
     return (uint32_t)(kTable >> (4u * (nib & 0xFu))) & 0xFu;
 }
 
